@@ -1,0 +1,196 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.npz by executing the reference's own code
+(/root/reference/models.py, train_and_eval.py, utils.py) UNMODIFIED on CPU, with dgl/ogb/pytz
+provided by oracle/dgl_shim.py.  Run in the authoring container only (the reference is not present
+on the GPU box):
+
+    python oracle/make_golden.py
+
+Instrumentation is applied to torch only (torch.randperm and F.dropout are wrapped to RECORD the
+permutation / keep-mask the reference drew), never to reference code.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+import dgl_shim  # noqa: E402
+
+dgl_shim.install()
+sys.path.insert(0, "/root/reference")
+import models as ref_models  # noqa: E402
+import train_and_eval as ref_te  # noqa: E402
+import utils as ref_utils  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def rand_graph(rng, n, e, self_loops=False, isolated=0, dup=0):
+    src = rng.integers(0, n, e)
+    dst = np.floor(n * rng.random(e) ** 2).astype(np.int64)  # skewed in-degree, hubs at low ids
+    if dup:
+        src = np.concatenate([src, src[:dup]])
+        dst = np.concatenate([dst, dst[:dup]])  # exact duplicate edges (multigraph)
+    if isolated:
+        keep = dst < n - isolated  # last `isolated` nodes get in-degree 0
+        src, dst = src[keep], dst[keep]
+    if self_loops:
+        src = np.concatenate([src, np.arange(n)])
+        dst = np.concatenate([dst, np.arange(n)])
+    return src.astype(np.int64), dst.astype(np.int64)
+
+
+def randomise_bn(model, gen):
+    for m in model.modules():
+        if isinstance(m, torch.nn.BatchNorm1d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=gen))
+            m.running_var.copy_(torch.rand(m.num_features, generator=gen) * 1.5 + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=gen) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=gen))
+
+
+def sd_np(model, prefix="sd."):
+    return {prefix + k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def teacher_case(name, model_name, n, e, f, hidden, c, layers, norm, bs, seed, **gkw):
+    rng = np.random.default_rng(seed)
+    src, dst = rand_graph(rng, n, e, **gkw)
+    g = dgl_shim.graph((src, dst), num_nodes=n)
+    ref_utils.set_seed(seed)
+    conf = dict(model_name=model_name, num_layers=layers, feat_dim=f, hidden_dim=hidden, label_dim=c,
+                dropout_ratio=0.5, norm_type=norm, device="cpu")
+    model = ref_models.Model(conf)
+    gen = torch.Generator().manual_seed(seed + 1)
+    randomise_bn(model, gen)
+    if model_name == "GCN":  # DGL zero-inits the bias; make it count
+        for lyr in model.encoder.layers:
+            lyr.bias.data.copy_(torch.randn(lyr.bias.shape, generator=gen) * 0.1)
+    feats = torch.randn(n, f, generator=gen)
+    labels = torch.randint(0, c, (n,), generator=gen)
+    model.eval()
+    if model_name == "SAGE":
+        data = dgl_shim.NodeDataLoader(g, torch.arange(n), dgl_shim.MultiLayerFullNeighborSampler(1),
+                                       batch_size=bs, shuffle=False, drop_last=False)
+    else:
+        data = g
+    crit = torch.nn.NLLLoss()
+    evaluator = ref_utils.get_evaluator("cora")
+    idx_eval = torch.arange(0, n, 3)
+    out, loss, score = ref_te.evaluate(model, data, feats, labels, crit, evaluator, idx_eval)
+    with torch.no_grad():
+        logits = model.inference(data, feats)
+    np.savez_compressed(
+        os.path.join(OUT, f"teacher_{name}.npz"), src=src, dst=dst, n=n, feats=feats.numpy(),
+        labels=labels.numpy(), idx_eval=idx_eval.numpy(), logits=logits.numpy(), out=out.numpy(),
+        loss=loss, score=score, model_name=model_name, num_layers=layers, hidden=hidden,
+        norm=norm, batch_size=bs, **sd_np(model))
+    print(name, "logits", tuple(logits.shape), "loss", loss, "score", score)
+
+
+class Recorder:
+    """Wraps torch.randperm / F.dropout to record what the reference drew."""
+
+    def __init__(self):
+        self.perms, self.masks = [], []
+        self._rp, self._do = torch.randperm, F.dropout
+
+    def __enter__(self):
+        def randperm(*a, **k):
+            p = self._rp(*a, **k)
+            self.perms.append(p.clone())
+            return p
+
+        def dropout(x, p=0.5, training=True, inplace=False):
+            y = self._do(x, p, training, inplace)
+            if training and p > 0:
+                self.masks.append((y != 0).to(torch.uint8))
+            return y
+
+        torch.randperm = randperm
+        F.dropout = dropout
+        return self
+
+    def __exit__(self, *a):
+        torch.randperm, F.dropout = self._rp, self._do
+
+
+def student_case(name, model_name, n, f, hidden, c, layers, norm, dropout, bs, lr, wd, lamb, epochs,
+                 seed):
+    gen = torch.Generator().manual_seed(seed + 7)
+    feats = torch.randn(n, f, generator=gen)
+    labels = torch.randint(0, c, (n,), generator=gen)
+    out_t = torch.log_softmax(torch.randn(n, c, generator=gen) * 2.0, dim=1)
+    ref_utils.set_seed(seed)
+    conf = dict(model_name=model_name, num_layers=layers, feat_dim=f, hidden_dim=hidden, label_dim=c,
+                dropout_ratio=dropout, norm_type=norm, device="cpu")
+    model = ref_models.Model(conf)
+    init = sd_np(model, "init.")
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    crit_l = torch.nn.NLLLoss()
+    crit_t = torch.nn.KLDivLoss(reduction="batchmean", log_target=True)
+    evaluator = ref_utils.get_evaluator("cora")
+    n_l = n // 2  # hard-label set = first half; soft-label set = everything (train_student.py:297-299)
+    feats_l, labels_l = feats[:n_l], labels[:n_l]
+    losses = []
+    ref_utils.set_seed(seed)
+    with Recorder() as rec:
+        for _ in range(epochs):
+            ll = ref_te.train_mini_batch(model, feats_l, labels_l, bs, crit_l, opt, lamb)
+            lt = ref_te.train_mini_batch(model, feats, out_t, bs, crit_t, opt, 1 - lamb)
+            losses += [ll, lt]
+    out_all, loss_eval, score_eval = ref_te.evaluate_mini_batch(model, feats, labels, crit_l, bs,
+                                                                evaluator)
+    extra = {}
+    for i, p in enumerate(rec.perms):
+        extra[f"perm.{i}"] = p.numpy()
+    for i, m in enumerate(rec.masks):
+        extra[f"mask.{i}"] = np.packbits(m.numpy(), axis=None)
+        extra[f"maskshape.{i}"] = np.array(m.shape)
+    for k, prm in model.named_parameters():
+        st = opt.state[prm]
+        extra[f"adam.{k}.exp_avg"] = st["exp_avg"].numpy().copy()
+        extra[f"adam.{k}.exp_avg_sq"] = st["exp_avg_sq"].numpy().copy()
+        extra[f"adam.{k}.step"] = np.array(float(st["step"]))
+    np.savez_compressed(
+        os.path.join(OUT, f"student_{name}.npz"), feats=feats.numpy(), labels=labels.numpy(),
+        out_t=out_t.numpy(), n_l=n_l, model_name=model_name, num_layers=layers, hidden=hidden,
+        norm=norm, dropout=dropout, batch_size=bs, lr=lr, wd=wd, lamb=lamb, epochs=epochs,
+        losses=np.array(losses), out_all=out_all.numpy(), loss_eval=loss_eval, score_eval=score_eval,
+        **init, **sd_np(model, "final."), **extra)
+    print(name, "losses", [round(x, 5) for x in losses], "eval", loss_eval, score_eval,
+          "perms", len(rec.perms), "masks", len(rec.masks))
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(1)  # bit-stable fixtures
+    # teacher: SAGE.inference through the reference's own batched layer-wise loop
+    teacher_case("sage_bn3", "SAGE", n=300, e=2400, f=20, hidden=32, c=7, layers=3, norm="batch",
+                 bs=64, seed=0, isolated=5, dup=100)
+    teacher_case("sage_none2", "SAGE", n=157, e=900, f=13, hidden=16, c=5, layers=2, norm="none",
+                 bs=50, seed=1, self_loops=True, dup=30)
+    teacher_case("sage_wide", "SAGE", n=211, e=3000, f=100, hidden=256, c=47, layers=3, norm="batch",
+                 bs=4096, seed=2, isolated=3)
+    # teacher: GCN.forward (needs in-degree >= 1 everywhere -> self loops)
+    teacher_case("gcn_cora_like", "GCN", n=200, e=800, f=50, hidden=16, c=7, layers=2, norm="none",
+                 bs=0, seed=3, self_loops=True)
+    teacher_case("gcn_agg_first", "GCN", n=120, e=500, f=8, hidden=24, c=3, layers=3, norm="batch",
+                 bs=0, seed=4, self_loops=True, dup=20)
+    # student: reference train_mini_batch / evaluate_mini_batch with autograd + torch.optim.Adam
+    student_case("mlp_bn3", "MLP", n=500, f=20, hidden=32, c=7, layers=3, norm="batch", dropout=0.0,
+                 bs=64, lr=0.01, wd=0.0, lamb=0.3, epochs=2, seed=0)
+    student_case("mlp_lamb0", "MLP", n=300, f=12, hidden=24, c=5, layers=3, norm="batch",
+                 dropout=0.0, bs=32, lr=0.01, wd=0.0005, lamb=0.0, epochs=2, seed=1)
+    student_case("mlp_none2_wd", "MLP", n=260, f=9, hidden=17, c=4, layers=2, norm="none",
+                 dropout=0.0, bs=40, lr=0.005, wd=0.001, lamb=0.5, epochs=2, seed=2)
+    student_case("mlp_dropout", "MLP3w4", n=400, f=16, hidden=48, c=6, layers=3, norm="batch",
+                 dropout=0.5, bs=64, lr=0.01, wd=0.0, lamb=0.4, epochs=1, seed=3)
+    student_case("mlp_small_n", "MLP", n=50, f=10, hidden=16, c=3, layers=3, norm="batch",
+                 dropout=0.0, bs=512, lr=0.01, wd=0.0, lamb=1.0, epochs=2, seed=4)
+    student_case("mlp_1layer", "MLP", n=200, f=10, hidden=16, c=4, layers=1, norm="batch",
+                 dropout=0.0, bs=32, lr=0.01, wd=0.0, lamb=0.5, epochs=1, seed=5)

@@ -1,0 +1,63 @@
+"""Shared helpers for the parity tests: load tests/golden/*.npz into the oracle's containers."""
+import os
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+TEACHER_CASES = ["sage_bn3", "sage_none2", "sage_wide", "gcn_cora_like", "gcn_agg_first"]
+STUDENT_CASES = ["mlp_bn3", "mlp_lamb0", "mlp_none2_wd", "mlp_dropout", "mlp_small_n", "mlp_1layer"]
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"), allow_pickle=False)
+    return {k: z[k] for k in z.files}
+
+
+def sub(d, prefix, dtype=None):
+    """{'encoder.x': tensor} for every key starting with `prefix`, prefix and 'encoder.' stripped."""
+    out = {}
+    for k, v in d.items():
+        if k.startswith(prefix):
+            kk = k[len(prefix):]
+            if kk.startswith("encoder."):
+                kk = kk[len("encoder."):]
+            t = torch.from_numpy(np.array(v))
+            if dtype is not None and t.is_floating_point():
+                t = t.to(dtype)
+            out[kk] = t.clone()
+    return out
+
+
+def teacher_params(d, dtype=torch.float32):
+    sd = sub(d, "sd.", dtype)
+    L = int(d["num_layers"])
+    sage = str(d["model_name"]) == "SAGE"
+    layers, norms = [], []
+    for l in range(L):
+        if sage:
+            layers.append((sd[f"layers.{l}.fc_neigh.weight"], sd[f"layers.{l}.fc_neigh.bias"]))
+        else:
+            layers.append((sd[f"layers.{l}.weight"], sd[f"layers.{l}.bias"]))
+        if str(d["norm"]) == "batch" and l != L - 1:
+            norms.append((sd[f"norms.{l}.weight"], sd[f"norms.{l}.bias"],
+                          sd[f"norms.{l}.running_mean"], sd[f"norms.{l}.running_var"]))
+    return layers, norms
+
+
+def student_masks(d, idx_perm_count, num_layers):
+    """Recorded keep-masks, regrouped as masks[pass][step][layer]."""
+    n_masks = sum(1 for k in d if k.startswith("maskshape."))
+    flat = []
+    for i in range(n_masks):
+        shape = tuple(int(x) for x in d[f"maskshape.{i}"])
+        bits = np.unpackbits(d[f"mask.{i}"])[: shape[0] * shape[1]].reshape(shape)
+        flat.append(torch.from_numpy(bits.astype(np.uint8)))
+    return flat
+
+
+def relerr(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
