@@ -1,0 +1,29 @@
+// Argument block shared by the SIMT and tcgen05 projection kernels.
+#pragma once
+#include "common.cuh"
+
+namespace glnn {
+
+struct GemmArgs {
+  const float* A;
+  int64_t lda;
+  int transA;
+  const float* B;
+  int64_t ldb;
+  int transB;
+  float* C;
+  int64_t ldc;
+  int64_t M, N, K;
+  const float* row_scale;
+  const float* bias;
+  const float* col_scale;
+  const float* col_shift;
+  int relu;
+  int vecA, vecB, vecC;
+  int k_per_split;  // multiple of BK
+};
+
+int gemm_simt(GemmArgs g, cudaStream_t st);                    // gemm_simt.cu
+int gemm_tc(const GemmArgs& g, cudaStream_t st, bool* taken);  // gemm_tc.cu
+
+}  // namespace glnn

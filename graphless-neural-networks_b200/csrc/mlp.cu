@@ -1,0 +1,733 @@
+// Student path (B): one pass of train_mini_batch (train_and_eval.py:59-86) and the eval forward of
+// evaluate_mini_batch (:108-136) for models.MLP, with no autograd anywhere.
+//
+// A step is a fixed kernel sequence
+//   gather -> [GEMM(+bias) -> BN batch stats -> BN apply + ReLU + dropout] x (L-1) -> GEMM(+bias)
+//   -> log-softmax + NLL|KL loss + d(lamb*loss)/dlogits (+ last-layer bias grad)
+//   -> [dW GEMM, dX GEMM, BN backward (2 kernels, also yields dgamma/dbeta/dbias)] x (L-1) -> dW_0
+//   -> flat Adam -> advance
+// over fixed workspace addresses; everything that changes from step to step (batch offset, Adam
+// step number, dropout stream) is derived on the device from a step counter, and everything that
+// changes from pass to pass (input matrix, targets, lamb, learning rate) lives in a small device
+// struct.  The sequence is therefore captured ONCE into a CUDA graph and replayed nb times per
+// pass with a single host read of the loss at the end of the pass (the reference syncs per step).
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace glnn {
+
+struct PassParams {       // device-resident, rewritten once per pass
+  const float* X;
+  int64_t ldx;
+  const void* target;
+  const int64_t* perm;
+  const uint8_t* masks;
+  float* loss_sum;
+  int64_t step0;
+  uint64_t seed;
+  int32_t kind;
+  float lamb;
+  float lr, beta1, beta2, eps, wd;
+};
+
+struct Dims {
+  int L, F, H, C, norm;
+  float p_drop, bn_eps, bn_mom;
+  int64_t R;  // batch rows
+};
+
+__host__ __device__ __forceinline__ int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }
+__host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+static inline int64_t up(int64_t x, int64_t a = 64) { return (x + a - 1) / a * a; }
+static inline int in_dim(const Dims& d, int l) { return l == 0 ? d.F : d.H; }
+static inline int out_dim(const Dims& d, int l) { return l == d.L - 1 ? d.C : d.H; }
+
+// flat parameter layout: [W_0 | b_0 | W_1 | b_1 | ... | gamma_0 | beta_0 | ...]
+struct ParamLayout {
+  int64_t w[16], b[16], gamma[16], beta[16], total;
+};
+static ParamLayout param_layout(const Dims& d) {
+  ParamLayout p{};
+  int64_t o = 0;
+  for (int l = 0; l < d.L; ++l) {
+    p.w[l] = o; o += static_cast<int64_t>(in_dim(d, l)) * out_dim(d, l);
+    p.b[l] = o; o += out_dim(d, l);
+  }
+  if (d.norm == 1)
+    for (int l = 0; l < d.L - 1; ++l) {
+      p.gamma[l] = o; o += d.H;
+      p.beta[l] = o; o += d.H;
+    }
+  p.total = o;
+  return p;
+}
+
+// workspace carve-up (floats unless noted)
+struct WsLayout {
+  int64_t pp, ctr, xb, tgt, z[16], a[16], mean[16], invstd[16], logits, dlogits, dh[2], part, perm,
+      fold, total_bytes;
+  int rs;  // row splits of the column reductions
+};
+static int row_splits(const Dims& d) {
+  const int col_tiles = std::max(1, (d.H + 31) / 32);
+  int rs = (4 * 148 + col_tiles - 1) / col_tiles;
+  rs = static_cast<int>(std::min<int64_t>(rs, std::max<int64_t>(1, d.R / 32)));
+  return std::max(1, std::min(rs, 64));
+}
+constexpr int64_t kPermCap = 1LL << 22;  // rows of one train_pass call (the host splits longer passes)
+
+static WsLayout ws_layout(const Dims& d, bool train) {
+  WsLayout w{};
+  int64_t o = 0;
+  auto take = [&](int64_t floats) { int64_t r = o; o += up(floats); return r; };
+  w.pp = take((sizeof(PassParams) + 3) / 4);
+  w.ctr = take(4);
+  w.xb = take(d.R * d.F);
+  w.tgt = take(std::max<int64_t>(d.R * d.C, 2 * d.R));
+  for (int l = 0; l < d.L - 1; ++l) {
+    w.z[l] = take(d.R * d.H);
+    w.a[l] = take(d.R * d.H);
+    w.mean[l] = take(d.H);
+    w.invstd[l] = take(d.H);
+  }
+  w.logits = take(d.R * d.C);
+  w.dlogits = take(d.R * d.C);
+  w.dh[0] = take(d.R * d.H);
+  w.dh[1] = take(d.R * d.H);
+  w.rs = row_splits(d);
+  w.part = take(static_cast<int64_t>(w.rs) * 2 * d.H);
+  w.fold = take(2LL * d.H * std::max(1, d.L - 1));
+  w.perm = take(train ? 2 * kPermCap : 0);  // int64 copy of the pass permutation
+  w.total_bytes = o * 4;
+  return w;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float keep_scale(const PassParams* pp, int step, int layer, int nlay,
+                                            int64_t R, int H, int64_t r, int c, float p_drop) {
+  if (p_drop <= 0.f) return 1.f;
+  bool keep;
+  if (pp->masks) {
+    keep = pp->masks[((static_cast<int64_t>(step) * nlay + layer) * R + r) * H + c] != 0;
+  } else {  // counter-based stream: splitmix64 of (seed, step, layer, element)
+    uint64_t x = pp->seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(pp->step0 + step) + 1) +
+                 0xD1B54A32D192ED03ull * (static_cast<uint64_t>(layer) + 1) +
+                 static_cast<uint64_t>(r) * H + c;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    keep = (static_cast<float>(x >> 40) * (1.0f / 16777216.0f)) >= p_drop;
+  }
+  return keep ? 1.f / (1.f - p_drop) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const PassParams* __restrict__ pp,
+                                                     const int* __restrict__ ctr, int64_t R, int F,
+                                                     int C, float* __restrict__ xb,
+                                                     float* __restrict__ tgt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= R) return;
+  const int64_t src = pp->perm[static_cast<int64_t>(*ctr) * R + r];
+  const float* x = pp->X + src * pp->ldx;
+  float* o = xb + r * F;
+  if ((F & 3) == 0 && (pp->ldx & 3) == 0 && ((reinterpret_cast<uintptr_t>(pp->X) & 15) == 0)) {
+    for (int j = lane * 4; j < F; j += 128) *reinterpret_cast<float4*>(o + j) = ldg4(x + j);
+  } else {
+    for (int j = lane; j < F; j += 32) o[j] = __ldg(x + j);
+  }
+  if (pp->kind == 0) {
+    if (lane == 0) reinterpret_cast<int64_t*>(tgt)[r] = static_cast<const int64_t*>(pp->target)[src];
+  } else {
+    const float* t = static_cast<const float*>(pp->target) + src * C;
+    for (int j = lane; j < C; j += 32) tgt[r * C + j] = __ldg(t + j);
+  }
+}
+
+// Column statistics of Z[R,H] over a row split: chunk mean and chunk M2 (two passes over the chunk,
+// which sits in L1/L2), combined later with Chan's formula.  block (32, 8).
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ Z, int64_t R, int H,
+                                                       int rs, float* __restrict__ part) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  const int64_t rows = (R + rs - 1) / rs;
+  const int64_t r0 = blockIdx.y * rows, r1 = min(R, r0 + rows);
+  const float cnt = static_cast<float>(imax64(r1 - r0, 1));
+  float s = 0.f;
+  if (c < H)
+    for (int64_t r = r0 + ty; r < r1; r += 8) s += Z[r * H + c];
+  sm[ty][tx] = s;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += sm[i][tx];
+  const float mu = tot / cnt;
+  __syncthreads();
+  float q = 0.f;
+  if (c < H)
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float dz = Z[r * H + c] - mu;
+      q = fmaf(dz, dz, q);
+    }
+  sm[ty][tx] = q;
+  __syncthreads();
+  if (ty == 0 && c < H) {
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m2 += sm[i][tx];
+    part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c] = mu;
+    part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c] = m2;
+  }
+}
+
+// Combines the split statistics, normalises, applies gamma/beta, ReLU and dropout; the first row
+// tile also stores mean / invstd for the backward pass and updates the running statistics
+// (momentum update with the UNBIASED variance, as nn.BatchNorm1d does).  norm == 0: y = z.
+__global__ void __launch_bounds__(256) bn_apply_kernel(
+    const float* __restrict__ Z, float* __restrict__ A, int64_t R, int H, int rs,
+    const float* __restrict__ part, const float* __restrict__ gamma, const float* __restrict__ beta,
+    float* __restrict__ run_mean, float* __restrict__ run_var, float* __restrict__ save_mean,
+    float* __restrict__ save_invstd, int norm, float eps, float mom, float p_drop,
+    const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
+    int rows_per_block) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  if (c >= H) return;
+  float mu = 0.f, inv = 1.f, g = 1.f, b = 0.f;
+  if (norm) {
+    const int64_t rows = (R + rs - 1) / rs;
+    float n = 0.f, m2 = 0.f;
+    for (int s = 0; s < rs; ++s) {
+      const float nb = static_cast<float>(imax64(imin64(R, (s + 1) * rows) - s * rows, 0));
+      if (nb <= 0.f) continue;
+      const float mb = part[(static_cast<int64_t>(s) * 2 + 0) * H + c];
+      const float qb = part[(static_cast<int64_t>(s) * 2 + 1) * H + c];
+      const float delta = mb - mu, tot = n + nb;
+      mu += delta * (nb / tot);
+      m2 += qb + delta * delta * (n * nb / tot);
+      n = tot;
+    }
+    const float var = m2 / static_cast<float>(R);
+    inv = 1.f / sqrtf(var + eps);
+    g = gamma[c];
+    b = beta[c];
+    if (blockIdx.y == 0 && ty == 0) {
+      save_mean[c] = mu;
+      save_invstd[c] = inv;
+      const float unb = m2 / static_cast<float>(imax64(R - 1, 1));
+      run_mean[c] = (1.f - mom) * run_mean[c] + mom * mu;
+      run_var[c] = (1.f - mom) * run_var[c] + mom * unb;
+    }
+  }
+  const int step = *ctr;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = min(R, r0 + rows_per_block);
+  for (int64_t r = r0 + ty; r < r1; r += 8) {
+    const float z = Z[r * H + c];
+    float y = norm ? (z - mu) * inv * g + b : z;
+    y = fmaxf(y, 0.f);
+    A[r * H + c] = y * keep_scale(pp, step, layer, nlay, R, H, r, c, p_drop);
+  }
+}
+
+// Backward through dropout, ReLU and BatchNorm.  Pass 1: per split  S1 = sum g, S2 = sum g*xhat with
+// g = dA * keep/(1-p) * [y > 0].
+__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
+    const float* __restrict__ dA, const float* __restrict__ Z, int64_t R, int H, int rs,
+    const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ save_mean, const float* __restrict__ save_invstd, int norm, float p_drop,
+    const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
+    float* __restrict__ part) {
+  __shared__ float s1[8][33], s2[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  const int64_t rows = (R + rs - 1) / rs;
+  const int64_t r0 = blockIdx.y * rows, r1 = min(R, r0 + rows);
+  float a1 = 0.f, a2 = 0.f;
+  if (c < H) {
+    const float mu = norm ? save_mean[c] : 0.f, inv = norm ? save_invstd[c] : 1.f;
+    const float g = norm ? gamma[c] : 1.f, b = norm ? beta[c] : 0.f;
+    const int step = *ctr;
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float xh = (Z[r * H + c] - mu) * inv;
+      const float y = norm ? xh * g + b : Z[r * H + c];
+      float gr = dA[r * H + c] * keep_scale(pp, step, layer, nlay, R, H, r, c, p_drop);
+      gr = y > 0.f ? gr : 0.f;
+      a1 += gr;
+      a2 = fmaf(gr, xh, a2);
+    }
+  }
+  s1[ty][tx] = a1;
+  s2[ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < H) {
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { t1 += s1[i][tx]; t2 += s2[i][tx]; }
+    part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c] = t1;
+    part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c] = t2;
+  }
+}
+
+// Pass 2: dZ = gamma*invstd/R * (R*g - S1 - xhat*S2) written in place over dA; dgamma = S2,
+// dbeta = S1; the Linear bias gradient is the column sum of dZ (mathematically 0 in front of a
+// BatchNorm; the reference computes it the same way and Adam still sees its rounding noise).
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+    float* __restrict__ dA, const float* __restrict__ Z, int64_t R, int H, int rs,
+    const float* __restrict__ part, const float* __restrict__ gamma, const float* __restrict__ beta,
+    const float* __restrict__ save_mean, const float* __restrict__ save_invstd, int norm, float p_drop,
+    const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
+    int rows_per_block) {
+  __shared__ float sb[8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * 32 + tx;
+  float colsum = 0.f;
+  if (c < H) {
+    float S1 = 0.f, S2 = 0.f, mu = 0.f, inv = 1.f, g = 1.f, b = 0.f;
+    if (norm) {
+      for (int s = 0; s < rs; ++s) {
+        S1 += part[(static_cast<int64_t>(s) * 2 + 0) * H + c];
+        S2 += part[(static_cast<int64_t>(s) * 2 + 1) * H + c];
+      }
+      mu = save_mean[c]; inv = save_invstd[c]; g = gamma[c]; b = beta[c];
+      if (blockIdx.y == 0 && ty == 0) { dgamma[c] = S2; dbeta[c] = S1; }
+    }
+    const float fR = static_cast<float>(R);
+    const float k = g * inv / fR;
+    const int step = *ctr;
+    const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+    const int64_t r1 = min(R, r0 + rows_per_block);
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const float z = Z[r * H + c];
+      const float xh = (z - mu) * inv;
+      const float y = norm ? xh * g + b : z;
+      float gr = dA[r * H + c] * keep_scale(pp, step, layer, nlay, R, H, r, c, p_drop);
+      gr = y > 0.f ? gr : 0.f;
+      const float dz = norm ? k * (fR * gr - S1 - xh * S2) : gr;
+      dA[r * H + c] = dz;
+      colsum += dz;
+    }
+  }
+  sb[ty][tx] = colsum;
+  __syncthreads();
+  if (ty == 0 && c < H) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sb[i][tx];
+    atomicAdd(dbias + c, t);
+  }
+}
+
+// log-softmax + loss + gradient of lamb*loss w.r.t. the logits; one warp per row.  Also accumulates
+// the last layer's bias gradient (column sums of dlogits).
+__global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ logits,
+                                                   const float* __restrict__ tgt, int64_t R, int C,
+                                                   const PassParams* __restrict__ pp,
+                                                   float* __restrict__ dlogits,
+                                                   float* __restrict__ dbias) {
+  extern __shared__ float s_col[];  // [C] column sums + [8] row losses
+  float* s_loss = s_col + C;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int j = threadIdx.x; j < C; j += blockDim.x) s_col[j] = 0.f;
+  __syncthreads();
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + warp;
+  float loss = 0.f;
+  if (r < R) {
+    const float* x = logits + r * C;
+    float m = -INFINITY;
+    for (int j = lane; j < C; j += 32) m = fmaxf(m, x[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float se = 0.f;
+    for (int j = lane; j < C; j += 32) se += expf(x[j] - m);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+    const float lse = m + logf(se);
+    const float sc = pp->lamb / static_cast<float>(R);
+    if (pp->kind == 0) {
+      const int y = static_cast<int>(reinterpret_cast<const int64_t*>(tgt)[r]);
+      for (int j = lane; j < C; j += 32) {
+        const float s = x[j] - lse;
+        const float d = (expf(s) - (j == y ? 1.f : 0.f)) * sc;
+        dlogits[r * C + j] = d;
+        atomicAdd(&s_col[j], d);
+        if (j == y) loss = -s;
+      }
+    } else {
+      const float* t = tgt + r * C;
+      float st = 0.f;
+      for (int j = lane; j < C; j += 32) st += expf(t[j]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) st += __shfl_xor_sync(0xffffffffu, st, o);
+      for (int j = lane; j < C; j += 32) {
+        const float s = x[j] - lse, tj = t[j], et = expf(tj);
+        const float d = (expf(s) * st - et) * sc;
+        dlogits[r * C + j] = d;
+        atomicAdd(&s_col[j], d);
+        loss = fmaf(et, tj - s, loss);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  }
+  if (lane == 0) s_loss[warp] = loss;
+  __syncthreads();
+  for (int j = threadIdx.x; j < C; j += blockDim.x) atomicAdd(dbias + j, s_col[j]);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += s_loss[w];
+    atomicAdd(pp->loss_sum, t / static_cast<float>(R));
+  }
+}
+
+// torch.optim.Adam (amsgrad=False, L2 weight decay) over the flat parameter buffer.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v,
+                                                   int64_t n, const PassParams* __restrict__ pp,
+                                                   const int* __restrict__ ctr) {
+  __shared__ float s_step, s_bc2;
+  if (threadIdx.x == 0) {
+    const double t = static_cast<double>(pp->step0 + *ctr + 1);
+    const double bc1 = 1.0 - pow(static_cast<double>(pp->beta1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(pp->beta2), t);
+    s_step = static_cast<float>(static_cast<double>(pp->lr) / bc1);
+    s_bc2 = static_cast<float>(sqrt(bc2));
+  }
+  __syncthreads();
+  const float b1 = pp->beta1, b2 = pp->beta2, eps = pp->eps, wd = pp->wd;
+  const float step_size = s_step, bc2s = s_bc2;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float gi = g[i];
+    const float pi = p[i];
+    if (wd != 0.f) gi = fmaf(wd, pi, gi);
+    const float mi = m[i] * b1 + gi * (1.f - b1);
+    const float vi = v[i] * b2 + gi * gi * (1.f - b2);
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2s + eps;
+    p[i] = pi - step_size * (mi / denom);
+  }
+}
+
+__global__ void advance_kernel(int* ctr, int64_t* nbt, int n_norm) {
+  if (threadIdx.x == 0) *ctr += 1;
+  if (nbt && threadIdx.x < n_norm) nbt[threadIdx.x] += 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static int gemm_run(const float* A, int64_t lda, int tA, const float* B, int64_t ldb, int tB, float* C,
+                    int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
+                    const float* col_scale, const float* col_shift, int relu, cudaStream_t st) {
+  return glnn_gemm_f32(A, lda, tA, B, ldb, tB, C, ldc, M, N, K, nullptr, bias, col_scale, col_shift,
+                       relu, 0, st);
+}
+
+struct StepCtx {
+  Dims d;
+  ParamLayout pl;
+  WsLayout wl;
+  float *params, *grads, *m, *v, *bn_stats;
+  int64_t* nbt;
+  float* ws;
+};
+
+static int enqueue_step(const StepCtx& c, cudaStream_t st) {
+  const Dims& d = c.d;
+  const int64_t R = d.R;
+  const PassParams* pp = reinterpret_cast<const PassParams*>(c.ws + c.wl.pp);
+  int* ctr = reinterpret_cast<int*>(c.ws + c.wl.ctr);
+  float* xb = c.ws + c.wl.xb;
+  float* tgt = c.ws + c.wl.tgt;
+  float* part = c.ws + c.wl.part;
+  const int rs = c.wl.rs;
+  const int nlay = d.L - 1;
+  const dim3 blk(32, 8);
+  const int col_tiles = (d.H + 31) / 32;
+  const int rows_per_block = static_cast<int>(std::max<int64_t>(32, (R + rs - 1) / rs));
+  const int row_tiles = static_cast<int>((R + rows_per_block - 1) / rows_per_block);
+  int rc;
+
+  gather_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, st>>>(pp, ctr, R, d.F, d.C, xb, tgt);
+  GLNN_LAUNCH_OK("gather_kernel");
+
+  // forward
+  const float* h = xb;
+  for (int l = 0; l < d.L; ++l) {
+    const int din = in_dim(d, l), dout = out_dim(d, l);
+    float* z = (l == d.L - 1) ? c.ws + c.wl.logits : c.ws + c.wl.z[l];
+    rc = gemm_run(h, din, 0, c.params + c.pl.w[l], din, 1, z, dout, R, dout, din,
+                  c.params + c.pl.b[l], nullptr, nullptr, 0, st);
+    if (rc != 0) return rc;
+    if (l == d.L - 1) break;
+    if (d.norm) {
+      bn_stats_kernel<<<dim3(col_tiles, rs), blk, 0, st>>>(z, R, d.H, rs, part);
+      GLNN_LAUNCH_OK("bn_stats_kernel");
+    }
+    bn_apply_kernel<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
+        z, c.ws + c.wl.a[l], R, d.H, rs, part, d.norm ? c.params + c.pl.gamma[l] : nullptr,
+        d.norm ? c.params + c.pl.beta[l] : nullptr, d.norm ? c.bn_stats + 2LL * l * d.H : nullptr,
+        d.norm ? c.bn_stats + (2LL * l + 1) * d.H : nullptr, c.ws + c.wl.mean[l],
+        c.ws + c.wl.invstd[l], d.norm, d.bn_eps, d.bn_mom, d.p_drop, pp, ctr, l, nlay,
+        rows_per_block);
+    GLNN_LAUNCH_OK("bn_apply_kernel");
+    h = c.ws + c.wl.a[l];
+  }
+
+  // loss + dlogits (+ last bias grad)
+  float* dlog = c.ws + c.wl.dlogits;
+  GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[d.L - 1], 0, sizeof(float) * d.C, st));
+  loss_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, sizeof(float) * (d.C + 8), st>>>(
+      c.ws + c.wl.logits, tgt, R, d.C, pp, dlog, c.grads + c.pl.b[d.L - 1]);
+  GLNN_LAUNCH_OK("loss_kernel");
+
+  // backward
+  const float* dz = dlog;  // gradient w.r.t. the output of layer l's Linear
+  for (int l = d.L - 1; l >= 0; --l) {
+    const int din = in_dim(d, l), dout = out_dim(d, l);
+    const float* hin = (l == 0) ? xb : c.ws + c.wl.a[l - 1];
+    // dW_l [dout, din] = dz^T [dout, R] * hin [R, din]
+    rc = gemm_run(dz, dout, 1, hin, din, 0, c.grads + c.pl.w[l], din, dout, din, R, nullptr, nullptr,
+                  nullptr, 0, st);
+    if (rc != 0) return rc;
+    if (l == 0) break;
+    // dA_{l-1} [R, din] = dz [R, dout] * W_l [dout, din]
+    float* da = c.ws + c.wl.dh[l & 1];
+    rc = gemm_run(dz, dout, 0, c.params + c.pl.w[l], din, 0, da, din, R, din, dout, nullptr, nullptr,
+                  nullptr, 0, st);
+    if (rc != 0) return rc;
+    const int k = l - 1;  // hidden layer whose activation we go back through
+    const float* gam = d.norm ? c.params + c.pl.gamma[k] : nullptr;
+    const float* bet = d.norm ? c.params + c.pl.beta[k] : nullptr;
+    if (d.norm) {
+      bn_bwd_stats_kernel<<<dim3(col_tiles, rs), blk, 0, st>>>(
+          da, c.ws + c.wl.z[k], R, d.H, rs, gam, bet, c.ws + c.wl.mean[k], c.ws + c.wl.invstd[k],
+          d.norm, d.p_drop, pp, ctr, k, nlay, part);
+      GLNN_LAUNCH_OK("bn_bwd_stats_kernel");
+    }
+    GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[k], 0, sizeof(float) * d.H, st));
+    bn_bwd_apply_kernel<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
+        da, c.ws + c.wl.z[k], R, d.H, rs, part, gam, bet, c.ws + c.wl.mean[k], c.ws + c.wl.invstd[k],
+        d.norm, d.p_drop, pp, ctr, k, nlay, d.norm ? c.grads + c.pl.gamma[k] : nullptr,
+        d.norm ? c.grads + c.pl.beta[k] : nullptr, c.grads + c.pl.b[k], rows_per_block);
+    GLNN_LAUNCH_OK("bn_bwd_apply_kernel");
+    dz = da;
+  }
+
+  const int64_t P = c.pl.total;
+  const unsigned ablocks = static_cast<unsigned>(std::min<int64_t>((P + 255) / 256, 8LL * sm_count()));
+  adam_kernel<<<ablocks, 256, 0, st>>>(c.params, c.grads, c.m, c.v, P, pp, ctr);
+  GLNN_LAUNCH_OK("adam_kernel");
+  advance_kernel<<<1, 32, 0, st>>>(ctr, d.norm ? c.nbt : nullptr, d.norm ? d.L - 1 : 0);
+  GLNN_LAUNCH_OK("advance_kernel");
+  return 0;
+}
+
+// graph cache: one executable graph per distinct (shape, buffer set)
+struct GraphKey {
+  Dims d;
+  const void *params, *grads, *m, *v, *bn, *nbt, *ws;
+  bool operator<(const GraphKey& o) const {
+    return memcmp(this, &o, sizeof(GraphKey)) < 0;
+  }
+};
+static std::mutex g_mu;
+static std::map<GraphKey, cudaGraphExec_t> g_graphs;
+static cudaStream_t g_cap_stream = nullptr;
+
+static int get_graph(const StepCtx& c, cudaGraphExec_t* out) {
+  GraphKey k;
+  memset(&k, 0, sizeof(k));
+  k.d = c.d; k.params = c.params; k.grads = c.grads; k.m = c.m; k.v = c.v; k.bn = c.bn_stats;
+  k.nbt = c.nbt; k.ws = c.ws;
+  std::lock_guard<std::mutex> lock(g_mu);
+  auto it = g_graphs.find(k);
+  if (it != g_graphs.end()) { *out = it->second; return 0; }
+  if (!g_cap_stream) GLNN_CUDA_OK(cudaStreamCreateWithFlags(&g_cap_stream, cudaStreamNonBlocking));
+  if (g_graphs.size() >= 64) {  // bounded cache
+    for (auto& kv : g_graphs) cudaGraphExecDestroy(kv.second);
+    g_graphs.clear();
+  }
+  GLNN_CUDA_OK(cudaStreamBeginCapture(g_cap_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_step(c, g_cap_stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(g_cap_stream, &graph);
+  if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return (int)e; }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { set_error("graph instantiate failed: %s", cudaGetErrorString(e)); return (int)e; }
+  g_graphs[k] = exec;
+  *out = exec;
+  return 0;
+}
+
+static int make_dims(const glnn_mlp_desc* desc, int64_t rows, Dims* d) {
+  GLNN_REQUIRE(desc, GLNN_ERR_ARG, "mlp: null desc");
+  GLNN_REQUIRE(desc->num_layers >= 1 && desc->num_layers <= 16, GLNN_ERR_SHAPE,
+               "mlp: num_layers must be in [1,16]");
+  GLNN_REQUIRE(desc->feat_dim > 0 && desc->label_dim > 0 && (desc->num_layers == 1 || desc->hidden_dim > 0),
+               GLNN_ERR_SHAPE, "mlp: non-positive dimension");
+  GLNN_REQUIRE(desc->norm == 0 || desc->norm == 1, GLNN_ERR_ARG, "mlp: norm must be 0 or 1");
+  GLNN_REQUIRE(desc->dropout >= 0.f && desc->dropout < 1.f, GLNN_ERR_ARG, "mlp: dropout in [0,1)");
+  memset(d, 0, sizeof(Dims));
+  d->L = desc->num_layers; d->F = desc->feat_dim; d->H = desc->num_layers == 1 ? 1 : desc->hidden_dim;
+  d->C = desc->label_dim; d->norm = desc->num_layers == 1 ? 0 : desc->norm;
+  d->p_drop = desc->dropout; d->bn_eps = desc->bn_eps; d->bn_mom = desc->bn_momentum; d->R = rows;
+  return 0;
+}
+
+}  // namespace glnn
+
+extern "C" int64_t glnn_mlp_param_count(const glnn_mlp_desc* desc) {
+  glnn::Dims d;
+  if (glnn::make_dims(desc, 1, &d) != 0) return -1;
+  return glnn::param_layout(d).total;
+}
+
+extern "C" int64_t glnn_mlp_bn_stat_count(const glnn_mlp_desc* desc) {
+  glnn::Dims d;
+  if (glnn::make_dims(desc, 1, &d) != 0) return -1;
+  return d.norm ? 2LL * d.H * (d.L - 1) : 0;
+}
+
+extern "C" int64_t glnn_mlp_workspace_bytes(const glnn_mlp_desc* desc, int64_t rows) {
+  glnn::Dims d;
+  if (rows < 1 || glnn::make_dims(desc, rows, &d) != 0) return -1;
+  return glnn::ws_layout(d, true).total_bytes;
+}
+
+extern "C" int glnn_mlp_train_pass(const glnn_mlp_desc* desc, float* params, float* grads,
+                                   float* exp_avg, float* exp_avg_sq, float* bn_stats,
+                                   int64_t* num_batches_tracked, int64_t adam_step0,
+                                   const glnn_adam_hparams* hp, const float* X, int64_t ldx,
+                                   const void* target, int target_kind, const int64_t* perm,
+                                   int64_t nb, int64_t bs, const uint8_t* drop_masks, uint64_t seed,
+                                   float lamb, float* loss_sum, void* workspace,
+                                   int64_t workspace_bytes, glnn_stream_t stream) {
+  using namespace glnn;
+  Dims d;
+  GLNN_REQUIRE(bs >= 1 && nb >= 0, GLNN_ERR_ARG, "mlp_train_pass: bad batch geometry");
+  int rc = make_dims(desc, bs, &d);
+  if (rc != 0) return rc;
+  if (nb == 0) return 0;
+  GLNN_REQUIRE(params && grads && exp_avg && exp_avg_sq && hp && X && target && perm && loss_sum &&
+                   workspace, GLNN_ERR_ARG, "mlp_train_pass: null pointer");
+  GLNN_REQUIRE(!d.norm || bn_stats, GLNN_ERR_ARG, "mlp_train_pass: bn_stats required with norm=1");
+  GLNN_REQUIRE(!d.norm || bs >= 2, GLNN_ERR_SHAPE,
+               "mlp_train_pass: BatchNorm needs more than 1 row per batch (torch raises too)");
+  GLNN_REQUIRE(target_kind == 0 || target_kind == 1, GLNN_ERR_ARG, "mlp_train_pass: target_kind");
+  GLNN_REQUIRE(ldx >= d.F, GLNN_ERR_SHAPE, "mlp_train_pass: ldx < feat_dim");
+  GLNN_REQUIRE(nb * bs <= kPermCap, GLNN_ERR_SHAPE,
+               "mlp_train_pass: at most %lld rows per call (split the pass)", (long long)kPermCap);
+  (void)sm_count();  // resolve device attributes before any stream capture
+  GLNN_REQUIRE(aligned16(workspace), GLNN_ERR_ALIGN, "mlp_train_pass: workspace alignment");
+  StepCtx c;
+  c.d = d;
+  c.pl = param_layout(d);
+  c.wl = ws_layout(d, true);
+  GLNN_REQUIRE(workspace_bytes >= c.wl.total_bytes, GLNN_ERR_WORKSPACE,
+               "mlp_train_pass: workspace %lld < %lld bytes", (long long)workspace_bytes,
+               (long long)c.wl.total_bytes);
+  c.params = params; c.grads = grads; c.m = exp_avg; c.v = exp_avg_sq; c.bn_stats = bn_stats;
+  c.nbt = num_batches_tracked; c.ws = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  // per-pass state: permutation copy, pass parameters, step counter
+  int64_t* perm_dev = reinterpret_cast<int64_t*>(c.ws + c.wl.perm);
+  cudaPointerAttributes attr;
+  cudaMemcpyKind kind = cudaMemcpyDefault;
+  if (cudaPointerGetAttributes(&attr, perm) != cudaSuccess) cudaGetLastError();
+  GLNN_CUDA_OK(cudaMemcpyAsync(perm_dev, perm, sizeof(int64_t) * nb * bs, kind, st));
+  PassParams pp;
+  memset(&pp, 0, sizeof(pp));
+  pp.X = X; pp.ldx = ldx; pp.target = target; pp.perm = perm_dev; pp.masks = drop_masks;
+  pp.loss_sum = loss_sum; pp.step0 = adam_step0; pp.seed = seed; pp.kind = target_kind;
+  pp.lamb = lamb; pp.lr = hp->lr; pp.beta1 = hp->beta1; pp.beta2 = hp->beta2; pp.eps = hp->eps;
+  pp.wd = hp->weight_decay;
+  GLNN_CUDA_OK(cudaMemcpyAsync(c.ws + c.wl.pp, &pp, sizeof(pp), cudaMemcpyHostToDevice, st));
+  GLNN_CUDA_OK(cudaMemsetAsync(c.ws + c.wl.ctr, 0, sizeof(int), st));
+  // `pp` lives on this stack frame: the copy above must have been staged before we return
+  // (cudaMemcpyAsync from pageable memory returns after staging, so this is already guaranteed).
+
+  static const bool no_graph = getenv("GLNN_NO_GRAPH") != nullptr;
+  if (!no_graph && nb >= 2) {
+    cudaGraphExec_t exec = nullptr;
+    rc = get_graph(c, &exec);
+    if (rc != 0) return rc;
+    for (int64_t i = 0; i < nb; ++i) GLNN_CUDA_OK(cudaGraphLaunch(exec, st));
+    return 0;
+  }
+  for (int64_t i = 0; i < nb; ++i) {
+    rc = enqueue_step(c, st);
+    if (rc != 0) return rc;
+  }
+  return 0;
+}
+
+extern "C" int glnn_mlp_eval(const glnn_mlp_desc* desc, const float* params, const float* bn_stats,
+                             const float* X, int64_t ldx, int64_t n, float* out, int64_t ldo,
+                             int log_softmax, int64_t rows_per_chunk, void* workspace,
+                             int64_t workspace_bytes, glnn_stream_t stream) {
+  using namespace glnn;
+  GLNN_REQUIRE(n >= 0 && rows_per_chunk >= 1, GLNN_ERR_ARG, "mlp_eval: bad sizes");
+  Dims d;
+  int rc = make_dims(desc, rows_per_chunk, &d);
+  if (rc != 0) return rc;
+  if (n == 0) return 0;
+  GLNN_REQUIRE(params && X && out && workspace, GLNN_ERR_ARG, "mlp_eval: null pointer");
+  GLNN_REQUIRE(!d.norm || bn_stats, GLNN_ERR_ARG, "mlp_eval: bn_stats required with norm=1");
+  GLNN_REQUIRE(ldx >= d.F && ldo >= d.C, GLNN_ERR_SHAPE, "mlp_eval: leading dimension too small");
+  const ParamLayout pl = param_layout(d);
+  const WsLayout wl = ws_layout(d, false);
+  GLNN_REQUIRE(workspace_bytes >= wl.total_bytes, GLNN_ERR_WORKSPACE,
+               "mlp_eval: workspace %lld < %lld bytes", (long long)workspace_bytes,
+               (long long)wl.total_bytes);
+  float* ws = static_cast<float*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* fold = ws + wl.fold;
+  if (d.norm)
+    for (int l = 0; l < d.L - 1; ++l) {
+      rc = glnn_bn_fold_f32(params + pl.gamma[l], params + pl.beta[l], bn_stats + 2LL * l * d.H,
+                            bn_stats + (2LL * l + 1) * d.H, d.bn_eps, fold + 2LL * l * d.H,
+                            fold + (2LL * l + 1) * d.H, d.H, st);
+      if (rc != 0) return rc;
+    }
+  for (int64_t r0 = 0; r0 < n; r0 += rows_per_chunk) {
+    const int64_t R = std::min(rows_per_chunk, n - r0);
+    const float* h = X + r0 * ldx;
+    int64_t ldh = ldx;
+    for (int l = 0; l < d.L; ++l) {
+      const int din = in_dim(d, l), dout = out_dim(d, l);
+      const bool last = (l == d.L - 1);
+      float* z = last ? (log_softmax ? ws + wl.logits : out + r0 * ldo)
+                      : ws + (l & 1 ? wl.a[0] : wl.z[0]);
+      const int64_t ldz = (last && !log_softmax) ? ldo : dout;
+      rc = gemm_run(h, ldh, 0, params + pl.w[l], din, 1, z, ldz, R, dout, din, params + pl.b[l],
+                    (!last && d.norm) ? fold + 2LL * l * d.H : nullptr,
+                    (!last && d.norm) ? fold + (2LL * l + 1) * d.H : nullptr, last ? 0 : 1, st);
+      if (rc != 0) return rc;
+      h = z;
+      ldh = dout;
+    }
+    if (log_softmax) {
+      rc = glnn_log_softmax_f32(ws + wl.logits, d.C, out + r0 * ldo, ldo, R, d.C, st);
+      if (rc != 0) return rc;
+    }
+  }
+  return 0;
+}

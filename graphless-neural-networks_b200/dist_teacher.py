@@ -1,0 +1,142 @@
+"""Destination-row sharded SAGE teacher forward over the GPUs of one box.
+
+The reference is single-process; this is how the same forward spreads over NVLink-connected B200s:
+  * rows (destination nodes) are cut into G contiguous ranges balanced by NNZ (power-law degrees
+    make node-count balance wrong); rank g owns CSR rows [cut[g], cut[g+1]);
+  * every rank keeps a full replica of the current layer's embeddings in a PADDED layout
+    [G * rows_max, d]: rank g's rows live at [g * rows_max, g * rows_max + rows_g).  Column ids of
+    the local CSR slice are relabelled into that layout once, so the gather kernel indexes the
+    replica directly and the exchange is one equal-sized all-gather per layer;
+  * per layer: local aggregation + projection for the owned rows (same kernels as 1 GPU) and ONE
+    all-gather of a [rows_max, d] slab (NCCL over NVLink 5 / NVSwitch) -- of the layer input for
+    an aggregate-first layer, of the narrow projection for a project-first layer.  The final
+    log-probabilities are gathered the same way.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+
+
+def nnz_balanced_cuts(indptr, world):
+    """Row boundaries cut[0..world] with ~equal nnz (+ rows, so empty rows also spread)."""
+    p = indptr.to(torch.int64).cpu()
+    n = p.numel() - 1
+    weight = p + torch.arange(n + 1, dtype=torch.int64)  # nnz + rows, monotone
+    total = int(weight[-1])
+    targets = torch.tensor([total * g // world for g in range(1, world)], dtype=torch.int64)
+    inner = torch.searchsorted(weight, targets).clamp_(0, n)
+    cuts = [0] + inner.tolist() + [n]
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return cuts
+
+
+class ShardedGraph:
+    """Rank-local slice of a CSRGraph in the padded global layout."""
+
+    def __init__(self, g, rank, world):
+        self.rank, self.world, self.n = rank, world, g.num_nodes()
+        self.cuts = nnz_balanced_cuts(g.indptr, world)
+        self.rows_max = max(self.cuts[i + 1] - self.cuts[i] for i in range(world))
+        r0, r1 = self.cuts[rank], self.cuts[rank + 1]
+        self.r0, self.rows = r0, r1 - r0
+        p = g.indptr.to(torch.int64)
+        e0, e1 = int(p[r0]), int(p[r1])
+        dev = g.indices.device
+        cuts_t = torch.tensor(self.cuts, dtype=torch.int64, device=dev)
+        cols = g.indices[e0:e1].to(torch.int64)
+        owner = torch.searchsorted(cuts_t, cols, right=True) - 1
+        cols = owner * self.rows_max + (cols - cuts_t[owner])
+        local_ptr = p[r0:r1 + 1] - e0
+        deg = local_ptr[1:] - local_ptr[:-1]
+        # the SAGE "gcn" self term becomes an explicit edge to the row's own slot in the replica
+        # (it sits at an offset there), and the mean uses 1 / (true in-degree + 1) as a row scale
+        rows = torch.arange(self.rows, device=dev, dtype=torch.int64)
+        self_pos = local_ptr[1:] + rows            # position of the appended self edge of each row
+        nnz = int(local_ptr[-1]) + self.rows
+        merged = torch.empty(nnz, dtype=torch.int64, device=dev)
+        is_self = torch.zeros(nnz, dtype=torch.bool, device=dev)
+        is_self[self_pos] = True
+        merged[is_self] = rank * self.rows_max + rows
+        merged[~is_self] = cols
+        self.indices = merged.to(torch.int32)
+        new_ptr = local_ptr + torch.arange(self.rows + 1, device=dev, dtype=torch.int64)
+        self.indptr = new_ptr.to(torch.int32) if nnz < 2 ** 31 else new_ptr
+        self.inv_deg1 = (1.0 / (deg.to(torch.float32) + 1.0)).contiguous()
+
+    def to_padded(self, x):
+        """[n, d] in original node order -> [world * rows_max, d] padded layout (zeros in pads)."""
+        out = torch.zeros(self.world * self.rows_max, x.shape[1], dtype=x.dtype, device=x.device)
+        for g in range(self.world):
+            a, b = self.cuts[g], self.cuts[g + 1]
+            out[g * self.rows_max: g * self.rows_max + (b - a)] = x[a:b]
+        return out
+
+    def from_padded(self, xp):
+        return torch.cat([xp[g * self.rows_max: g * self.rows_max + (self.cuts[g + 1] - self.cuts[g])]
+                          for g in range(self.world)])
+
+
+def _pad_rows(w, b, dpad):
+    """Zero-pads an nn.Linear weight [d_out, d_in] / bias [d_out] to dpad output rows."""
+    d_out = w.shape[0]
+    if dpad == d_out:
+        return w, b
+    wp = torch.zeros(dpad, w.shape[1], dtype=w.dtype, device=w.device)
+    wp[:d_out] = w
+    bp = torch.zeros(dpad, dtype=b.dtype, device=b.device)
+    bp[:d_out] = b
+    return wp, bp
+
+
+def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None, log_softmax=True):
+    """layers: [(W [out,in], b)], norms: [(scale, shift)] folded eval-BN per hidden layer (or []).
+    feats_pad: padded replica of the input features (valid on every rank).  Returns the padded
+    replica [world * rows_max, label_dim] of the output (log-probabilities when log_softmax).
+
+    Exchange plan: an aggregate-first layer needs the full replica of its input (all-gather of the
+    previous output, d_in wide); a project-first layer (4-padded d_out < d_in) projects only the
+    owned rows and all-gathers the narrow projection instead -- for ogbn-products the last layer
+    moves 48 instead of 256 columns.  `kernels` (default: the CUDA ops) is injectable so the host
+    logic can be exercised with gloo on CPU by the tests."""
+    k = kernels or ops
+    world, rm = sg.world, sg.rows_max
+    lo, hi = sg.rank * rm, sg.rank * rm + sg.rows
+
+    def gather(buf):
+        if world > 1:
+            dist.all_gather_into_tensor(buf, buf[lo: lo + rm].clone(), group=group)
+
+    h, h_full = feats_pad, True
+    L = len(layers)
+    for l, (w, b) in enumerate(layers):
+        last = l == L - 1
+        scale, shift = (norms[l] if (norms and not last) else (None, None))
+        relu = 0 if last else 1
+        d_out, d_in = w.shape
+        dpad = (d_out + 3) // 4 * 4
+        if dpad < d_in and (scale is None or dpad == d_out):
+            wp, bp = _pad_rows(w, b, dpad)
+            z = torch.zeros(world * rm, dpad, dtype=h.dtype, device=h.device)
+            k.gemm(h[lo:hi, :d_in], wp, trans_b=True, out=z[lo:hi])
+            gather(z)
+            y = torch.zeros(world * rm, dpad, dtype=h.dtype, device=h.device)
+            k.spmm_csr(sg.indptr, sg.indices, z, d=dpad, out=y[lo:hi], dst_scale=sg.inv_deg1,
+                       bias=bp, col_scale=scale, col_shift=shift, relu=relu)
+        else:
+            if not h_full:
+                gather(h)
+            agg = k.spmm_csr(sg.indptr, sg.indices, h, d=d_in, dst_scale=sg.inv_deg1)
+            y = torch.zeros(world * rm, dpad, dtype=h.dtype, device=h.device)
+            k.gemm(agg, w, trans_b=True, out=y[lo:hi, :d_out], bias=b, col_scale=scale,
+                   col_shift=shift, relu=relu)
+        h, h_full = y, False
+    c = layers[-1][0].shape[0]
+    out = torch.zeros(world * rm, c, dtype=h.dtype, device=h.device)
+    if log_softmax:
+        k.log_softmax(h[lo:hi, :c], out=out[lo:hi])
+    else:
+        out[lo:hi] = h[lo:hi, :c]
+    gather(out)
+    return out

@@ -1,0 +1,93 @@
+"""Tensor-level wrappers over the C ABI (one function per entry point of include/glnn_b200.h).
+Inputs must be CUDA fp32 tensors with unit stride in the last dimension; the row stride is passed
+through as the leading dimension, so column-sliced views work without copies."""
+import torch
+
+from . import _lib
+from ._lib import check, ptr, require_cuda, stream
+
+
+def _ld(t):
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError("expected a 2-D tensor with unit stride in the last dimension")
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def _f32(*ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.float32:
+            raise ValueError("glnn_b200 kernels are fp32")
+
+
+def spmm_csr(indptr, indices, x, d=None, out=None, self_add=False, mean_plus_one=False,
+             src_scale=None, dst_scale=None, bias=None, col_scale=None, col_shift=None, relu=0):
+    """glnn_spmm_csr_f32.  indptr int32/int64 [n_dst+1], indices int32 [nnz], x [n_src, >=d]."""
+    lib = _lib.load()
+    require_cuda(indptr, indices, x, out, src_scale, dst_scale, bias, col_scale, col_shift)
+    _f32(x, out, src_scale, dst_scale, bias, col_scale, col_shift)
+    if indices.dtype != torch.int32:
+        raise ValueError("indices must be int32")
+    if indptr.dtype not in (torch.int32, torch.int64):
+        raise ValueError("indptr must be int32 or int64")
+    n_dst = indptr.numel() - 1
+    d = x.shape[1] if d is None else d
+    if out is None:
+        out = torch.empty(n_dst, d, dtype=torch.float32, device=x.device)
+    check(lib.glnn_spmm_csr_f32(ptr(indptr), int(indptr.dtype == torch.int64), ptr(indices), ptr(x),
+                                _ld(x), ptr(out), _ld(out), n_dst, x.shape[0], d, int(self_add),
+                                int(mean_plus_one), ptr(src_scale), ptr(dst_scale), ptr(bias),
+                                ptr(col_scale), ptr(col_shift), int(relu), stream()),
+          "glnn_spmm_csr_f32")
+    return out
+
+
+def gemm(a, b, trans_a=False, trans_b=False, out=None, row_scale=None, bias=None, col_scale=None,
+         col_shift=None, relu=0, impl=0):
+    """glnn_gemm_f32: out = epilogue(op(a) @ op(b)).  trans_b=True takes an nn.Linear weight."""
+    lib = _lib.load()
+    require_cuda(a, b, out, row_scale, bias, col_scale, col_shift)
+    _f32(a, b, out, row_scale, bias, col_scale, col_shift)
+    m, k = (a.shape[1], a.shape[0]) if trans_a else (a.shape[0], a.shape[1])
+    kb, n = (b.shape[1], b.shape[0]) if trans_b else (b.shape[0], b.shape[1])
+    if k != kb:
+        raise ValueError(f"gemm: inner dimensions differ ({k} vs {kb})")
+    if out is None:
+        out = torch.empty(m, n, dtype=torch.float32, device=a.device)
+    check(lib.glnn_gemm_f32(ptr(a), _ld(a), int(trans_a), ptr(b), _ld(b), int(trans_b), ptr(out),
+                            _ld(out), m, n, k, ptr(row_scale), ptr(bias), ptr(col_scale),
+                            ptr(col_shift), int(relu), int(impl), stream()), "glnn_gemm_f32")
+    return out
+
+
+def bn_fold(gamma, beta, mean, var, eps):
+    lib = _lib.load()
+    require_cuda(gamma, beta, mean, var)
+    n = gamma.numel()
+    out = torch.empty(2, n, dtype=torch.float32, device=gamma.device)
+    check(lib.glnn_bn_fold_f32(ptr(gamma), ptr(beta), ptr(mean), ptr(var), float(eps), ptr(out[0]),
+                               ptr(out[1]), n, stream()), "glnn_bn_fold_f32")
+    return out[0], out[1]
+
+
+def log_softmax(x, out=None):
+    lib = _lib.load()
+    require_cuda(x, out)
+    _f32(x, out)
+    if out is None:
+        out = torch.empty(x.shape[0], x.shape[1], dtype=torch.float32, device=x.device)
+    check(lib.glnn_log_softmax_f32(ptr(x), _ld(x), ptr(out), _ld(out), x.shape[0], x.shape[1],
+                                   stream()), "glnn_log_softmax_f32")
+    return out
+
+
+def nll_acc(logp, labels, idx=None):
+    """(sum of -logp[i, y_i], number of argmax hits) over rows idx (None = all) as a 2-float tensor."""
+    lib = _lib.load()
+    require_cuda(logp, labels, idx)
+    if labels.dtype != torch.int64 or (idx is not None and idx.dtype != torch.int64):
+        raise ValueError("labels / idx must be int64")
+    n = logp.shape[0] if idx is None else idx.numel()
+    out = torch.zeros(2, dtype=torch.float32, device=logp.device)
+    check(lib.glnn_nll_acc_f32(ptr(logp), _ld(logp), logp.shape[1], ptr(labels), ptr(idx), n,
+                               ptr(out), stream()), "glnn_nll_acc_f32")
+    return out

@@ -1,0 +1,232 @@
+/* glnn_b200.h -- C ABI of libglnn_b200.so, the B200 (sm_100a) implementation of the GLNN hot path.
+ *
+ * The reference (snap-research/graphless-neural-networks @ 80d0f8ea) is pure Python and has no FFI;
+ * its extension points are the `models.Model` class, the step functions of train_and_eval.py and
+ * the out.npz file (README.md:77-79).  Each entry point below names the
+ * reference call it replaces.  The Python side (glnn_b200/_lib.py) binds them with ctypes; the stub
+ * a maintainer would add to the reference is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is CALLER-OWNED DEVICE memory unless the name ends in `_host`; the library never
+ *     frees caller memory and keeps no reference to it after the call returns;
+ *   - matrices are row-major fp32 with an explicit leading dimension (elements);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*) and is asynchronous; no entry
+ *     point synchronises the device unless documented;
+ *   - return value: 0 = success; < 0 = argument/shape/alignment error, nothing was launched;
+ *     > 0 = a cudaError_t passed through.  glnn_last_error() returns a thread-local message.
+ */
+#ifndef GLNN_B200_H_
+#define GLNN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLNN_ABI_VERSION 1
+
+#define GLNN_ERR_ARG (-1)       /* null pointer / negative size / unsupported flag combination  */
+#define GLNN_ERR_SHAPE (-2)     /* dimension outside the supported range                        */
+#define GLNN_ERR_ALIGN (-3)     /* pointer or leading dimension violates an alignment rule      */
+#define GLNN_ERR_WORKSPACE (-4) /* workspace too small (see the matching *_workspace_bytes)     */
+#define GLNN_ERR_DEVICE (-5)    /* not an sm_100 device                                         */
+
+#if defined(__GNUC__)
+#define GLNN_API __attribute__((visibility("default")))
+#else
+#define GLNN_API
+#endif
+
+typedef void* glnn_stream_t;
+
+GLNN_API int glnn_version(void);
+GLNN_API const char* glnn_last_error(void);
+/* Fills SM count and compute capability of the current device.  Fails with GLNN_ERR_DEVICE when the
+ * device is not compute capability 10.x. */
+GLNN_API int glnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1/K2/K3: CSR neighbour aggregation  (dgl update_all(copy_u, sum) + the scalings around it)
+ *
+ *   acc[v,:] = sum_{e in [indptr[v], indptr[v+1])} src_scale[indices[e]] * X[indices[e], :]
+ *   if self_add:        acc[v,:] += X[v,:]                  (dst nodes are a prefix of src nodes)
+ *   if mean_plus_one:   acc[v,:] /= (in_deg(v) + 1)         (SAGEConv "gcn", models.py:112,138)
+ *   if dst_scale:       acc[v,:] *= dst_scale[v]            (GraphConv norm="both", models.py:193)
+ *   t      = acc[v,c] + bias[c];            if relu == 2: t = max(t, 0)   (GCN: relu -> norm)
+ *   t      = t * col_scale[c] + col_shift[c];  if relu == 1: t = max(t, 0)   (SAGE: norm -> relu)
+ *   Y[v,c] = t
+ *
+ * Replaces: dgl.nn.SAGEConv("gcn") aggregation (models.py:84-99,112,138), dgl.nn.GraphConv
+ * aggregation (models.py:170-187,193) and g.update_all(copy_u,sum) in utils.py:185.
+ * indptr is int32 or int64 (indptr64), indices int32.  src_scale, dst_scale, bias, col_scale,
+ * col_shift may be NULL.  Fast path needs d % 4 == 0, ldx % 4 == 0, ldy % 4 == 0 and 16-byte
+ * aligned X/Y; anything else takes a scalar path.  Multi-edges count with multiplicity; an empty
+ * row yields the epilogue applied to (self_add ? X[v] : 0).
+ */
+GLNN_API int glnn_spmm_csr_f32(const void* indptr, int indptr64, const int32_t* indices, const float* X,
+                      int64_t ldx, float* Y, int64_t ldy, int64_t n_dst, int64_t n_src, int d,
+                      int self_add, int mean_plus_one, const float* src_scale,
+                      const float* dst_scale, const float* bias, const float* col_scale,
+                      const float* col_shift, int relu, glnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4: fp32-faithful dense projection with fused epilogue
+ *
+ *   t      = row_scale[m] * sum_k opA(m,k) * opB(k,n) + bias[n];   if relu == 2: t = max(t, 0)
+ *   C[m,n] = t * col_scale[n] + col_shift[n];                      if relu == 1: C = max(C, 0)
+ *   opA(m,k) = transA ? A[k*lda + m] : A[m*lda + k]
+ *   opB(k,n) = transB ? B[n*ldb + k] : B[k*ldb + n]      (transB=1 is an nn.Linear weight [N,K])
+ *
+ * Replaces: nn.Linear inside SAGEConv.fc_neigh / MLP.layers (models.py:46,84-99), torch.matmul in
+ * GraphConv (models.py:170-187), and their autograd backward GEMMs in train_mini_batch
+ * (train_and_eval.py:82-85).  Accumulation is fp32 (or error-compensated 3xTF32 on the tensor
+ * path, which holds the 1e-4 parity bound).  Any epilogue pointer may be NULL.
+ * `impl`: 0 = auto, 1 = force SIMT fp32, 2 = force tcgen05 3xTF32 (error if the shape is not
+ * eligible).
+ */
+GLNN_API int glnn_gemm_f32(const float* A, int64_t lda, int transA, const float* B, int64_t ldb, int transB,
+                  float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* row_scale,
+                  const float* bias, const float* col_scale, const float* col_shift, int relu,
+                  int impl, glnn_stream_t stream);
+
+/* K5 (eval): folds BatchNorm1d running statistics into a per-column affine for the epilogues
+ * above: scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (models.py:139-141). */
+GLNN_API int glnn_bn_fold_f32(const float* gamma, const float* beta, const float* mean, const float* var,
+                     float eps, float* scale, float* shift, int n, glnn_stream_t stream);
+
+/* K7: Y[r,:] = log_softmax(X[r, 0:c])  (train_and_eval.py:98,124).  In-place allowed. */
+GLNN_API int glnn_log_softmax_f32(const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n, int c,
+                         glnn_stream_t stream);
+
+/* K7+K8 (eval): for the rows listed in idx (int64, NULL = all n rows) of log-probabilities LP
+ * accumulates  out[0] += sum_i -LP[idx_i, labels[idx_i]]  and  out[1] += #(argmax == label)
+ * (criterion + evaluator of train_and_eval.py:99-104,129-134).  `out` is 2 floats, zeroed by
+ * the caller. */
+GLNN_API int glnn_nll_acc_f32(const float* LP, int64_t ld, int c, const int64_t* labels, const int64_t* idx,
+                     int64_t n, float* out, glnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Student (B): MLP distillation.  Replaces the body of train_mini_batch (train_and_eval.py:59-86)
+ * and evaluate_mini_batch (:108-136) for models.MLP (models.py:7-53) with norm_type in
+ * {"none","batch"}.
+ *
+ * Parameter memory is FLAT: one fp32 buffer per role (params, grads, exp_avg, exp_avg_sq) with the
+ * layout   [W_0 (out x in) | b_0 | W_1 | b_1 | ... | gamma_0 | beta_0 | gamma_1 | ...]   and a flat
+ * buffer bn_stats = [running_mean_0 | running_var_0 | running_mean_1 | ...].  The host side keeps
+ * nn.Parameter / optimizer-state tensors as views into these buffers so state_dict() and
+ * torch.optim.Adam stay coherent.
+ */
+typedef struct glnn_mlp_desc {
+  int32_t num_layers;  /* >= 1 */
+  int32_t feat_dim;
+  int32_t hidden_dim;
+  int32_t label_dim;
+  int32_t norm;        /* 0 = none, 1 = BatchNorm1d */
+  float dropout;       /* drop probability p, 0 <= p < 1 */
+  float bn_eps;        /* 1e-5 */
+  float bn_momentum;   /* 0.1 */
+} glnn_mlp_desc;
+
+typedef struct glnn_adam_hparams {
+  float lr, beta1, beta2, eps, weight_decay; /* torch.optim.Adam, L2 decay (train_student.py:275) */
+} glnn_adam_hparams;
+
+/* Number of fp32 elements in the flat parameter buffer / in bn_stats. */
+GLNN_API int64_t glnn_mlp_param_count(const glnn_mlp_desc* desc);
+GLNN_API int64_t glnn_mlp_bn_stat_count(const glnn_mlp_desc* desc);
+/* Bytes of scratch needed for batches of up to `rows` rows (train or eval). */
+GLNN_API int64_t glnn_mlp_workspace_bytes(const glnn_mlp_desc* desc, int64_t rows);
+
+/* One pass of train_mini_batch: nb optimizer steps over batches perm[i*bs : (i+1)*bs] of rows of
+ * X [n, feat_dim].  target_kind 0: target = int64 labels [n] + NLLLoss (mean);  1: target = fp32
+ * teacher LOG-probabilities [n, label_dim] + KLDivLoss(batchmean, log_target=True).
+ * Each step: gather -> forward (BN batch statistics, running-stat update, dropout) -> log-softmax
+ * -> loss -> backward of lamb*loss -> Adam step (adam_step0 + i + 1).  loss_sum[0] accumulates the
+ * UNSCALED per-step mean losses (the caller zeroes it and divides by nb).
+ * drop_masks: NULL -> device counter-based RNG keyed by (seed, step, layer, element); otherwise
+ * uint8 keep-masks laid out [nb][num_layers-1][bs][hidden_dim] (parity mode).
+ * num_batches_tracked (int64 [num_layers-1], may be NULL) is advanced by nb on the device.
+ * At most 2^22 rows (nb * bs) per call; the host splits longer passes and carries adam_step0.
+ * The kernel sequence of a step is captured once into a CUDA graph per (shape, buffer set) and
+ * replayed nb times (set GLNN_NO_GRAPH=1 to launch kernels directly). */
+GLNN_API int glnn_mlp_train_pass(const glnn_mlp_desc* desc, float* params, float* grads, float* exp_avg,
+                        float* exp_avg_sq, float* bn_stats, int64_t* num_batches_tracked,
+                        int64_t adam_step0, const glnn_adam_hparams* hp, const float* X, int64_t ldx,
+                        const void* target, int target_kind, const int64_t* perm, int64_t nb,
+                        int64_t bs, const uint8_t* drop_masks, uint64_t seed, float lamb,
+                        float* loss_sum, void* workspace, int64_t workspace_bytes,
+                        glnn_stream_t stream);
+
+/* Eval-mode forward of n contiguous rows -> out [n, label_dim] (ldo): log-probabilities if
+ * log_softmax != 0 (evaluate_mini_batch), raw logits otherwise (Model.forward).  Row results are
+ * independent of how rows are batched, so `rows_per_chunk` only bounds scratch
+ * (glnn_mlp_workspace_bytes(desc, rows_per_chunk)). */
+GLNN_API int glnn_mlp_eval(const glnn_mlp_desc* desc, const float* params, const float* bn_stats,
+                  const float* X, int64_t ldx, int64_t n, float* out, int64_t ldo, int log_softmax,
+                  int64_t rows_per_chunk, void* workspace, int64_t workspace_bytes,
+                  glnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Teacher (A): whole eval-mode forward, layer planning included.
+ *
+ * glnn_sage_forward  replaces SAGE.inference (models.py:121-148; full-neighbour, eval mode, where
+ *   the reference's per-batch loop equals one full-graph pass per layer -- SURVEY.md section 3.2):
+ *   per layer  h = fc_neigh((sum_{u->v} h_u + h_v) / (deg_v + 1));  hidden layers: BN(eval) -> ReLU.
+ *   A layer whose (4-padded) d_out is smaller than d_in is projected first (legal by linearity;
+ *   it only changes fp32 rounding), otherwise aggregated first as DGL 0.6.1 does.
+ * glnn_gcn_forward  replaces GCN.forward in eval mode (models.py:189-199) over GraphConv
+ *   norm="both": h = act(D_in^-1/2 A (D_out^-1/2 h) W + b), W first iff d_in > d_out (DGL's rule),
+ *   ReLU inside the conv then BN(eval) on hidden layers.  src_norm/dst_norm are the clamped
+ *   out/in-degree^-1/2 vectors [n].
+ * If log_softmax != 0 the output is log-probabilities (evaluate, train_and_eval.py:97-98).
+ * All pointers (including those inside glnn_gnn_layer) are DEVICE pointers.
+ */
+typedef struct glnn_gnn_layer {
+  const float* weight;   /* SAGE: [d_out, d_in] (nn.Linear);  GCN: [d_in, d_out] (GraphConv) */
+  const float* bias;     /* [d_out] */
+  const float* bn_scale; /* eval BN folded by glnn_bn_fold_f32; NULL when the layer has no norm */
+  const float* bn_shift;
+  int32_t d_in, d_out;
+} glnn_gnn_layer;
+
+GLNN_API int64_t glnn_gnn_forward_workspace_bytes(int64_t n, const glnn_gnn_layer* layers, int num_layers);
+
+GLNN_API int glnn_sage_forward(const void* indptr, int indptr64, const int32_t* indices, int64_t n,
+                      const float* X, int64_t ldx, const glnn_gnn_layer* layers, int num_layers,
+                      float* out, int64_t ldo, int log_softmax, void* workspace,
+                      int64_t workspace_bytes, glnn_stream_t stream);
+
+GLNN_API int glnn_gcn_forward(const void* indptr, int indptr64, const int32_t* indices, int64_t n,
+                     const float* src_norm, const float* dst_norm, const float* X, int64_t ldx,
+                     const glnn_gnn_layer* layers, int num_layers, float* out, int64_t ldo,
+                     int log_softmax, void* workspace, int64_t workspace_bytes,
+                     glnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-buffer entry point (what an out-of-process / non-torch caller binds; used for the e2e
+ * benchmark leg).  SAGE("gcn") eval forward = SAGE.inference + log_softmax: copies the CSR graph,
+ * features and weights from HOST memory, runs glnn_sage_forward on the device and copies the
+ * [n, label_dim] log-probabilities back.  Synchronous; allocates and frees its own device memory.
+ * Weights follow the state_dict layout: per layer W [out,in], b [out]; per hidden layer optional
+ * BN (gamma, beta, running_mean, running_var), NULL when norm_type="none".
+ */
+typedef struct glnn_sage_layer_host {
+  const float* weight; /* [d_out, d_in] */
+  const float* bias;   /* [d_out] */
+  const float* bn_gamma;
+  const float* bn_beta;
+  const float* bn_mean;
+  const float* bn_var;
+  int32_t d_in, d_out;
+} glnn_sage_layer_host;
+
+GLNN_API int glnn_sage_inference_host(const int64_t* indptr_host, const int32_t* indices_host, int64_t n,
+                             const float* feats_host, const glnn_sage_layer_host* layers,
+                             int num_layers, float bn_eps, float* out_logprob_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLNN_B200_H_ */

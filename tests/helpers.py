@@ -61,3 +61,58 @@ def student_masks(d, idx_perm_count, num_layers):
 def relerr(a, b):
     a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+class TorchKernels:
+    """CPU test double for glnn_b200.ops (same keyword surface), built on the oracle's SpMM.  Used
+    only to exercise HOST logic (sharding, relabelling, exchange plan) under gloo without a GPU."""
+
+    @staticmethod
+    def _epi(y, bias, col_scale, col_shift, relu, out):
+        if bias is not None:
+            y = y + bias
+        if relu == 2:
+            y = y.clamp(min=0)
+        if col_scale is not None:
+            y = y * col_scale + col_shift
+        if relu == 1:
+            y = y.clamp(min=0)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+
+    @staticmethod
+    def spmm_csr(indptr, indices, x, d=None, out=None, self_add=False, mean_plus_one=False,
+                 src_scale=None, dst_scale=None, bias=None, col_scale=None, col_shift=None, relu=0):
+        import glnn_oracle as O
+        d = x.shape[1] if d is None else d
+        xs = x[:, :d].contiguous()
+        if src_scale is not None:
+            xs = xs * src_scale.unsqueeze(1)
+        y = O.spmm_sum(indptr.long(), indices.long(), xs, n_src=x.shape[0])
+        n_dst = indptr.numel() - 1
+        if self_add:
+            y = y + x[:n_dst, :d]
+        if mean_plus_one:
+            deg = (indptr[1:] - indptr[:-1]).to(y.dtype).unsqueeze(1)
+            y = y / (deg + 1)
+        if dst_scale is not None:
+            y = y * dst_scale.unsqueeze(1)
+        return TorchKernels._epi(y, bias, col_scale, col_shift, relu, out)
+
+    @staticmethod
+    def gemm(a, b, trans_a=False, trans_b=False, out=None, row_scale=None, bias=None, col_scale=None,
+             col_shift=None, relu=0, impl=0):
+        y = (a.t() if trans_a else a) @ (b.t() if trans_b else b)
+        if row_scale is not None:
+            y = y * row_scale.unsqueeze(1)
+        return TorchKernels._epi(y, bias, col_scale, col_shift, relu, out)
+
+    @staticmethod
+    def log_softmax(x, out=None):
+        y = torch.log_softmax(x, 1)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y

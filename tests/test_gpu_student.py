@@ -1,0 +1,225 @@
+"""GPU parity tests for the student path (B): the fused train_mini_batch pass and evaluate_mini_batch
+against (1) the fixtures produced by the reference's own train_mini_batch / evaluate_mini_batch
+(autograd + torch.optim.Adam) and (2) the CPU oracle at the real layer shapes."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+import glnn_oracle as O
+from helpers import STUDENT_CASES, load, relerr, student_masks, sub
+from test_oracle_golden import noise_driven
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _student_model(d, dev, prefix="init."):
+    from glnn_b200.models import Model
+    conf = dict(model_name=str(d["model_name"]), num_layers=int(d["num_layers"]),
+                feat_dim=d["feats"].shape[1], hidden_dim=int(d["hidden"]),
+                label_dim=d["out_t"].shape[1], dropout_ratio=float(d["dropout"]),
+                norm_type=str(d["norm"]), device=dev)
+    model = Model(conf)
+    sd = {k[len(prefix):]: torch.from_numpy(np.array(v)) for k, v in d.items() if k.startswith(prefix)}
+    model.load_state_dict(sd)
+    return model
+
+
+class _Replay:
+    """Feeds the permutations the reference drew (recorded in the fixture) to torch.randperm."""
+
+    def __init__(self, perms):
+        self.perms, self.i, self._orig = perms, 0, torch.randperm
+
+    def __enter__(self):
+        def randperm(n, *a, **k):
+            p = self.perms[self.i]
+            self.i += 1
+            assert p.numel() == n
+            return p.clone()
+        torch.randperm = randperm
+        return self
+
+    def __exit__(self, *a):
+        torch.randperm = self._orig
+
+
+def _run_fixture(d, dev, use_masks):
+    from glnn_b200 import mlp_engine, train_and_eval as TE
+    model = _student_model(d, dev)
+    opt = torch.optim.Adam(model.parameters(), lr=float(d["lr"]), weight_decay=float(d["wd"]))
+    feats = torch.from_numpy(d["feats"]).to(dev)
+    labels = torch.from_numpy(d["labels"]).to(dev)
+    out_t = torch.from_numpy(d["out_t"]).to(dev)
+    n_l, bs, lamb = int(d["n_l"]), int(d["batch_size"]), float(d["lamb"])
+    L, H = int(d["num_layers"]), int(d["hidden"])
+    crit_l = torch.nn.NLLLoss()
+    crit_t = torch.nn.KLDivLoss(reduction="batchmean", log_target=True)
+    perms = [torch.from_numpy(d[f"perm.{i}"]) for i in range(2 * int(d["epochs"]))]
+    losses = []
+    if not use_masks:
+        with _Replay(perms):
+            for _ in range(int(d["epochs"])):
+                losses.append(TE.train_mini_batch(model, feats[:n_l], labels[:n_l], bs, crit_l, opt, lamb))
+                losses.append(TE.train_mini_batch(model, feats, out_t, bs, crit_t, opt, 1 - lamb))
+    else:  # parity mode with the reference's recorded dropout keep-masks
+        flat = student_masks(d, 0, L)
+        mi = 0
+        model.train()
+        for ep in range(int(d["epochs"])):
+            for pi, (f, t, lam) in enumerate([(feats[:n_l], labels[:n_l], lamb), (feats, out_t, 1 - lamb)]):
+                perm = perms[2 * ep + pi]
+                nb = max(1, f.shape[0] // bs)
+                idx = perm[: nb * bs].view(nb, -1)
+                rows = idx.shape[1]
+                masks = torch.stack([torch.stack([flat[mi + s * (L - 1) + l] for l in range(L - 1)])
+                                     for s in range(nb)]).to(dev)
+                mi += nb * (L - 1)
+                assert masks.shape == (nb, L - 1, rows, H)
+                loss = mlp_engine.train_pass(model.encoder, opt, f, t, idx.to(dev), lam, masks)
+                losses.append(loss.item() / nb)
+    return model, opt, losses, feats, labels
+
+
+@pytest.mark.parametrize("case", STUDENT_CASES)
+def test_student_matches_reference_golden(dev, case):
+    from glnn_b200 import train_and_eval as TE, utils as U
+    d = load("student_" + case)
+    use_masks = float(d["dropout"]) > 0
+    model, opt, losses, feats, labels = _run_fixture(d, dev, use_masks)
+    assert np.allclose(losses, d["losses"], rtol=TOL, atol=1e-6)
+    L, norm = int(d["num_layers"]), str(d["norm"])
+    sd = {k[len("encoder."):]: v.detach().cpu() for k, v in model.state_dict().items()}
+    final = sub(d, "final.")
+    for k, v in final.items():
+        if k.endswith("num_batches_tracked"):
+            assert int(sd[k]) == int(v), k
+        elif not noise_driven(k, L, norm):
+            assert relerr(sd[k], v) < 5e-4, k
+    for name, p in model.named_parameters():
+        k = name[len("encoder."):]
+        if noise_driven(k, L, norm):
+            continue
+        st = opt.state[p]
+        assert int(st["step"]) == int(d[f"adam.{name}.step"])
+        assert relerr(st["exp_avg"].cpu(), d[f"adam.{name}.exp_avg"]) < 2e-3, k
+        assert relerr(st["exp_avg_sq"].cpu(), d[f"adam.{name}.exp_avg_sq"]) < 2e-3, k
+    if norm != "batch" or L == 1:
+        out_all, loss, score = TE.evaluate_mini_batch(model, feats, labels, torch.nn.NLLLoss(),
+                                                      int(d["batch_size"]), U.get_evaluator("cora"))
+        assert relerr(out_all.cpu(), d["out_all"]) < TOL
+
+
+@pytest.mark.parametrize("case", STUDENT_CASES)
+def test_student_eval_on_reference_state(dev, case):
+    """evaluate_mini_batch on the reference's final weights: log-probs, loss and accuracy."""
+    from glnn_b200 import train_and_eval as TE, utils as U
+    d = load("student_" + case)
+    model = _student_model(d, dev, prefix="final.")
+    feats = torch.from_numpy(d["feats"]).to(dev)
+    labels = torch.from_numpy(d["labels"]).to(dev)
+    out_all, loss, score = TE.evaluate_mini_batch(model, feats, labels, torch.nn.NLLLoss(),
+                                                  int(d["batch_size"]), U.get_evaluator("cora"))
+    assert relerr(out_all.cpu(), d["out_all"]) < TOL
+    assert abs(loss - float(d["loss_eval"])) < 1e-4
+    assert abs(score - float(d["score_eval"])) < 1e-6
+    # Model.forward in eval mode returns raw logits whose log_softmax is the same thing
+    with torch.no_grad():
+        logits = model.eval()(None, feats)
+    assert relerr(logits.log_softmax(1).cpu(), d["out_all"]) < TOL
+
+
+@pytest.mark.parametrize("graph_mode", [True, False])
+@pytest.mark.parametrize("shape", [(128, 256, 40, 512, "MLP"), (100, 256, 47, 1024, "MLP3w8"),
+                                   (128, 1024, 40, 512, "MLP3w4")])
+def test_student_real_shapes_vs_oracle(dev, shape, graph_mode, monkeypatch):
+    """arxiv / products layer shapes: 6 NLL + 6 KL steps against the fp32 CPU oracle."""
+    from glnn_b200 import mlp_engine
+    from glnn_b200.models import Model
+    f, h, c, bs, name = shape
+    n, nb = bs * 6 + 17, 6
+    gen = torch.Generator().manual_seed(11)
+    feats = torch.randn(n, f, generator=gen)
+    labels = torch.randint(0, c, (n,), generator=gen)
+    out_t = torch.log_softmax(torch.randn(n, c, generator=gen) * 2, 1)
+    torch.manual_seed(5)
+    model = Model(dict(model_name=name, num_layers=3, feat_dim=f, hidden_dim=h, label_dim=c,
+                       dropout_ratio=0.0, norm_type="batch", device=dev))
+    p = {k[len("encoder."):]: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    state = O.init_adam_state(p)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=0.0)
+    idx1 = torch.randperm(n, generator=gen)[: nb * bs].view(nb, bs)
+    idx2 = torch.randperm(n, generator=gen)[: nb * bs].view(nb, bs)
+    want = [O.train_mini_batch(p, state, feats, labels, "nll", bs, idx1, 0.3, 3, "batch", 0.0, 0.01, 0.0),
+            O.train_mini_batch(p, state, feats, out_t, "kl", bs, idx2, 0.7, 3, "batch", 0.0, 0.01, 0.0)]
+    model.train()
+    fd, ld, td = feats.to(dev), labels.to(dev), out_t.to(dev)
+    if graph_mode:
+        got = [mlp_engine.train_pass(model.encoder, opt, fd, ld, idx1.to(dev), 0.3).item() / nb,
+               mlp_engine.train_pass(model.encoder, opt, fd, td, idx2, 0.7).item() / nb]
+    else:  # one step per call -> direct launches (no graph replay)
+        got = [0.0, 0.0]
+        for i in range(nb):
+            got[0] += mlp_engine.train_pass(model.encoder, opt, fd, ld, idx1[i:i + 1].to(dev), 0.3).item() / nb
+        for i in range(nb):
+            got[1] += mlp_engine.train_pass(model.encoder, opt, fd, td, idx2[i:i + 1].to(dev), 0.7).item() / nb
+    assert np.allclose(got, want, rtol=TOL)
+    sd = {k[len("encoder."):]: v.detach().cpu() for k, v in model.state_dict().items()}
+    for k in ("layers.0.weight", "layers.1.weight", "layers.2.weight", "layers.2.bias",
+              "norms.0.weight", "norms.1.bias", "norms.0.running_var", "norms.1.running_var"):
+        assert relerr(sd[k], p[k]) < 5e-4, k
+    assert int(sd["norms.0.num_batches_tracked"]) == 2 * nb
+    # eval forward on identical state
+    model.load_state_dict({"encoder." + k: v for k, v in p.items()})
+    got_eval = mlp_engine.eval_forward(model.encoder, fd)
+    assert relerr(got_eval.cpu(), O.evaluate_mini_batch(p, feats, bs, 3, "batch")) < TOL
+
+
+def test_state_dict_roundtrip_and_views(dev):
+    """Flat-buffer views survive deepcopy(state_dict()) / load_state_dict (early stopping path)."""
+    from glnn_b200 import mlp_engine
+    from glnn_b200.models import Model
+    torch.manual_seed(0)
+    model = Model(dict(model_name="MLP", num_layers=3, feat_dim=16, hidden_dim=32, label_dim=5,
+                       dropout_ratio=0.0, norm_type="batch", device=dev))
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    x = torch.randn(256, 16, device=dev)
+    y = torch.randint(0, 5, (256,), device=dev)
+    idx = torch.arange(256).view(4, 64)
+    mlp_engine.train_pass(model.encoder, opt, x, y, idx, 1.0)
+    snap = copy.deepcopy(model.state_dict())
+    before = mlp_engine.eval_forward(model.encoder, x).clone()
+    mlp_engine.train_pass(model.encoder, opt, x, y, idx, 1.0)
+    assert not torch.allclose(before, mlp_engine.eval_forward(model.encoder, x))
+    model.load_state_dict(snap)
+    assert torch.equal(before, mlp_engine.eval_forward(model.encoder, x))
+    fl = model.encoder._flat
+    assert model.encoder.layers[0].weight.data_ptr() == fl.params.data_ptr()
+
+
+def test_dropout_device_stream_statistics(dev):
+    """Fast mode (device counter-based RNG): finite, decreasing loss on a learnable target."""
+    from glnn_b200 import mlp_engine
+    from glnn_b200.models import Model
+    torch.manual_seed(0)
+    model = Model(dict(model_name="MLP", num_layers=3, feat_dim=32, hidden_dim=256, label_dim=8,
+                       dropout_ratio=0.5, norm_type="batch", device=dev))
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    x = torch.randn(4096, 32, device=dev)
+    y = (x[:, :8].argmax(1)).long()
+    idx = torch.randperm(4096).view(8, 512)
+    l0 = mlp_engine.train_pass(model.encoder, opt, x, y, idx, 1.0).item() / 8
+    for _ in range(10):
+        l1 = mlp_engine.train_pass(model.encoder, opt, x, y, idx, 1.0).item() / 8
+    assert np.isfinite(l1) and l1 < l0
+    acts = mlp_engine.eval_forward(model.encoder, x)
+    assert torch.isfinite(acts).all()

@@ -1,0 +1,315 @@
+"""GPU parity tests for the teacher path (A): aggregation kernel, projection kernel and the whole
+SAGE / GCN forward, all called through the C ABI (ctypes) and checked against the CPU oracle, the
+golden fixtures produced by the reference, and size-independent properties at full products size.
+Tolerance: north_star's 1e-4 relative fp32 (most checks are far tighter)."""
+import numpy as np
+import pytest
+import torch
+
+import glnn_oracle as O
+from helpers import TEACHER_CASES, load, relerr, sub
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from glnn_b200 import _lib
+    lib = _lib.load()
+    import ctypes
+    assert lib.glnn_device_info(ctypes.byref(ctypes.c_int()), ctypes.byref(ctypes.c_int()),
+                                ctypes.byref(ctypes.c_int())) == 0
+    return torch.device("cuda:0")
+
+
+def _rand_graph(n_dst, n_src, e, seed, hubs=0, empty=0):
+    rng = np.random.default_rng(seed)
+    src = rng.integers(0, n_src, e)
+    dst = np.floor(n_dst * rng.random(e) ** 2).astype(np.int64)
+    if hubs:  # a few rows far above the hub threshold (1024)
+        src = np.concatenate([src, rng.integers(0, n_src, hubs * 3000)])
+        dst = np.concatenate([dst, np.repeat(rng.integers(0, n_dst, hubs), 3000)])
+    if empty:
+        keep = dst < n_dst - empty
+        src, dst = src[keep], dst[keep]
+    return O.csr_from_edges(src, dst, n_dst)
+
+
+@pytest.mark.parametrize("d", [1, 3, 4, 7, 8, 20, 47, 48, 64, 100, 128, 200, 256, 300, 516, 1433])
+def test_spmm_plain_widths(dev, d):
+    from glnn_b200 import ops
+    n = 777
+    indptr, indices = _rand_graph(n, n, 9000, seed=d, hubs=2, empty=7)
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(d))
+    want = O.spmm_sum(indptr, indices, x.double())
+    got = ops.spmm_csr(torch.from_numpy(indptr).to(dev), torch.from_numpy(indices).int().to(dev),
+                       x.to(dev))
+    assert relerr(got.cpu(), want) < 1e-5
+
+
+@pytest.mark.parametrize("iptr32", [True, False])
+@pytest.mark.parametrize("d,opts", [
+    (100, dict(self_add=True, mean_plus_one=True)),
+    (48, dict(self_add=True, mean_plus_one=True, bias=True, affine=True, relu=1)),
+    (64, dict(dst_scale=True, bias=True, relu=2, affine=True)),
+    (7, dict(dst_scale=True, bias=True)),
+    (33, dict(src_scale=True)),
+    (256, dict(src_scale=True, dst_scale=True, self_add=True, mean_plus_one=True, bias=True, relu=1)),
+])
+def test_spmm_epilogues(dev, d, opts, iptr32):
+    from glnn_b200 import ops
+    n = 1500
+    indptr, indices = _rand_graph(n, n, 20000, seed=d + 1, hubs=1, empty=3)
+    g = torch.Generator().manual_seed(d)
+    x = torch.randn(n, d, generator=g)
+    ss = torch.rand(n, generator=g) + 0.5 if opts.get("src_scale") else None
+    ds = torch.rand(n, generator=g) + 0.5 if opts.get("dst_scale") else None
+    bias = torch.randn(d, generator=g) if opts.get("bias") else None
+    cs = torch.rand(d, generator=g) + 0.5 if opts.get("affine") else None
+    sh = torch.randn(d, generator=g) if opts.get("affine") else None
+    xd = x.double()
+    acc = O.spmm_sum(indptr, indices, xd * ss.double().unsqueeze(1) if ss is not None else xd)
+    deg = torch.from_numpy(np.diff(indptr)).double().unsqueeze(1)
+    if opts.get("self_add"):
+        acc = acc + xd
+    if opts.get("mean_plus_one"):
+        acc = acc / (deg + 1)
+    if ds is not None:
+        acc = acc * ds.double().unsqueeze(1)
+    if bias is not None:
+        acc = acc + bias.double()
+    relu = opts.get("relu", 0)
+    if relu == 2:
+        acc = acc.clamp(min=0)
+    if cs is not None:
+        acc = acc * cs.double() + sh.double()
+    if relu == 1:
+        acc = acc.clamp(min=0)
+    cu = lambda t: None if t is None else t.to(dev)
+    ip = torch.from_numpy(indptr)
+    got = ops.spmm_csr((ip.int() if iptr32 else ip).to(dev), torch.from_numpy(indices).int().to(dev),
+                       x.to(dev), self_add=opts.get("self_add", False),
+                       mean_plus_one=opts.get("mean_plus_one", False), src_scale=cu(ss),
+                       dst_scale=cu(ds), bias=cu(bias), col_scale=cu(cs), col_shift=cu(sh), relu=relu)
+    assert relerr(got.cpu(), acc) < 1e-5
+
+
+def test_spmm_strided_views_and_bipartite(dev):
+    """Column-sliced input/output (leading dimension > d) and n_src != n_dst (a block)."""
+    from glnn_b200 import ops
+    n_dst, n_src, d = 300, 900, 40
+    indptr, indices = _rand_graph(n_dst, n_src, 5000, seed=5)
+    xfull = torch.randn(n_src, 64)
+    yfull = torch.zeros(n_dst, 48, device=dev)
+    ops.spmm_csr(torch.from_numpy(indptr).to(dev), torch.from_numpy(indices).int().to(dev),
+                 xfull.to(dev)[:, 8:8 + d], d=d, out=yfull[:, 4:4 + d])
+    want = O.spmm_sum(indptr, indices, xfull[:, 8:8 + d].double(), n_src=n_src)
+    assert relerr(yfull[:, 4:4 + d].cpu(), want) < 1e-5
+    assert float(yfull[:, :4].abs().sum()) == 0 and float(yfull[:, 44:].abs().sum()) == 0
+
+
+def test_spmm_empty_and_errors(dev):
+    from glnn_b200 import ops
+    x = torch.randn(5, 8, device=dev)
+    indptr = torch.zeros(6, dtype=torch.int32, device=dev)
+    indices = torch.zeros(0, dtype=torch.int32, device=dev)
+    y = ops.spmm_csr(indptr, indices, x, self_add=True, mean_plus_one=True)
+    assert torch.equal(y, x)  # in-degree 0 -> h_v / 1
+    with pytest.raises(ValueError):
+        ops.spmm_csr(indptr, indices.long(), x)
+    with pytest.raises(ValueError):  # self_add with fewer src than dst rows
+        ops.spmm_csr(indptr, indices, x[:3], self_add=True)
+
+
+GEMM_SHAPES = [
+    (300, 256, 100, False, True), (257, 47, 256, False, True), (129, 7, 1433, False, False),
+    (100, 200, 47, False, False), (64, 100, 513, True, False), (2048, 100, 4096, True, False),
+    (47, 2048, 4096, True, False), (1, 1, 1, False, True), (513, 130, 33, True, True),
+]
+
+
+@pytest.mark.parametrize("m,n,k,ta,tb", GEMM_SHAPES)
+def test_gemm_simt_vs_fp64(dev, m, n, k, ta, tb):
+    from glnn_b200 import ops
+    g = torch.Generator().manual_seed(m * 7 + n)
+    a = torch.randn((k, m) if ta else (m, k), generator=g)
+    b = torch.randn((n, k) if tb else (k, n), generator=g)
+    want = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
+    got = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb, impl=1)
+    assert relerr(got.cpu(), want) < 2e-6
+
+
+@pytest.mark.parametrize("relu", [0, 1, 2])
+def test_gemm_epilogue(dev, relu):
+    from glnn_b200 import ops
+    g = torch.Generator().manual_seed(relu)
+    m, n, k = 333, 96, 70
+    a, b = torch.randn(m, k, generator=g), torch.randn(n, k, generator=g)
+    rs, bias = torch.rand(m, generator=g) + 0.5, torch.randn(n, generator=g)
+    cs, sh = torch.rand(n, generator=g) + 0.5, torch.randn(n, generator=g)
+    want = (a.double() @ b.double().t()) * rs.double().unsqueeze(1) + bias.double()
+    if relu == 2:
+        want = want.clamp(min=0)
+    want = want * cs.double() + sh.double()
+    if relu == 1:
+        want = want.clamp(min=0)
+    out = torch.full((m, 100), 7.0, device=dev)
+    ops.gemm(a.to(dev), b.to(dev), trans_b=True, out=out[:, :n], row_scale=rs.to(dev),
+             bias=bias.to(dev), col_scale=cs.to(dev), col_shift=sh.to(dev), relu=relu, impl=1)
+    assert relerr(out[:, :n].cpu(), want) < 2e-6
+    assert bool((out[:, n:] == 7.0).all())  # padding columns untouched
+
+
+def _model_from_golden(d, dev):
+    from glnn_b200.models import Model
+    conf = dict(model_name=str(d["model_name"]), num_layers=int(d["num_layers"]),
+                feat_dim=d["feats"].shape[1], hidden_dim=int(d["hidden"]),
+                label_dim=d["logits"].shape[1], dropout_ratio=0.5, norm_type=str(d["norm"]),
+                device=dev)
+    model = Model(conf)
+    sd = {k[len("sd."):]: torch.from_numpy(np.array(v)) for k, v in d.items() if k.startswith("sd.")}
+    model.load_state_dict(sd)
+    return model.eval()
+
+
+@pytest.mark.parametrize("case", TEACHER_CASES)
+def test_teacher_matches_reference_golden(dev, case):
+    """Same inputs and weights as the reference run (fixtures): logits, log-probs, loss, score."""
+    from glnn_b200 import graph as G, train_and_eval as TE, utils as U
+    d = load("teacher_" + case)
+    model = _model_from_golden(d, dev)
+    g = G.graph((d["src"], d["dst"]), num_nodes=int(d["n"])).to(dev)
+    feats = torch.from_numpy(d["feats"]).to(dev)
+    labels = torch.from_numpy(d["labels"]).to(dev)
+    data = G.FullNeighborLoader(g, int(d["batch_size"])) if str(d["model_name"]) == "SAGE" else g
+    with torch.no_grad():
+        logits = model.inference(data, feats)
+    assert relerr(logits.cpu(), d["logits"]) < TOL
+    out, loss, score = TE.evaluate(model, data, feats, labels, torch.nn.NLLLoss(),
+                                   U.get_evaluator("cora"), torch.from_numpy(d["idx_eval"]).to(dev))
+    assert relerr(out.cpu(), d["out"]) < TOL
+    assert abs(loss - float(d["loss"])) < 1e-4 * max(1.0, abs(float(d["loss"])))
+    assert abs(score - float(d["score"])) < 1e-6
+
+
+@pytest.mark.parametrize("model_name,dims", [("SAGE", (128, 256, 40, 3)), ("SAGE", (100, 256, 47, 3)),
+                                             ("GCN", (1433, 64, 7, 2))])
+def test_teacher_midsize_vs_oracle(dev, model_name, dims):
+    """arxiv / products / cora layer shapes on a 20k-node skewed multigraph vs the CPU oracle."""
+    from glnn_b200 import graph as G
+    from glnn_b200.models import Model
+    f, h, c, L = dims
+    n, e = 20000, 300000
+    rng = np.random.default_rng(1)
+    src = rng.integers(0, n, e)
+    dst = np.floor(n * rng.random(e) ** 2).astype(np.int64)
+    src, dst = np.concatenate([src, dst, np.arange(n)]), np.concatenate([dst, src, np.arange(n)])
+    torch.manual_seed(0)
+    model = Model(dict(model_name=model_name, num_layers=L, feat_dim=f, hidden_dim=h, label_dim=c,
+                       dropout_ratio=0.2, norm_type="batch", device=dev)).eval()
+    gen = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for m in model.modules():
+            if isinstance(m, torch.nn.BatchNorm1d):
+                m.running_mean.copy_(torch.randn(m.num_features, generator=gen))
+                m.running_var.copy_(torch.rand(m.num_features, generator=gen) * 1.5 + 0.5)
+                m.weight.copy_(torch.rand(m.num_features, generator=gen) + 0.5)
+                m.bias.copy_(torch.randn(m.num_features, generator=gen))
+    feats = torch.randn(n, f, generator=gen)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    layers, norms = [], []
+    for l in range(L):
+        pre = f"encoder.layers.{l}." + ("fc_neigh." if model_name == "SAGE" else "")
+        layers.append((sd[pre + "weight"], sd[pre + "bias"]))
+        if l != L - 1:
+            norms.append(tuple(sd[f"encoder.norms.{l}.{k}"] for k in
+                               ("weight", "bias", "running_mean", "running_var")))
+    indptr, indices = O.csr_from_edges(src, dst, n)
+    if model_name == "SAGE":
+        want = O.sage_inference(indptr, indices, feats, layers, norms, batch_size=None)
+    else:
+        want = O.gcn_forward(indptr, indices, feats, layers, norms)
+    g = G.graph((src, dst), num_nodes=n).to(dev)
+    with torch.no_grad():
+        got = model.inference(G.FullNeighborLoader(g) if model_name == "SAGE" else g, feats.to(dev))
+    assert relerr(got.cpu(), want) < TOL
+
+
+def test_gcn_zero_in_degree_raises(dev):
+    from glnn_b200 import graph as G
+    from glnn_b200.models import Model
+    g = G.graph((np.array([0]), np.array([1])), num_nodes=2).to(dev)
+    model = Model(dict(model_name="GCN", num_layers=2, feat_dim=4, hidden_dim=4, label_dim=2,
+                       dropout_ratio=0.0, norm_type="none", device=dev)).eval()
+    with pytest.raises(ValueError):
+        with torch.no_grad():
+            model(g, torch.ones(2, 4, device=dev))
+
+
+def test_sage_host_entry_point(dev):
+    """glnn_sage_inference_host (host buffers in, host log-probs out) equals the device path."""
+    import ctypes
+    from glnn_b200 import _lib
+    d = load("teacher_sage_bn3")
+    n = int(d["n"])
+    indptr, indices = O.csr_from_edges(d["src"], d["dst"], n)
+    sd = sub(d, "sd.")
+    L = int(d["num_layers"])
+    keep = [np.ascontiguousarray(indptr), np.ascontiguousarray(indices.astype(np.int32)),
+            np.ascontiguousarray(d["feats"])]
+    arr = (_lib.SageLayerHost * L)()
+    for l in range(L):
+        w = sd[f"layers.{l}.fc_neigh.weight"].numpy().copy()
+        b = sd[f"layers.{l}.fc_neigh.bias"].numpy().copy()
+        keep += [w, b]
+        arr[l].weight, arr[l].bias = w.ctypes.data, b.ctypes.data
+        arr[l].d_out, arr[l].d_in = w.shape
+        if l != L - 1:
+            bn = [sd[f"norms.{l}.{k}"].numpy().copy() for k in
+                  ("weight", "bias", "running_mean", "running_var")]
+            keep += bn
+            arr[l].bn_gamma, arr[l].bn_beta, arr[l].bn_mean, arr[l].bn_var = \
+                [x.ctypes.data for x in bn]
+    out = np.empty((n, d["logits"].shape[1]), dtype=np.float32)
+    lib = _lib.load()
+    _lib.check(lib.glnn_sage_inference_host(keep[0].ctypes.data, keep[1].ctypes.data, n,
+                                            keep[2].ctypes.data, arr, L, 1e-5, out.ctypes.data),
+               "glnn_sage_inference_host")
+    assert relerr(out, d["out"]) < TOL
+
+
+def test_full_size_products_properties(dev):
+    """ogbn-products-sized synthetic graph (2,449,029 nodes, 123.7M edges): linearity, column-sum
+    checksum and exact sampled rows of the aggregation kernel."""
+    from glnn_b200 import ops
+    from glnn_b200.workloads import synthetic_graph
+    n, d = 2449029, 48
+    g = synthetic_graph(n, 61859140, mirror=True, self_loops=False, device=dev, seed=0)
+    assert g.num_edges() == 123718280
+    gen = torch.Generator(device=dev).manual_seed(0)
+    x = torch.randn(n, d, device=dev, generator=gen)
+    y = torch.randn(n, d, device=dev, generator=gen)
+    ax = ops.spmm_csr(g.indptr, g.indices, x)
+    ay = ops.spmm_csr(g.indptr, g.indices, y)
+    axy = ops.spmm_csr(g.indptr, g.indices, 2.0 * x - 3.0 * y)
+    assert relerr(axy, 2.0 * ax - 3.0 * ay) < 1e-5
+    # checksum: sum_v (A x)[v] = sum_u out_deg(u) x[u]
+    lhs = ax.double().sum(0)
+    rhs = (g.out_degrees().double().unsqueeze(1) * x.double()).sum(0)
+    assert relerr(lhs, rhs) < 1e-6
+    # exact rows, including the heaviest hub
+    deg = g.in_degrees()
+    rows = torch.cat([deg.argmax().view(1), torch.randint(0, n, (256,), device=dev)])
+    ip = g.indptr.long()
+    for r in rows.tolist():
+        nb = g.indices[ip[r]:ip[r + 1]].long()
+        want = x[nb].double().sum(0)
+        assert relerr(ax[r], want) < 1e-5
+    # SAGE epilogue at full size: mean over (neighbours + self)
+    m = ops.spmm_csr(g.indptr, g.indices, x, self_add=True, mean_plus_one=True)
+    want = (ax.double() + x.double()) / (deg.double().unsqueeze(1) + 1)
+    assert relerr(m, want) < 1e-5
