@@ -24,6 +24,6 @@ struct GemmArgs {
 };
 
 int gemm_simt(GemmArgs g, cudaStream_t st);                    // gemm_simt.cu
-int gemm_tc(const GemmArgs& g, cudaStream_t st, bool* taken);  // gemm_tc.cu
+int gemm_tc(const GemmArgs& g, cudaStream_t st, bool force, bool* taken);  // gemm_tc.cu
 
 }  // namespace glnn

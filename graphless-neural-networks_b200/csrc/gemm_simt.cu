@@ -249,7 +249,7 @@ extern "C" int glnn_gemm_f32(const float* A, int64_t lda, int transA, const floa
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl != 1) {
     bool taken = false;
-    int rc = gemm_tc(g, st, &taken);
+    int rc = gemm_tc(g, st, impl == 2, &taken);
     if (rc != 0) return rc;
     if (taken) return 0;
     GLNN_REQUIRE(impl != 2, GLNN_ERR_SHAPE, "gemm: shape not eligible for the tcgen05 path");

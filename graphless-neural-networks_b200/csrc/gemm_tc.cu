@@ -8,15 +8,17 @@
 // the tf32 rate).  glnn_gemm_f32(impl=1) keeps the exact fp32 SIMT kernel as the anchor.
 //
 // Structure (one 128 x BN output tile per CTA, BK = 64 per stage, ring of stages):
-//   warps 0-7  producers: coalesced 16-byte global loads of the fp32 A/B tiles, split into hi/lo in
+//   warps 0-15 producers: coalesced 16-byte global loads of the fp32 A/B tiles, split into hi/lo in
 //              registers, written to shared memory directly in the UMMA canonical SWIZZLE_128B
 //              layout (K-major or MN-major, whichever matches the operand's contiguous dimension, so
 //              no transposition is ever needed), fence.proxy.async, mbarrier arrive;
-//   warp 8     one elected thread issues tcgen05.mma (kind::f16, M=128, N=BN, K=16): 4 k-steps x 3
+//   warp 16    one elected thread issues tcgen05.mma (kind::f16, M=128, N=BN, K=16): 4 k-steps x 3
 //              products per stage, accumulator in TMEM; tcgen05.commit releases the stage;
-//   warps 0-7  epilogue: tcgen05.ld of the accumulator, row scale / bias / eval-BN affine / ReLU,
+//   warps 0-15 epilogue: tcgen05.ld of the accumulator, row scale / bias / eval-BN affine / ReLU,
 //              16-byte stores.
 #include <cuda_bf16.h>
+
+#include <cstdlib>
 
 #include "gemm.cuh"
 
@@ -25,7 +27,8 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 64;          // fp32 elements per stage along K (= one 128-byte swizzle atom of bf16)
-constexpr int NPROD = 256;      // producer threads (8 warps)
+constexpr int NPROD = 512;      // producer threads (16 warps)
+constexpr int NPWARPS = NPROD / 32;
 constexpr int NTHREADS = NPROD + 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -108,72 +111,62 @@ __device__ __forceinline__ float4 load4_guard(const float* p, int64_t i, int64_t
   return r;
 }
 
-// K-major operand tile: ROWS (m or n) x 64 k from a matrix whose k index is contiguous
-// (P[row * ld + k]).  smem: row r at r*128 B, 16-byte chunk c stored at chunk (c ^ (r & 7)).
-template <int ROWS>
-__device__ __forceinline__ void load_kmajor(const float* __restrict__ P, int64_t ld, int64_t row0,
-                                            int64_t rows, int64_t k0, int64_t kend, uint8_t* s_hi,
-                                            uint8_t* s_lo, int tid) {
-  const int l = tid & 15;            // float4 index within the 64-wide k slice
-  const int rbase = tid >> 4;        // 16 rows per pass
-  constexpr int ITER = ROWS / 16;
-#pragma unroll
-  for (int i0 = 0; i0 < ITER; i0 += 8) {
-    float4 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rbase + (i0 + i) * 16;
-      const int64_t row = row0 + r;
-      v[i] = (row < rows) ? load4_guard(P + row * ld, k0 + l * 4, kend)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int r = rbase + (i0 + i) * 16;
-      uint2 hi, lo;
-      split4(v[i], hi, lo);
-      const uint32_t off = r * 128 + (((l >> 1) ^ (r & 7)) << 4) + ((l & 1) << 3);
-      *reinterpret_cast<uint2*>(s_hi + off) = hi;
-      *reinterpret_cast<uint2*>(s_lo + off) = lo;
-    }
-  }
-}
+// Register-staged tile loader.  All 16-byte global loads of a stage are issued first (A and B
+// together: 12 independent loads per thread at BN = 256), then converted and stored, so that the
+// memory system sees the whole stage in flight at once.
+//
+// KMAJ = true : ROWS (m or n) x 64 k from a matrix whose k index is contiguous (P[row*ld + k]).
+//   smem: row r at r*128 B, 16-byte chunk c stored at chunk (c ^ (r & 7))       [K-major SW128]
+// KMAJ = false: 64 k x ROWS (m or n) from a matrix whose m/n index is contiguous (P[k*ld + col]).
+//   smem: 64-wide column block j at j*8192 B, k-group g (8 k) at g*1024 B, k row kk at kk*128 B,
+//   16-byte chunk c stored at chunk (c ^ kk)                                     [MN-major SW128]
+template <int ROWS, bool KMAJ>
+struct TileIO {
+  static constexpr int N4 = ROWS * (BK / 4) / NPROD;  // float4 per thread
+  static_assert(N4 >= 1 && (ROWS * (BK / 4)) % NPROD == 0, "tile / producer-count mismatch");
+  float4 v[N4];
 
-// MN-major operand tile: 64 k x COLS (m or n) from a matrix whose m/n index is contiguous
-// (P[k * ld + col]).  smem: 64-wide column block j at j*8192 B, k-group g (8 k) at g*1024 B,
-// k row kk at kk*128 B, 16-byte chunk c stored at chunk (c ^ kk).
-template <int COLS>
-__device__ __forceinline__ void load_mnmajor(const float* __restrict__ P, int64_t ld, int64_t col0,
-                                             int64_t cols, int64_t k0, int64_t kend, uint8_t* s_hi,
-                                             uint8_t* s_lo, int tid) {
-  constexpr int F4_PER_ROW = COLS / 4;           // 32 (COLS=128) or 64 (COLS=256)
-  constexpr int ROWS_PER_PASS = NPROD / F4_PER_ROW;
-  constexpr int ITER = BK / ROWS_PER_PASS;       // 8 or 16
-  const int l = tid % F4_PER_ROW;
-  const int kb = tid / F4_PER_ROW;
+  __device__ __forceinline__ void load(const float* __restrict__ P, int64_t ld, int64_t r0,
+                                       int64_t rows, int64_t k0, int64_t kend, int tid) {
 #pragma unroll
-  for (int i0 = 0; i0 < ITER; i0 += 8) {
-    float4 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int kk = kb + (i0 + i) * ROWS_PER_PASS;
-      const int64_t k = k0 + kk;
-      v[i] = (k < kend) ? load4_guard(P + k * ld, col0 + l * 4, cols)
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < N4; ++i) {
+      const int f = tid + i * NPROD;
+      if constexpr (KMAJ) {
+        const int r = f >> 4, l = f & 15;
+        const int64_t row = r0 + r;
+        v[i] = (row < rows) ? load4_guard(P + row * ld, k0 + l * 4, kend)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+        constexpr int F4 = ROWS / 4;
+        const int kk = f / F4, l = f % F4;
+        const int64_t k = k0 + kk;
+        v[i] = (k < kend) ? load4_guard(P + k * ld, r0 + l * 4, rows)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
+  }
+
+  __device__ __forceinline__ void store(uint8_t* s_hi, uint8_t* s_lo, int tid) const {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int kk = kb + (i0 + i) * ROWS_PER_PASS;
+    for (int i = 0; i < N4; ++i) {
+      const int f = tid + i * NPROD;
+      uint32_t off;
+      if constexpr (KMAJ) {
+        const int r = f >> 4, l = f & 15;
+        off = r * 128 + (((l >> 1) ^ (r & 7)) << 4) + ((l & 1) << 3);
+      } else {
+        constexpr int F4 = ROWS / 4;
+        const int kk = f / F4, l = f % F4;
+        const int j = l >> 4, c = (l & 15) >> 1, half = l & 1;
+        off = j * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + ((c ^ (kk & 7)) << 4) + (half << 3);
+      }
       uint2 hi, lo;
       split4(v[i], hi, lo);
-      const int j = l >> 4, c = (l & 15) >> 1, half = l & 1;
-      const uint32_t off = j * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + ((c ^ (kk & 7)) << 4) +
-                           (half << 3);
       *reinterpret_cast<uint2*>(s_hi + off) = hi;
       *reinterpret_cast<uint2*>(s_lo + off) = lo;
     }
   }
-}
+};
 
 template <int BN>
 struct Smem {
@@ -209,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
     mbar_init(accum, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == NPWARPS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
                  "r"(static_cast<uint32_t>(BN))
@@ -221,8 +214,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
+  if (warp < NPWARPS) {
     // ------------------------------- producers -------------------------------
+    TileIO<BM, A_K> ta;
+    TileIO<BN, B_K> tb;
+    ta.load(g.A, g.lda, m0, g.M, 0, g.K, tid);
+    tb.load(g.B, g.ldb, n0, g.N, 0, g.K, tid);
     for (int kb = 0; kb < nkb; ++kb) {
       const int s = kb % S::STAGES, it = kb / S::STAGES;
       if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
@@ -230,10 +227,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
       uint8_t *a_hi = st, *a_lo = st + S::A_BYTES, *b_hi = st + 2 * S::A_BYTES,
               *b_lo = st + 2 * S::A_BYTES + S::B_BYTES;
       const int64_t k0 = static_cast<int64_t>(kb) * BK;
-      if constexpr (A_K) load_kmajor<BM>(g.A, g.lda, m0, g.M, k0, g.K, a_hi, a_lo, tid);
-      else load_mnmajor<BM>(g.A, g.lda, m0, g.M, k0, g.K, a_hi, a_lo, tid);
-      if constexpr (B_K) load_kmajor<BN>(g.B, g.ldb, n0, g.N, k0, g.K, b_hi, b_lo, tid);
-      else load_mnmajor<BN>(g.B, g.ldb, n0, g.N, k0, g.K, b_hi, b_lo, tid);
+      ta.store(a_hi, a_lo, tid);
+      tb.store(b_hi, b_lo, tid);
+      if (kb + 1 < nkb) {  // next stage's loads go out before we signal this one
+        ta.load(g.A, g.lda, m0, g.M, k0 + BK, g.K, tid);
+        tb.load(g.B, g.ldb, n0, g.N, k0 + BK, g.K, tid);
+      }
       fence_proxy_async();
       mbar_arrive(&full[s]);
     }
@@ -266,17 +265,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
     umma_commit(accum);
   }
 
-  if (warp < 8) {
+  if (warp < NPWARPS) {
     // ------------------------------- epilogue -------------------------------
     mbar_wait(accum, 0);
     tc_fence_after();
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, part = warp >> 2;  // TMEM lane quarter, column part (4 parts)
     const int64_t m = m0 + q * 32 + lane;
     const float rs = (g.row_scale && m < g.M) ? __ldg(g.row_scale + m) : 1.f;
-    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int COLS_PER_WARP = BN / (NPWARPS / 4);
 #pragma unroll 1
     for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 16) {
-      const int col = half * COLS_PER_WARP + c0;
+      const int col = part * COLS_PER_WARP + c0;
       uint32_t r[16];
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + col;
       asm volatile(
@@ -318,7 +317,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == NPWARPS) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(static_cast<uint32_t>(BN))
                  : "memory");
@@ -353,16 +352,17 @@ static int launch_major(const GemmArgs& g, cudaStream_t st) {
 
 // Takes the shape when both operands can be read with aligned 16-byte loads along their contiguous
 // dimension and the problem is big enough for a 128-row tile to pay off.
-int gemm_tc(const GemmArgs& g0, cudaStream_t st, bool* taken) {
+int gemm_tc(const GemmArgs& g0, cudaStream_t st, bool force, bool* taken) {
   *taken = false;
   static const bool disabled = getenv("GLNN_NO_TC") != nullptr;
-  if (disabled) return 0;
+  if (disabled && !force) return 0;
   GemmArgs g = g0;
-  if (g.K < 1 || g.M < 64 || g.N < 8) return 0;
+  if (g.K < 1 || g.M < 1 || g.N < 1) return 0;
+  if (!force && (g.M < 64 || g.N < 8)) return 0;
   if (!aligned16(g.A) || !aligned16(g.B) || (g.lda % 4) != 0 || (g.ldb % 4) != 0) return 0;
   // the guarded tail loader needs the contiguous extent to be a multiple of 4 only for alignment of
   // the NEXT row, which lda/ldb % 4 already guarantees
-  if (2.0 * g.M * g.N * g.K < 2.0e8) return 0;  // tiny problems: launch-bound either way
+  if (!force && 2.0 * g.M * g.N * g.K < 2.0e8) return 0;  // tiny problems: launch-bound either way
   g.vecC = (g.ldc % 4 == 0) && aligned16(g.C);
   int rc;
   if (g.N > 128) rc = tc::launch_major<256>(g, st);

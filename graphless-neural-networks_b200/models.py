@@ -155,9 +155,10 @@ class SAGE(_Encoder):
                     output_dim, norm_type)
 
     def forward(self, blocks, feats):
-        raise NotImplementedError(
-            "SAGE.forward over sampled blocks (teacher training, train_and_eval.py:32-56) is a "
-            "'next' row of the hot-path scope (SURVEY.md section 8f)")
+        """Sampled-block forward used by teacher training (models.py:101-119); autograd runs over
+        the aggregation / projection kernels (teacher_train.py)."""
+        from . import teacher_train
+        return teacher_train.sage_forward_blocks(self, blocks, feats)
 
     def inference(self, data, feats, log_softmax=False):
         """Full-neighbour layer-wise inference for every node (models.py:121-148)."""

@@ -58,6 +58,16 @@ def student_masks(d, idx_perm_count, num_layers):
     return flat
 
 
+def relerr_q(a, b, q=0.999):
+    """q-quantile of |a-b| over max|b|: robust to the handful of Adam-amplified outliers (elements
+    whose gradient is at the rounding-noise level move by O(lr) under ANY change of summation
+    order, because the first Adam steps apply lr * g / (|g| + 1e-8))."""
+    a, b = torch.as_tensor(a).double().flatten(), torch.as_tensor(b).double().flatten()
+    d = (a - b).abs()
+    kth = max(1, int(round(q * d.numel())))
+    return float(d.kthvalue(kth).values / b.abs().max().clamp_min(1e-30))
+
+
 def relerr(a, b):
     a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))

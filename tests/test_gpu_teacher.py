@@ -143,6 +143,54 @@ def test_gemm_simt_vs_fp64(dev, m, n, k, ta, tb):
     assert relerr(got.cpu(), want) < 2e-6
 
 
+TC_SHAPES = [
+    (300, 256, 100, False, True), (1000, 48, 256, False, True), (4096, 2048, 128, False, True),
+    (516, 130, 36, True, True), (700, 200, 260, False, False), (2048, 100, 4096, True, False),
+    (256, 256, 4096, True, False), (132, 260, 68, True, False), (128, 128, 64, False, True),
+    (1, 8, 4, False, True), (2048, 2048, 2048, False, False),
+]
+
+
+@pytest.mark.parametrize("m,n,k,ta,tb", TC_SHAPES)
+def test_gemm_tcgen05_bf16x3_vs_fp64(dev, m, n, k, ta, tb):
+    """Tensor-core path (bf16x3 split, fp32 accumulate in TMEM) in all four operand-major
+    combinations; bound 3e-5 on max|err| / max|ref| (design estimate ~1e-5 worst case)."""
+    from glnn_b200 import ops
+    g = torch.Generator().manual_seed(m + 3 * n + k)
+    a = torch.randn((k, m) if ta else (m, k), generator=g)
+    b = torch.randn((n, k) if tb else (k, n), generator=g)
+    want = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
+    got = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb, impl=2)
+    assert relerr(got.cpu(), want) < 3e-5
+
+
+def test_gemm_tcgen05_declines_unaligned_operands(dev):
+    """Leading dimensions that are not 16-byte multiples cannot be read with vector loads: impl=2
+    refuses, impl=0 (auto) silently takes the exact SIMT kernel."""
+    from glnn_b200 import ops
+    a, b = torch.randn(513, 33, device=dev), torch.randn(130, 33, device=dev)
+    with pytest.raises(ValueError):
+        ops.gemm(a, b, trans_b=True, impl=2)
+    got = ops.gemm(a, b, trans_b=True, impl=0)
+    assert relerr(got.cpu(), a.double().cpu() @ b.double().cpu().t()) < 2e-6
+
+
+def test_gemm_tcgen05_epilogue_and_strides(dev):
+    from glnn_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    m, n, k = 777, 200, 132
+    a, b = torch.randn(m, 160, generator=g), torch.randn(n, 140, generator=g)
+    rs, bias = torch.rand(m, generator=g) + 0.5, torch.randn(n, generator=g)
+    cs, sh = torch.rand(n, generator=g) + 0.5, torch.randn(n, generator=g)
+    want = (a[:, :k].double() @ b[:, :k].double().t()) * rs.double().unsqueeze(1) + bias.double()
+    want = (want * cs.double() + sh.double()).clamp(min=0)
+    out = torch.full((m, 204), 7.0, device=dev)
+    ops.gemm(a.to(dev)[:, :k], b.to(dev)[:, :k], trans_b=True, out=out[:, :n], row_scale=rs.to(dev),
+             bias=bias.to(dev), col_scale=cs.to(dev), col_shift=sh.to(dev), relu=1, impl=2)
+    assert relerr(out[:, :n].cpu(), want) < 3e-5
+    assert bool((out[:, n:] == 7.0).all())
+
+
 @pytest.mark.parametrize("relu", [0, 1, 2])
 def test_gemm_epilogue(dev, relu):
     from glnn_b200 import ops
