@@ -90,10 +90,23 @@ def _pad_rows(w, b, dpad):
     return wp, bp
 
 
+def _buffer(sg, key, rows, cols, like):
+    """Per-shard cache of activation buffers: a forward reuses the same HBM every call (no
+    allocator traffic, no memsets of multi-GB tensors inside the timed region).  Pad rows are never
+    read by the gathers (no column id points at them), so their content is irrelevant."""
+    cache = sg.__dict__.setdefault("_bufs", {})
+    t = cache.get(key)
+    if t is None or t.shape != (rows, cols) or t.device != like.device or t.dtype != like.dtype:
+        t = torch.zeros(rows, cols, dtype=like.dtype, device=like.device)
+        cache[key] = t
+    return t
+
+
 def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None, log_softmax=True):
     """layers: [(W [out,in], b)], norms: [(scale, shift)] folded eval-BN per hidden layer (or []).
     feats_pad: padded replica of the input features (valid on every rank).  Returns the padded
-    replica [world * rows_max, label_dim] of the output (log-probabilities when log_softmax).
+    replica [world * rows_max, label_dim] of the output (log-probabilities when log_softmax); the
+    returned tensor is a cached buffer that the next call overwrites.
 
     Exchange plan: an aggregate-first layer needs the full replica of its input (all-gather of the
     previous output, d_in wide); a project-first layer (4-padded d_out < d_in) projects only the
@@ -105,8 +118,8 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
     lo, hi = sg.rank * rm, sg.rank * rm + sg.rows
 
     def gather(buf):
-        if world > 1:
-            dist.all_gather_into_tensor(buf, buf[lo: lo + rm].clone(), group=group)
+        if world > 1:  # in place: this rank's slab already sits at its offset in the output
+            dist.all_gather_into_tensor(buf, buf[lo: lo + rm], group=group)
 
     h, h_full = feats_pad, True
     L = len(layers)
@@ -118,22 +131,24 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
         dpad = (d_out + 3) // 4 * 4
         if dpad < d_in and (scale is None or dpad == d_out):
             wp, bp = _pad_rows(w, b, dpad)
-            z = torch.zeros(world * rm, dpad, dtype=h.dtype, device=h.device)
+            z = _buffer(sg, ("z", l), world * rm, dpad, h)
             k.gemm(h[lo:hi, :d_in], wp, trans_b=True, out=z[lo:hi])
             gather(z)
-            y = torch.zeros(world * rm, dpad, dtype=h.dtype, device=h.device)
+            y = _buffer(sg, ("y", l), world * rm, dpad, h)
             k.spmm_csr(sg.indptr, sg.indices, z, d=dpad, out=y[lo:hi], dst_scale=sg.inv_deg1,
                        bias=bp, col_scale=scale, col_shift=shift, relu=relu)
         else:
             if not h_full:
                 gather(h)
-            agg = k.spmm_csr(sg.indptr, sg.indices, h, d=d_in, dst_scale=sg.inv_deg1)
-            y = torch.zeros(world * rm, dpad, dtype=h.dtype, device=h.device)
-            k.gemm(agg, w, trans_b=True, out=y[lo:hi, :d_out], bias=b, col_scale=scale,
-                   col_shift=shift, relu=relu)
+            agg = _buffer(sg, ("agg", l), max(sg.rows, 1), (d_in + 3) // 4 * 4, h)
+            k.spmm_csr(sg.indptr, sg.indices, h, d=d_in, out=agg[: sg.rows, :d_in],
+                       dst_scale=sg.inv_deg1)
+            y = _buffer(sg, ("y", l), world * rm, dpad, h)
+            k.gemm(agg[: sg.rows, :d_in], w, trans_b=True, out=y[lo:hi, :d_out], bias=b,
+                   col_scale=scale, col_shift=shift, relu=relu)
         h, h_full = y, False
     c = layers[-1][0].shape[0]
-    out = torch.zeros(world * rm, c, dtype=h.dtype, device=h.device)
+    out = _buffer(sg, ("out",), world * rm, c, h)
     if log_softmax:
         k.log_softmax(h[lo:hi, :c], out=out[lo:hi])
     else:

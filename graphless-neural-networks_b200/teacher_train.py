@@ -49,7 +49,7 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, w, b, weight_is_out_in):
         x = x.contiguous()
         ctx.save_for_backward(x, w)
-        ctx.oi = weight_is_out_in
+        ctx.oi, ctx.has_bias = weight_is_out_in, b is not None
         return ops.gemm(x, w, trans_b=weight_is_out_in, bias=b)
 
     @staticmethod
@@ -62,7 +62,7 @@ class _Linear(torch.autograd.Function):
         else:       # y = x W   : dx = dy W^T, dW = x^T dy
             dx = ops.gemm(dy, w, trans_b=True)
             dw = ops.gemm(x, dy, trans_a=True)
-        return dx, dw, dy.sum(0), None
+        return dx, dw, (dy.sum(0) if ctx.has_bias else None), None
 
 
 def _transpose_csr(indptr, indices, n_src):
