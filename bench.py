@@ -205,52 +205,68 @@ def _event_ms(fn, iters, torch):
 
 
 def teacher_kernel_breakdown(g, feats, model, iters, torch):
-    """Per-kernel CUDA-event times of one forward, launched through the same C-ABI calls and in the
-    same order as glnn_sage_forward (aggregate-first / project-first plan included)."""
+    """Per-stage CUDA-event times of one forward, launched through the same C-ABI calls, in the same
+    order and with the same operand formats as glnn_sage_forward (csrc/teacher.cu): aggregate-first
+    layers gather straight into bf16 hi/lo planes and project on tcgen05; a project-first layer
+    projects planes and gathers the narrow result with the epilogue fused."""
     from glnn_b200 import ops
     n, e = g.num_nodes(), g.num_edges()
     enc = model.encoder
     L = enc.num_layers
+    pf = [((c.fc_neigh.weight.shape[0] + 3) // 4 * 4) < c.fc_neigh.weight.shape[1] for c in enc.layers]
     rows = []
-    h = feats
+    h = feats            # fp32 tensor or ops.Planes
+    idx_bytes = 4 * (n + 1) + 4 * e
     for l, conv in enumerate(enc.layers):
-        w, b = conv.fc_neigh.weight, conv.fc_neigh.bias
+        w, b = conv.fc_neigh.weight.detach(), conv.fc_neigh.bias.detach()
         d_out, d_in = w.shape
         dpad = (d_out + 3) // 4 * 4
         last = l == L - 1
+        out_planes = (not last) and pf[l + 1]
         scale = shift = None
         if not last and enc.norm_type == "batch":
             bn = enc.norms[l]
             scale, shift = ops.bn_fold(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
         relu = 0 if last else 1
-        idx_bytes = 4 * (n + 1) + 4 * e
-        if dpad < d_in:
+        if pf[l]:
             wp = torch.zeros(dpad, d_in, device=w.device)
-            wp[:d_out] = w.detach()
+            wp[:d_out] = w
             bp = torch.zeros(dpad, device=w.device)
-            bp[:d_out] = b.detach()
+            bp[:d_out] = b
+            wpl = ops.split_planes(wp)
+            hp = h if isinstance(h, ops.Planes) else ops.split_planes(h)
             z = torch.empty(n, dpad, device=w.device)
-            y = torch.empty(n, dpad, device=w.device)
-            t = _event_ms(lambda: ops.gemm(h, wp, trans_b=True, out=z), iters, torch)
-            rows.append((f"L{l} gemm {d_in}->{dpad} (project first)", t,
+            t = _event_ms(lambda: ops.gemm_planes(hp, wpl, trans_b=True, out=z), iters, torch)
+            rows.append((f"L{l} gemm {d_in}->{dpad} (project first, tcgen05 bf16x3)", t,
                          4 * n * (d_in + dpad) + 4 * d_in * dpad, 2.0 * n * d_in * dpad, "gemm"))
+            y = torch.empty(n, dpad, device=w.device)
             t = _event_ms(lambda: ops.spmm_csr(g.indptr, g.indices, z, out=y, self_add=True,
                                                mean_plus_one=True, bias=bp, col_scale=scale,
                                                col_shift=shift, relu=relu), iters, torch)
-            rows.append((f"L{l} spmm d={dpad}", t, idx_bytes + 8 * n * dpad, 2.0 * e * dpad, "spmm"))
-            h = y[:, :d_out] if last else y
-        else:
-            a = torch.empty(n, (d_in + 3) // 4 * 4, device=w.device)
-            y = torch.empty(n, dpad, device=w.device)
-            t = _event_ms(lambda: ops.spmm_csr(g.indptr, g.indices, h, d=d_in, out=a[:, :d_in],
-                                               self_add=True, mean_plus_one=True), iters, torch)
-            rows.append((f"L{l} spmm d={d_in}", t, idx_bytes + 8 * n * d_in, 2.0 * e * d_in, "spmm"))
-            t = _event_ms(lambda: ops.gemm(a[:, :d_in], w.detach(), trans_b=True, out=y[:, :d_out],
-                                           bias=b.detach(), col_scale=scale, col_shift=shift,
-                                           relu=relu), iters, torch)
-            rows.append((f"L{l} gemm {d_in}->{d_out}", t, 4 * n * (d_in + d_out) + 4 * d_in * d_out,
-                         2.0 * n * d_in * d_out, "gemm"))
+            rows.append((f"L{l} spmm d={dpad} (+bias epilogue)", t, idx_bytes + 8 * n * dpad,
+                         2.0 * e * dpad, "spmm"))
             h = y[:, :d_out]
+        else:
+            tp = ops.spmm_csr_planes(g.indptr, g.indices, h, d=d_in, self_add=True, mean_plus_one=True)
+            t = _event_ms(lambda: ops.spmm_csr_planes(g.indptr, g.indices, h, d=d_in, self_add=True,
+                                                      mean_plus_one=True, out=tp), iters, torch)
+            rows.append((f"L{l} spmm d={d_in} (-> planes)", t, idx_bytes + 8 * n * d_in,
+                         2.0 * e * d_in, "spmm"))
+            wpl = ops.split_planes(w)
+            if out_planes:
+                t = _event_ms(lambda: ops.gemm_planes(tp, wpl, trans_b=True, out_planes=True, bias=b,
+                                                      col_scale=scale, col_shift=shift, relu=relu),
+                              iters, torch)
+                h = ops.gemm_planes(tp, wpl, trans_b=True, out_planes=True, bias=b, col_scale=scale,
+                                    col_shift=shift, relu=relu)
+            else:
+                y = torch.empty(n, dpad, device=w.device)
+                t = _event_ms(lambda: ops.gemm_planes(tp, wpl, trans_b=True, out=y[:, :d_out], bias=b,
+                                                      col_scale=scale, col_shift=shift, relu=relu),
+                              iters, torch)
+                h = y[:, :d_out]
+            rows.append((f"L{l} gemm {d_in}->{d_out} (tcgen05 bf16x3, +BN+ReLU)", t,
+                         4 * n * (d_in + d_out) + 4 * d_in * d_out, 2.0 * n * d_in * d_out, "gemm"))
     out = torch.empty(n, h.shape[1], device=feats.device)
     t = _event_ms(lambda: ops.log_softmax(h, out=out), iters, torch)
     rows.append(("log_softmax", t, 8 * n * h.shape[1], 0.0, "rowwise"))
@@ -281,7 +297,7 @@ def student_step_rate(dev, torch, steps=20, warmup=3):
     return {"config": "MLP3w8 100-2048-2048-47 bs4096 KL+Adam step (ogbn-products student)",
             "value": bs / (per_step * 1e-3), "unit": "nodes/s", "ms_per_step": per_step,
             "tflops": flops / (per_step * 1e-3) / 1e12, "params": P,
-            "launches_per_step": 21}
+            "launches_per_step": 23}
 
 
 def run_b200(args):
@@ -318,7 +334,9 @@ def run_b200(args):
         def step():
             with torch.no_grad():
                 return model.encoder.inference(loader, feats, log_softmax=True)
-        launches_per_step = 3 + 3 + 1 + 2  # 3 aggregation + 3 projection + log_softmax + 2 bn_fold
+        # 3 aggregations x (main + hub drain + hub finish) + 3 projections + 3 weight splits +
+        # log_softmax + 2 bn_fold
+        launches_per_step = 9 + 3 + 3 + 1 + 2
     else:
         sg = DT.ShardedGraph(g, rank, world)
         feats_pad = sg.to_padded(feats)
@@ -357,6 +375,15 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
 
+    if world > 1:  # per-phase device times of one sharded forward on every rank (diagnostic)
+        tm = []
+        with torch.no_grad():
+            DT.sage_forward_sharded(sg, feats_pad, layers, norms, timings=tm)
+        torch.cuda.synchronize()
+        phases = [(tm[i][0], round(tm[i - 1][1].elapsed_time(tm[i][1]), 3)) for i in range(1, len(tm))]
+        info = {"rank": rank, "rows": sg.rows, "nnz": int(sg.indices.numel()), "phases_ms": phases}
+        gathered = [None] * world
+        dist.all_gather_object(gathered, info)
     if args.light:
         if rank == 0:
             clocks.stop()
@@ -369,21 +396,20 @@ def run_b200(args):
 
     # end-to-end: host (pinned) CSR + features in, host log-probabilities out, every step
     if world == 1:
+        from glnn_b200.pipeline import HostTeacherPipeline
         h_indptr, h_indices = g.indptr.cpu().pin_memory(), g.indices.cpu().pin_memory()
         h_feats = feats.cpu().pin_memory()
-        d_indptr, d_indices = torch.empty_like(g.indptr), torch.empty_like(g.indices)
-        d_feats = torch.empty_like(feats)
-        h_out = torch.empty(n, dims[3]).pin_memory()
-        g2 = G.CSRGraph(d_indptr, d_indices, n)
-        loader2 = G.FullNeighborLoader(g2)
+        h_outs = [torch.empty(n, dims[3]).pin_memory() for _ in range(2)]
+        h_out = h_outs[0]
+        pipe = HostTeacherPipeline(model.encoder, n, g.indptr, g.indices, dims[0], dims[3], dev)
 
         def e2e_step():
-            d_indptr.copy_(h_indptr, non_blocking=True)
-            d_indices.copy_(h_indices, non_blocking=True)
-            d_feats.copy_(h_feats, non_blocking=True)
-            with torch.no_grad():
-                o = model.encoder.inference(loader2, d_feats, log_softmax=True)
-            h_out.copy_(o, non_blocking=True)
+            # every step uploads its CSR + features and downloads its log-probabilities; uploads /
+            # downloads of neighbouring steps overlap with compute on copy streams
+            pipe.submit(h_indptr, h_indices, h_feats, h_outs[pipe.step % 2])
+
+        def e2e_drain():
+            pipe.drain()
         h2d = h_indptr.numel() * h_indptr.element_size() + h_indices.numel() * 4 + h_feats.numel() * 4
     else:
         h_ptr, h_idx = sg.indptr.cpu().pin_memory(), sg.indices.cpu().pin_memory()
@@ -403,12 +429,17 @@ def run_b200(args):
                 o = DT.sage_forward_sharded(sg, d_feats, layers, norms)
             sg.indptr, sg.indices = keep
             h_out.copy_(o[lo: lo + sg.rows], non_blocking=True)
+
+        def e2e_drain():
+            pass
         h2d = h_ptr.numel() * h_ptr.element_size() + h_idx.numel() * 4 + h_feats.numel() * 4
     e2e_step()
+    e2e_drain()
     barrier()
     ev0.record()
     for _ in range(args.steps):
         e2e_step()
+    e2e_drain()
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
@@ -436,10 +467,14 @@ def run_b200(args):
                    "l2": "inputs (features 0.98 GB, CSR 0.5 GB, activations 2.5 GB) far exceed the "
                          "126 MB L2; no flush needed"},
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "nodes/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_out.numel() * 4)},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_out.numel() * 4),
+                "overlap": ("copy streams: step i+1 upload / step i-1 download overlap step i compute "
+                            "(2 device input slots)") if world == 1 else "none (serial per step)"},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk,
     }
+    if world > 1:
+        line["shards"] = gathered
 
     if world == 1:
         rows = teacher_kernel_breakdown(g, feats, model, max(3, min(args.steps, 10)), torch)

@@ -21,9 +21,16 @@ struct GemmArgs {
   int relu;
   int vecA, vecB, vecC;
   int k_per_split;  // multiple of BK
+  // --- tensor-core "planes" mode: operands already split into bf16 hi / lo planes (same leading
+  // dimensions lda / ldb, in elements); optional plane output of C; split-K over k-blocks ---
+  const uint16_t *Ah, *Al, *Bh, *Bl;
+  uint16_t *Ch, *Cl;
+  int64_t ldcp;
+  int kb_per_split;
 };
 
 int gemm_simt(GemmArgs g, cudaStream_t st);                    // gemm_simt.cu
 int gemm_tc(const GemmArgs& g, cudaStream_t st, bool force, bool* taken);  // gemm_tc.cu
+int gemm_tc_planes(GemmArgs g, cudaStream_t st);                             // gemm_tc.cu
 
 }  // namespace glnn

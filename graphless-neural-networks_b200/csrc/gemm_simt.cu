@@ -246,6 +246,10 @@ extern "C" int glnn_gemm_f32(const float* A, int64_t lda, int transA, const floa
   g.relu = relu;
   g.vecA = g.vecB = g.vecC = 0;
   g.k_per_split = 0;
+  g.Ah = g.Al = g.Bh = g.Bl = nullptr;
+  g.Ch = g.Cl = nullptr;
+  g.ldcp = 0;
+  g.kb_per_split = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl != 1) {
     bool taken = false;

@@ -18,6 +18,7 @@
 //              16-byte stores.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "gemm.cuh"
@@ -168,6 +169,56 @@ struct TileIO {
   }
 };
 
+__device__ __forceinline__ void cp_async16(uint8_t* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Planes mode: the operand already exists as two bf16 planes, so a stage is filled by 16-byte
+// cp.async copies (zero-filled past the matrix edge) that land directly at their swizzled position
+// -- no registers, no conversion, a whole stage in flight per thread group.
+template <int ROWS, bool KMAJ>
+__device__ __forceinline__ void copy_planes(const uint16_t* __restrict__ hi,
+                                            const uint16_t* __restrict__ lo, int64_t ld, int64_t r0,
+                                            int64_t rows, int64_t k0, int64_t kend, uint8_t* s_hi,
+                                            uint8_t* s_lo, int tid) {
+  constexpr int NC = ROWS * 8 / NPROD;  // 16-byte chunks per thread and plane
+  static_assert(NC >= 1, "tile too small for the producer count");
+#pragma unroll
+  for (int i = 0; i < NC; ++i) {
+    const int f = tid + i * NPROD;
+    int64_t src;
+    int valid;
+    uint32_t off;
+    if constexpr (KMAJ) {
+      const int r = f >> 3, c = f & 7;
+      const int64_t row = r0 + r, k = k0 + c * 8;
+      valid = (row < rows) ? static_cast<int>(max(static_cast<long long>(0),
+                                 min(static_cast<long long>(8), static_cast<long long>(kend - k)))) : 0;
+      src = row * ld + k;
+      off = r * 128 + ((c ^ (r & 7)) << 4);
+    } else {
+      constexpr int CH = ROWS / 8;  // chunks per k row
+      const int kk = f / CH, ci = f % CH;
+      const int64_t k = k0 + kk, col = r0 + ci * 8;
+      valid = (k < kend) ? static_cast<int>(max(static_cast<long long>(0),
+                               min(static_cast<long long>(8), static_cast<long long>(rows - col)))) : 0;
+      src = k * ld + col;
+      const int j = ci >> 3, c = ci & 7;
+      off = j * 8192 + (kk >> 3) * 1024 + (kk & 7) * 128 + ((c ^ (kk & 7)) << 4);
+    }
+    if (valid <= 0) src = 0;
+    cp_async16(s_hi + off, hi + src, static_cast<uint32_t>(valid * 2));
+    cp_async16(s_lo + off, lo + src, static_cast<uint32_t>(valid * 2));
+  }
+}
+
 template <int BN>
 struct Smem {
   static constexpr int A_BYTES = BM * BK * 2;   // one bf16 plane
@@ -177,7 +228,7 @@ struct Smem {
   static constexpr int TOTAL = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, bool A_K, bool B_K>
+template <int BN, bool A_K, bool B_K, bool PLANES, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs g) {
   using S = Smem<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -192,7 +243,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m0 = static_cast<int64_t>(blockIdx.x) * BM;
   const int64_t n0 = static_cast<int64_t>(blockIdx.y) * BN;
-  const int nkb = static_cast<int>((g.K + BK - 1) / BK);
+  const int nkb_total = static_cast<int>((g.K + BK - 1) / BK);
+  const int kb0 = SPLIT ? static_cast<int>(blockIdx.z) * g.kb_per_split : 0;
+  const int nkb = SPLIT ? min(nkb_total, kb0 + g.kb_per_split) - kb0 : nkb_total;
 
   if (tid == 0) {
     for (int s = 0; s < S::STAGES; ++s) {
@@ -216,6 +269,26 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
 
   if (warp < NPWARPS) {
     // ------------------------------- producers -------------------------------
+    if constexpr (PLANES) {
+      for (int i = 0; i < nkb; ++i) {
+        if (i >= S::STAGES - 1) {  // the oldest stage in flight has landed: hand it to the MMA warp
+          cp_async_wait<S::STAGES - 2>();
+          fence_proxy_async();
+          mbar_arrive(&full[(i - (S::STAGES - 1)) % S::STAGES]);
+        }
+        const int s = i % S::STAGES, it = i / S::STAGES;
+        if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+        uint8_t* st = tiles + s * S::STAGE;
+        const int64_t k0 = static_cast<int64_t>(kb0 + i) * BK;
+        copy_planes<BM, A_K>(g.Ah, g.Al, g.lda, m0, g.M, k0, g.K, st, st + S::A_BYTES, tid);
+        copy_planes<BN, B_K>(g.Bh, g.Bl, g.ldb, n0, g.N, k0, g.K, st + 2 * S::A_BYTES,
+                             st + 2 * S::A_BYTES + S::B_BYTES, tid);
+        cp_async_commit();
+      }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      for (int i = max(0, nkb - (S::STAGES - 1)); i < nkb; ++i) mbar_arrive(&full[i % S::STAGES]);
+    } else {
     TileIO<BM, A_K> ta;
     TileIO<BN, B_K> tb;
     ta.load(g.A, g.lda, m0, g.M, 0, g.K, tid);
@@ -235,6 +308,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
+    }
     }
   } else if (lane == 0) {
     // ------------------------------- MMA issuer -------------------------------
@@ -256,7 +330,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
 #pragma unroll
       for (int k = 0; k < BK / 16; ++k) {
         const uint64_t da = static_cast<uint64_t>(k * a_step), db = static_cast<uint64_t>(k * b_step);
-        umma_bf16(tmem_base, a_hi + da, b_hi + db, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_bf16(tmem_base, a_hi + da, b_hi + db, idesc, (kb | k) != 0 ? 1u : 0u);  // kb is slice-local
         umma_bf16(tmem_base, a_hi + da, b_lo + db, idesc, 1u);
         umma_bf16(tmem_base, a_lo + da, b_hi + db, idesc, 1u);
       }
@@ -286,30 +360,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
             "=r"(r[14]), "=r"(r[15])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < g.M) {
-        float* cp = g.C + m * g.ldc + n0 + col;
+      // epilogue math in registers: row scale, bias, (ReLU) affine (ReLU)
+      float o[16];
+      const bool lead = !SPLIT || blockIdx.z == 0;
 #pragma unroll
-        for (int j4 = 0; j4 < 16; j4 += 4) {
-          float o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int64_t n = n0 + col + j4 + j;
-            float x = __uint_as_float(r[j4 + j]) * rs;
-            if (n < g.N) {
-              if (g.bias) x += __ldg(g.bias + n);
-              if (g.relu == 2) x = fmaxf(x, 0.f);
-              if (g.col_scale) x = fmaf(x, __ldg(g.col_scale + n), __ldg(g.col_shift + n));
-              if (g.relu == 1) x = fmaxf(x, 0.f);
-            }
-            o[j] = x;
+      for (int j = 0; j < 16; ++j) {
+        const int64_t n = n0 + col + j;
+        float x = __uint_as_float(r[j]) * rs;
+        if (n < g.N) {
+          if (g.bias && lead) x += __ldg(g.bias + n);
+          if constexpr (!SPLIT) {
+            if (g.relu == 2) x = fmaxf(x, 0.f);
+            if (g.col_scale) x = fmaf(x, __ldg(g.col_scale + n), __ldg(g.col_shift + n));
+            if (g.relu == 1) x = fmaxf(x, 0.f);
           }
-          const int64_t nb = n0 + col + j4;
-          if (g.vecC && nb + 3 < g.N) {
-            *reinterpret_cast<float4*>(cp + j4) = make_float4(o[0], o[1], o[2], o[3]);
-          } else {
+        }
+        o[j] = x;
+      }
+      if constexpr (SPLIT) {
+        if (m < g.M) {
+          float* cp = g.C + m * g.ldc + n0 + col;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (nb + j < g.N) cp[j4 + j] = o[j];
+          for (int j = 0; j < 16; ++j)
+            if (n0 + col + j < g.N) atomicAdd(cp + j, o[j]);
+        }
+      } else {
+        // stage the tile in shared memory (the operand ring is free: every MMA has completed) so
+        // that global stores are full coalesced rows instead of one 16-byte piece per row
+        float* cs = reinterpret_cast<float*>(tiles) + (q * 32 + lane) * (BN + 4) + col;
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4)
+          *reinterpret_cast<float4*>(cs + j4) = make_float4(o[j4], o[j4 + 1], o[j4 + 2], o[j4 + 3]);
+      }
+    }
+    if constexpr (!SPLIT) {
+      asm volatile("bar.sync 1, %0;" ::"n"(NPROD) : "memory");
+      const float* cs = reinterpret_cast<const float*>(tiles);
+      for (int rr = warp; rr < BM; rr += NPWARPS) {
+        const int64_t mr = m0 + rr;
+        if (mr >= g.M) break;
+#pragma unroll
+        for (int c4 = lane; c4 < BN / 4; c4 += 32) {
+          const int64_t n = n0 + c4 * 4;
+          if (n >= g.N) continue;
+          const float4 v = *reinterpret_cast<const float4*>(cs + rr * (BN + 4) + c4 * 4);
+          if (g.C) {
+            float* cp = g.C + mr * g.ldc + n;
+            if (g.vecC && n + 3 < g.N) {
+              *reinterpret_cast<float4*>(cp) = v;
+            } else {
+              cp[0] = v.x;
+              if (n + 1 < g.N) cp[1] = v.y;
+              if (n + 2 < g.N) cp[2] = v.z;
+              if (n + 3 < g.N) cp[3] = v.w;
+            }
+          }
+          if (g.Ch && n + 3 < g.ldcp) {  // bf16 hi / lo planes of C (pad columns hold 0)
+            uint2 hi, lo;
+            split4(v, hi, lo);
+            *reinterpret_cast<uint2*>(g.Ch + mr * g.ldcp + n) = hi;
+            *reinterpret_cast<uint2*>(g.Cl + mr * g.ldcp + n) = lo;
           }
         }
       }
@@ -324,28 +434,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
   }
 }
 
-template <int BN, bool A_K, bool B_K>
-static int launch(const GemmArgs& g, cudaStream_t st) {
+template <int BN, bool A_K, bool B_K, bool PLANES, bool SPLIT>
+static int launch(const GemmArgs& g, int splits, cudaStream_t st) {
   using S = Smem<BN>;
   static bool configured = false;
-  auto kern = gemm_bf16x3_kernel<BN, A_K, B_K>;
+  auto kern = gemm_bf16x3_kernel<BN, A_K, B_K, PLANES, SPLIT>;
   if (!configured) {
     GLNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
-  dim3 grid(static_cast<unsigned>((g.M + BM - 1) / BM), static_cast<unsigned>((g.N + BN - 1) / BN));
+  dim3 grid(static_cast<unsigned>((g.M + BM - 1) / BM), static_cast<unsigned>((g.N + BN - 1) / BN),
+            static_cast<unsigned>(splits));
   kern<<<grid, NTHREADS, S::TOTAL, st>>>(g);
   GLNN_LAUNCH_OK("gemm_bf16x3_kernel");
   return 0;
 }
 
-template <int BN>
-static int launch_major(const GemmArgs& g, cudaStream_t st) {
+template <int BN, bool PLANES, bool SPLIT>
+static int launch_major(const GemmArgs& g, int splits, cudaStream_t st) {
   const bool a_k = !g.transA, b_k = g.transB;
-  if (a_k && b_k) return launch<BN, true, true>(g, st);
-  if (a_k && !b_k) return launch<BN, true, false>(g, st);
-  if (!a_k && b_k) return launch<BN, false, true>(g, st);
-  return launch<BN, false, false>(g, st);
+  if (a_k && b_k) return launch<BN, true, true, PLANES, SPLIT>(g, splits, st);
+  if (a_k && !b_k) return launch<BN, true, false, PLANES, SPLIT>(g, splits, st);
+  if (!a_k && b_k) return launch<BN, false, true, PLANES, SPLIT>(g, splits, st);
+  return launch<BN, false, false, PLANES, SPLIT>(g, splits, st);
 }
 
 }  // namespace tc
@@ -365,11 +476,48 @@ int gemm_tc(const GemmArgs& g0, cudaStream_t st, bool force, bool* taken) {
   if (!force && 2.0 * g.M * g.N * g.K < 2.0e8) return 0;  // tiny problems: launch-bound either way
   g.vecC = (g.ldc % 4 == 0) && aligned16(g.C);
   int rc;
-  if (g.N > 128) rc = tc::launch_major<256>(g, st);
-  else rc = tc::launch_major<128>(g, st);
+  if (g.N > 128) rc = tc::launch_major<256, false, false>(g, 1, st);
+  else rc = tc::launch_major<128, false, false>(g, 1, st);
   if (rc != 0) return rc;
   *taken = true;
   return 0;
+}
+
+// Operands given as bf16 hi / lo planes.  Split-K (atomic accumulation into a zeroed fp32 C) is used
+// for skinny outputs with a long K (weight gradients), where one tile per CTA would leave most SMs
+// idle.
+int gemm_tc_planes(GemmArgs g, cudaStream_t st) {
+  GLNN_REQUIRE(g.Ah && g.Al && g.Bh && g.Bl, GLNN_ERR_ARG, "gemm_planes: null operand plane");
+  GLNN_REQUIRE(g.C || g.Ch, GLNN_ERR_ARG, "gemm_planes: no output");
+  GLNN_REQUIRE((g.Ch == nullptr) == (g.Cl == nullptr), GLNN_ERR_ARG, "gemm_planes: C planes come in pairs");
+  GLNN_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0 && aligned16(g.Ah) && aligned16(g.Al) &&
+                   aligned16(g.Bh) && aligned16(g.Bl),
+               GLNN_ERR_ALIGN, "gemm_planes: operand planes need 16-byte aligned rows (ld %% 8 == 0)");
+  GLNN_REQUIRE(!g.Ch || (g.ldcp % 4 == 0 && g.ldcp >= g.N), GLNN_ERR_ALIGN, "gemm_planes: bad ldcp");
+  g.vecC = g.C && (g.ldc % 4 == 0) && aligned16(g.C);
+  const int bn = g.N > 128 ? 256 : 128;
+  const int64_t tiles = ((g.M + tc::BM - 1) / tc::BM) * ((g.N + bn - 1) / bn);
+  const int nkb = static_cast<int>((g.K + tc::BK - 1) / tc::BK);
+  int splits = 1;
+  const bool linear = !g.relu && !g.col_scale && !g.Ch && g.C;
+  if (linear && tiles * 2 <= sm_count() && nkb >= 16) {
+    splits = static_cast<int>(std::min<int64_t>((sm_count() + tiles - 1) / tiles, nkb / 4));
+    if (splits < 1) splits = 1;
+  }
+  if (splits > 1) {
+    g.kb_per_split = (nkb + splits - 1) / splits;
+    splits = (nkb + g.kb_per_split - 1) / g.kb_per_split;
+    if (g.ldc == g.N) {
+      GLNN_CUDA_OK(cudaMemsetAsync(g.C, 0, sizeof(float) * g.M * g.N, st));
+    } else {
+      GLNN_CUDA_OK(cudaMemset2DAsync(g.C, sizeof(float) * g.ldc, 0, sizeof(float) * g.N, g.M, st));
+    }
+    return bn == 256 ? tc::launch_major<256, true, true>(g, splits, st)
+                     : tc::launch_major<128, true, true>(g, splits, st);
+  }
+  g.kb_per_split = 0;
+  return bn == 256 ? tc::launch_major<256, true, false>(g, 1, st)
+                   : tc::launch_major<128, true, false>(g, 1, st);
 }
 
 }  // namespace glnn

@@ -18,10 +18,15 @@
 #include <mutex>
 #include <vector>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "gemm.cuh"
 
 namespace glnn {
+
+int split_planes(const float* X, int64_t ldx, int64_t rows, int cols, uint16_t* hi, uint16_t* lo,
+                 int64_t ldp, cudaStream_t st);  // planes.cu
 
 struct PassParams {       // device-resident, rewritten once per pass
   const float* X;
@@ -69,12 +74,16 @@ static ParamLayout param_layout(const Dims& d) {
   return p;
 }
 
-// workspace carve-up (floats unless noted)
+// workspace carve-up (offsets in floats).  GEMM operands live as bf16 hi/lo plane pairs ("P" fields:
+// hi plane at the offset, lo plane right behind it, leading dimension pad8(width)); everything a
+// non-GEMM kernel reads stays fp32.
 struct WsLayout {
-  int64_t pp, ctr, xb, tgt, z[16], a[16], mean[16], invstd[16], logits, dlogits, dh[2], part, perm,
-      fold, total_bytes;
+  int64_t pp, ctr, xbP, tgt, z[16], aP[16], mean[16], invstd[16], logits, dlogP, dh[2], dzP, wP[16],
+      part, perm, fold, total_bytes;
   int rs;  // row splits of the column reductions
 };
+static inline int pad8(int d) { return (d + 7) / 8 * 8; }
+static inline int64_t plane_pair_floats(int64_t rows, int width) { return rows * pad8(width); }
 static int row_splits(const Dims& d) {
   const int col_tiles = std::max(1, (d.H + 31) / 32);
   int rs = (4 * 148 + col_tiles - 1) / col_tiles;
@@ -89,18 +98,20 @@ static WsLayout ws_layout(const Dims& d, bool train) {
   auto take = [&](int64_t floats) { int64_t r = o; o += up(floats); return r; };
   w.pp = take((sizeof(PassParams) + 3) / 4);
   w.ctr = take(4);
-  w.xb = take(d.R * d.F);
+  w.xbP = take(plane_pair_floats(d.R, d.F));
   w.tgt = take(std::max<int64_t>(d.R * d.C, 2 * d.R));
   for (int l = 0; l < d.L - 1; ++l) {
     w.z[l] = take(d.R * d.H);
-    w.a[l] = take(d.R * d.H);
+    w.aP[l] = take(plane_pair_floats(d.R, d.H));
     w.mean[l] = take(d.H);
     w.invstd[l] = take(d.H);
   }
   w.logits = take(d.R * d.C);
-  w.dlogits = take(d.R * d.C);
+  w.dlogP = take(plane_pair_floats(d.R, d.C));
   w.dh[0] = take(d.R * d.H);
   w.dh[1] = take(d.R * d.H);
+  w.dzP = take(plane_pair_floats(d.R, d.H));
+  for (int l = 0; l < d.L; ++l) w.wP[l] = take(plane_pair_floats(out_dim(d, l), in_dim(d, l)));
   w.rs = row_splits(d);
   w.part = take(static_cast<int64_t>(w.rs) * 2 * d.H);
   w.fold = take(2LL * d.H * std::max(1, d.L - 1));
@@ -109,9 +120,29 @@ static WsLayout ws_layout(const Dims& d, bool train) {
   return w;
 }
 
+struct PlaneRef {
+  uint16_t *hi, *lo;
+  int64_t ld;
+};
+static PlaneRef plane_ref(float* ws, int64_t off, int64_t rows, int width) {
+  PlaneRef p;
+  p.ld = pad8(width);
+  p.hi = reinterpret_cast<uint16_t*>(ws + off);
+  p.lo = p.hi + rows * p.ld;
+  return p;
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_planes(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                             int64_t idx, float v) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  hi[idx] = *reinterpret_cast<const uint16_t*>(&h);
+  lo[idx] = *reinterpret_cast<const uint16_t*>(&l);
+}
+
 __device__ __forceinline__ float keep_scale(const PassParams* pp, int step, int layer, int nlay,
                                             int64_t R, int H, int64_t r, int c, float p_drop) {
   if (p_drop <= 0.f) return 1.f;
@@ -132,19 +163,15 @@ __device__ __forceinline__ float keep_scale(const PassParams* pp, int step, int 
 
 __global__ void __launch_bounds__(256) gather_kernel(const PassParams* __restrict__ pp,
                                                      const int* __restrict__ ctr, int64_t R, int F,
-                                                     int C, float* __restrict__ xb,
+                                                     int C, uint16_t* __restrict__ xb_hi,
+                                                     uint16_t* __restrict__ xb_lo, int64_t ldxb,
                                                      float* __restrict__ tgt) {
   const int lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= R) return;
   const int64_t src = pp->perm[static_cast<int64_t>(*ctr) * R + r];
   const float* x = pp->X + src * pp->ldx;
-  float* o = xb + r * F;
-  if ((F & 3) == 0 && (pp->ldx & 3) == 0 && ((reinterpret_cast<uintptr_t>(pp->X) & 15) == 0)) {
-    for (int j = lane * 4; j < F; j += 128) *reinterpret_cast<float4*>(o + j) = ldg4(x + j);
-  } else {
-    for (int j = lane; j < F; j += 32) o[j] = __ldg(x + j);
-  }
+  for (int j = lane; j < F; j += 32) store_planes(xb_hi, xb_lo, r * ldxb + j, __ldg(x + j));
   if (pp->kind == 0) {
     if (lane == 0) reinterpret_cast<int64_t*>(tgt)[r] = static_cast<const int64_t*>(pp->target)[src];
   } else {
@@ -194,7 +221,8 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 // tile also stores mean / invstd for the backward pass and updates the running statistics
 // (momentum update with the UNBIASED variance, as nn.BatchNorm1d does).  norm == 0: y = z.
 __global__ void __launch_bounds__(256) bn_apply_kernel(
-    const float* __restrict__ Z, float* __restrict__ A, int64_t R, int H, int rs,
+    const float* __restrict__ Z, uint16_t* __restrict__ A_hi, uint16_t* __restrict__ A_lo, int64_t lda,
+    int64_t R, int H, int rs,
     const float* __restrict__ part, const float* __restrict__ gamma, const float* __restrict__ beta,
     float* __restrict__ run_mean, float* __restrict__ run_var, float* __restrict__ save_mean,
     float* __restrict__ save_invstd, int norm, float eps, float mom, float p_drop,
@@ -236,7 +264,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(
     const float z = Z[r * H + c];
     float y = norm ? (z - mu) * inv * g + b : z;
     y = fmaxf(y, 0.f);
-    A[r * H + c] = y * keep_scale(pp, step, layer, nlay, R, H, r, c, p_drop);
+    store_planes(A_hi, A_lo, r * lda + c, y * keep_scale(pp, step, layer, nlay, R, H, r, c, p_drop));
   }
 }
 
@@ -279,11 +307,13 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
   }
 }
 
-// Pass 2: dZ = gamma*invstd/R * (R*g - S1 - xhat*S2) written in place over dA; dgamma = S2,
+// Pass 2: dZ = gamma*invstd/R * (R*g - S1 - xhat*S2) written as bf16 planes (it only feeds the dW and
+// dX projections); dgamma = S2,
 // dbeta = S1; the Linear bias gradient is the column sum of dZ (mathematically 0 in front of a
 // BatchNorm; the reference computes it the same way and Adam still sees its rounding noise).
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
-    float* __restrict__ dA, const float* __restrict__ Z, int64_t R, int H, int rs,
+    const float* __restrict__ dA, uint16_t* __restrict__ dZ_hi, uint16_t* __restrict__ dZ_lo,
+    int64_t lddz, const float* __restrict__ Z, int64_t R, int H, int rs,
     const float* __restrict__ part, const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, int norm, float p_drop,
     const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
@@ -315,7 +345,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
       float gr = dA[r * H + c] * keep_scale(pp, step, layer, nlay, R, H, r, c, p_drop);
       gr = y > 0.f ? gr : 0.f;
       const float dz = norm ? k * (fR * gr - S1 - xh * S2) : gr;
-      dA[r * H + c] = dz;
+      store_planes(dZ_hi, dZ_lo, r * lddz + c, dz);
       colsum += dz;
     }
   }
@@ -334,7 +364,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
 __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ logits,
                                                    const float* __restrict__ tgt, int64_t R, int C,
                                                    const PassParams* __restrict__ pp,
-                                                   float* __restrict__ dlogits,
+                                                   uint16_t* __restrict__ dl_hi,
+                                                   uint16_t* __restrict__ dl_lo, int64_t lddl,
                                                    float* __restrict__ dbias) {
   extern __shared__ float s_col[];  // [C] column sums + [8] row losses
   float* s_loss = s_col + C;
@@ -360,7 +391,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
       for (int j = lane; j < C; j += 32) {
         const float s = x[j] - lse;
         const float d = (expf(s) - (j == y ? 1.f : 0.f)) * sc;
-        dlogits[r * C + j] = d;
+        store_planes(dl_hi, dl_lo, r * lddl + j, d);
         atomicAdd(&s_col[j], d);
         if (j == y) loss = -s;
       }
@@ -373,7 +404,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
       for (int j = lane; j < C; j += 32) {
         const float s = x[j] - lse, tj = t[j], et = expf(tj);
         const float d = (expf(s) * st - et) * sc;
-        dlogits[r * C + j] = d;
+        store_planes(dl_hi, dl_lo, r * lddl + j, d);
         atomicAdd(&s_col[j], d);
         loss = fmaf(et, tj - s, loss);
       }
@@ -429,11 +460,14 @@ __global__ void advance_kernel(int* ctr, int64_t* nbt, int n_norm) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-static int gemm_run(const float* A, int64_t lda, int tA, const float* B, int64_t ldb, int tB, float* C,
-                    int64_t ldc, int64_t M, int64_t N, int64_t K, const float* bias,
-                    const float* col_scale, const float* col_shift, int relu, cudaStream_t st) {
-  return glnn_gemm_f32(A, lda, tA, B, ldb, tB, C, ldc, M, N, K, nullptr, bias, col_scale, col_shift,
-                       relu, 0, st);
+// Tensor-core projection on plane operands: C = op(A) op(B) (+ bias, BN affine, ReLU), fp32 and/or
+// plane output.
+static int gemm_p(const PlaneRef& A, int tA, const PlaneRef& B, int tB, float* C, int64_t ldc,
+                  const PlaneRef* Cp, int64_t M, int64_t N, int64_t K, const float* bias,
+                  const float* col_scale, const float* col_shift, int relu, cudaStream_t st) {
+  return glnn_gemm_bf16x3_planes(A.hi, A.lo, A.ld, tA, B.hi, B.lo, B.ld, tB, C, ldc,
+                                 Cp ? Cp->hi : nullptr, Cp ? Cp->lo : nullptr, Cp ? Cp->ld : 0, M, N, K,
+                                 nullptr, bias, col_scale, col_shift, relu, st);
 }
 
 struct StepCtx {
@@ -450,7 +484,6 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   const int64_t R = d.R;
   const PassParams* pp = reinterpret_cast<const PassParams*>(c.ws + c.wl.pp);
   int* ctr = reinterpret_cast<int*>(c.ws + c.wl.ctr);
-  float* xb = c.ws + c.wl.xb;
   float* tgt = c.ws + c.wl.tgt;
   float* part = c.ws + c.wl.part;
   const int rs = c.wl.rs;
@@ -461,16 +494,31 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   const int row_tiles = static_cast<int>((R + rows_per_block - 1) / rows_per_block);
   int rc;
 
-  gather_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, st>>>(pp, ctr, R, d.F, d.C, xb, tgt);
+  const PlaneRef xb = plane_ref(c.ws, c.wl.xbP, R, d.F);
+  const PlaneRef dlog = plane_ref(c.ws, c.wl.dlogP, R, d.C);
+  const PlaneRef dzp = plane_ref(c.ws, c.wl.dzP, R, d.H);
+  PlaneRef wp[16], ap[16];
+  for (int l = 0; l < d.L; ++l) {
+    wp[l] = plane_ref(c.ws, c.wl.wP[l], out_dim(d, l), in_dim(d, l));
+    if (l < d.L - 1) ap[l] = plane_ref(c.ws, c.wl.aP[l], R, d.H);
+    // weights -> planes at the top of every step (they changed in the previous Adam update, or were
+    // loaded from a state_dict between passes)
+    rc = split_planes(c.params + c.pl.w[l], in_dim(d, l), out_dim(d, l), in_dim(d, l), wp[l].hi,
+                      wp[l].lo, wp[l].ld, st);
+    if (rc != 0) return rc;
+  }
+
+  gather_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, st>>>(pp, ctr, R, d.F, d.C, xb.hi, xb.lo,
+                                                                    xb.ld, tgt);
   GLNN_LAUNCH_OK("gather_kernel");
 
   // forward
-  const float* h = xb;
+  const PlaneRef* h = &xb;
   for (int l = 0; l < d.L; ++l) {
     const int din = in_dim(d, l), dout = out_dim(d, l);
     float* z = (l == d.L - 1) ? c.ws + c.wl.logits : c.ws + c.wl.z[l];
-    rc = gemm_run(h, din, 0, c.params + c.pl.w[l], din, 1, z, dout, R, dout, din,
-                  c.params + c.pl.b[l], nullptr, nullptr, 0, st);
+    rc = gemm_p(*h, 0, wp[l], 1, z, dout, nullptr, R, dout, din, c.params + c.pl.b[l], nullptr, nullptr,
+                0, st);
     if (rc != 0) return rc;
     if (l == d.L - 1) break;
     if (d.norm) {
@@ -478,36 +526,35 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
       GLNN_LAUNCH_OK("bn_stats_kernel");
     }
     bn_apply_kernel<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
-        z, c.ws + c.wl.a[l], R, d.H, rs, part, d.norm ? c.params + c.pl.gamma[l] : nullptr,
-        d.norm ? c.params + c.pl.beta[l] : nullptr, d.norm ? c.bn_stats + 2LL * l * d.H : nullptr,
+        z, ap[l].hi, ap[l].lo, ap[l].ld, R, d.H, rs, part,
+        d.norm ? c.params + c.pl.gamma[l] : nullptr, d.norm ? c.params + c.pl.beta[l] : nullptr,
+        d.norm ? c.bn_stats + 2LL * l * d.H : nullptr,
         d.norm ? c.bn_stats + (2LL * l + 1) * d.H : nullptr, c.ws + c.wl.mean[l],
         c.ws + c.wl.invstd[l], d.norm, d.bn_eps, d.bn_mom, d.p_drop, pp, ctr, l, nlay,
         rows_per_block);
     GLNN_LAUNCH_OK("bn_apply_kernel");
-    h = c.ws + c.wl.a[l];
+    h = &ap[l];
   }
 
   // loss + dlogits (+ last bias grad)
-  float* dlog = c.ws + c.wl.dlogits;
   GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[d.L - 1], 0, sizeof(float) * d.C, st));
   loss_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, sizeof(float) * (d.C + 8), st>>>(
-      c.ws + c.wl.logits, tgt, R, d.C, pp, dlog, c.grads + c.pl.b[d.L - 1]);
+      c.ws + c.wl.logits, tgt, R, d.C, pp, dlog.hi, dlog.lo, dlog.ld, c.grads + c.pl.b[d.L - 1]);
   GLNN_LAUNCH_OK("loss_kernel");
 
   // backward
-  const float* dz = dlog;  // gradient w.r.t. the output of layer l's Linear
+  const PlaneRef* dz = &dlog;  // gradient w.r.t. the output of layer l's Linear
   for (int l = d.L - 1; l >= 0; --l) {
     const int din = in_dim(d, l), dout = out_dim(d, l);
-    const float* hin = (l == 0) ? xb : c.ws + c.wl.a[l - 1];
-    // dW_l [dout, din] = dz^T [dout, R] * hin [R, din]
-    rc = gemm_run(dz, dout, 1, hin, din, 0, c.grads + c.pl.w[l], din, dout, din, R, nullptr, nullptr,
-                  nullptr, 0, st);
+    const PlaneRef& hin = (l == 0) ? xb : ap[l - 1];
+    // dW_l [dout, din] = dz^T [dout, R] * hin [R, din]   (both operands MN-major)
+    rc = gemm_p(*dz, 1, hin, 0, c.grads + c.pl.w[l], din, nullptr, dout, din, R, nullptr, nullptr,
+                nullptr, 0, st);
     if (rc != 0) return rc;
     if (l == 0) break;
-    // dA_{l-1} [R, din] = dz [R, dout] * W_l [dout, din]
+    // dA_{l-1} [R, din] = dz [R, dout] * W_l [dout, din]  (W as MN-major B operand)
     float* da = c.ws + c.wl.dh[l & 1];
-    rc = gemm_run(dz, dout, 0, c.params + c.pl.w[l], din, 0, da, din, R, din, dout, nullptr, nullptr,
-                  nullptr, 0, st);
+    rc = gemm_p(*dz, 0, wp[l], 0, da, din, nullptr, R, din, dout, nullptr, nullptr, nullptr, 0, st);
     if (rc != 0) return rc;
     const int k = l - 1;  // hidden layer whose activation we go back through
     const float* gam = d.norm ? c.params + c.pl.gamma[k] : nullptr;
@@ -520,11 +567,12 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
     }
     GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[k], 0, sizeof(float) * d.H, st));
     bn_bwd_apply_kernel<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
-        da, c.ws + c.wl.z[k], R, d.H, rs, part, gam, bet, c.ws + c.wl.mean[k], c.ws + c.wl.invstd[k],
-        d.norm, d.p_drop, pp, ctr, k, nlay, d.norm ? c.grads + c.pl.gamma[k] : nullptr,
-        d.norm ? c.grads + c.pl.beta[k] : nullptr, c.grads + c.pl.b[k], rows_per_block);
+        da, dzp.hi, dzp.lo, dzp.ld, c.ws + c.wl.z[k], R, d.H, rs, part, gam, bet, c.ws + c.wl.mean[k],
+        c.ws + c.wl.invstd[k], d.norm, d.p_drop, pp, ctr, k, nlay,
+        d.norm ? c.grads + c.pl.gamma[k] : nullptr, d.norm ? c.grads + c.pl.beta[k] : nullptr,
+        c.grads + c.pl.b[k], rows_per_block);
     GLNN_LAUNCH_OK("bn_bwd_apply_kernel");
-    dz = da;
+    dz = &dzp;
   }
 
   const int64_t P = c.pl.total;
@@ -707,22 +755,41 @@ extern "C" int glnn_mlp_eval(const glnn_mlp_desc* desc, const float* params, con
                             fold + (2LL * l + 1) * d.H, d.H, st);
       if (rc != 0) return rc;
     }
+  PlaneRef wp[16];
+  for (int l = 0; l < d.L; ++l) {
+    wp[l] = plane_ref(ws, wl.wP[l], out_dim(d, l), in_dim(d, l));
+    rc = split_planes(params + pl.w[l], in_dim(d, l), out_dim(d, l), in_dim(d, l), wp[l].hi, wp[l].lo,
+                      wp[l].ld, st);
+    if (rc != 0) return rc;
+  }
   for (int64_t r0 = 0; r0 < n; r0 += rows_per_chunk) {
     const int64_t R = std::min(rows_per_chunk, n - r0);
-    const float* h = X + r0 * ldx;
-    int64_t ldh = ldx;
+    // layout offsets are computed for rows_per_chunk rows, so a shorter last chunk fits
+    const PlaneRef xb = plane_ref(ws, wl.xbP, rows_per_chunk, d.F);
+    rc = split_planes(X + r0 * ldx, ldx, R, d.F, xb.hi, xb.lo, xb.ld, st);
+    if (rc != 0) return rc;
+    PlaneRef hbuf[2];
+    if (d.L > 1) {
+      hbuf[0] = plane_ref(ws, wl.aP[0], rows_per_chunk, d.H);
+      hbuf[1] = plane_ref(ws, wl.dzP, rows_per_chunk, d.H);
+    }
+    const PlaneRef* h = &xb;
     for (int l = 0; l < d.L; ++l) {
       const int din = in_dim(d, l), dout = out_dim(d, l);
       const bool last = (l == d.L - 1);
-      float* z = last ? (log_softmax ? ws + wl.logits : out + r0 * ldo)
-                      : ws + (l & 1 ? wl.a[0] : wl.z[0]);
-      const int64_t ldz = (last && !log_softmax) ? ldo : dout;
-      rc = gemm_run(h, ldh, 0, params + pl.w[l], din, 1, z, ldz, R, dout, din, params + pl.b[l],
-                    (!last && d.norm) ? fold + 2LL * l * d.H : nullptr,
-                    (!last && d.norm) ? fold + (2LL * l + 1) * d.H : nullptr, last ? 0 : 1, st);
-      if (rc != 0) return rc;
-      h = z;
-      ldh = dout;
+      if (!last) {  // hidden layer: bias + eval-BN affine + ReLU in the epilogue, planes out
+        rc = gemm_p(*h, 0, wp[l], 1, nullptr, 0, &hbuf[l & 1], R, dout, din, params + pl.b[l],
+                    d.norm ? fold + 2LL * l * d.H : nullptr,
+                    d.norm ? fold + (2LL * l + 1) * d.H : nullptr, 1, st);
+        if (rc != 0) return rc;
+        h = &hbuf[l & 1];
+      } else {
+        float* z = log_softmax ? ws + wl.logits : out + r0 * ldo;
+        const int64_t ldz = log_softmax ? dout : ldo;
+        rc = gemm_p(*h, 0, wp[l], 1, z, ldz, nullptr, R, dout, din, params + pl.b[l], nullptr, nullptr,
+                    0, st);
+        if (rc != 0) return rc;
+      }
     }
     if (log_softmax) {
       rc = glnn_log_softmax_f32(ws + wl.logits, d.C, out + r0 * ldo, ldo, R, d.C, st);

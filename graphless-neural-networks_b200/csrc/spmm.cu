@@ -5,24 +5,45 @@
 // lanes), each lane holds VPL 16-byte column chunks.  A group reads G neighbour ids with one
 // coalesced load, broadcasts them with warp shuffles and keeps U independent 16-byte row loads per
 // lane in flight (memory-level parallelism is what hides the ~1 us DRAM latency of a random row).
-// Rows whose in-degree exceeds HUB_T (power-law hubs) are deferred and then processed by the whole
-// CTA: the neighbour range is cut into one segment per group, partials are combined through shared
-// memory in a fixed order, so results are deterministic.
+//
+// Power-law hubs: a row above kHubT in-edges would pin one warp (or one CTA) for milliseconds --
+// invisible when the whole kernel runs 18 ms on one GPU, but the critical path once the rows are
+// sharded over 4-8 GPUs (the shard that owns the hubs ran 2.6x longer than the others).  The main
+// kernel therefore only REGISTERS such rows: it cuts them into kHubSeg-edge tasks in a device task
+// list; a second, persistent kernel drains the list with every SM (each task is split over the
+// groups of a CTA, reduced through shared memory and atomically added into an fp32 scratch row);
+// a third, tiny kernel applies the epilogue to the hub rows.  If the scratch capacity is ever
+// exceeded the CTA processes the row itself, so the result is always complete.
 //
 // The epilogue fuses everything the reference does between the aggregation and the next dense op:
 // self term, 1/(deg+1) (SAGEConv "gcn"), per-destination scale (GraphConv), bias, eval-BatchNorm
-// affine and ReLU -- so a project-first layer needs no further pass over Y.
+// affine and ReLU -- and can emit the row as bf16 hi/lo planes, the operand format of the
+// tensor-core projection that follows an aggregate-first layer.
+#include <cuda_bf16.h>
+
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace glnn {
+
+struct HubTask {
+  int64_t beg;
+  int32_t len;
+  int32_t slot;
+};
 
 struct SpmmArgs {
   const void* indptr;
   const int32_t* indices;
   const float* X;
   int64_t ldx;
-  float* Y;
+  float* Y;        // fp32 output (may be null when planes are written)
   int64_t ldy;
+  uint16_t* Yh;    // optional bf16 hi / lo plane output
+  uint16_t* Yl;
+  int64_t ldyp;
   int64_t n_dst;
   int d;
   int indptr64;
@@ -34,10 +55,20 @@ struct SpmmArgs {
   const float* col_scale;
   const float* col_shift;
   int relu;
+  // hub scratch (library-owned, per device and stream)
+  int* hub_ctr;          // [0] tasks registered, [1] hub rows registered, [2] next task to run
+  HubTask* hub_tasks;
+  int64_t* hub_rows;     // row id per slot
+  float* hub_acc;        // [cap_rows][kHubAccLd]
+  int cap_tasks, cap_rows;
 };
 
 constexpr int kWarps = 8;
-constexpr int kHubT = 1024;
+constexpr int kHubT = 1024;      // rows above this many in-edges go through the task list
+constexpr int kHubSeg = 2048;    // edges per task
+constexpr int kHubAccLd = 512;   // widest column chunk of one launch
+constexpr int kCapTasks = 1 << 16;
+constexpr int kCapRows = 1 << 13;
 
 __device__ __forceinline__ int64_t load_ptr(const SpmmArgs& a, int64_t i) {
   return a.indptr64 ? __ldg(reinterpret_cast<const int64_t*>(a.indptr) + i)
@@ -55,11 +86,30 @@ __device__ __forceinline__ void load_chunk(const float* p, float (&v)[W]) {
 }
 
 template <int W>
-__device__ __forceinline__ void store_chunk(float* p, const float (&v)[W]) {
-  if constexpr (W == 4) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  } else {
-    p[0] = v[0];
+__device__ __forceinline__ void store_chunk(const SpmmArgs& a, int64_t row, int col,
+                                            const float (&v)[W]) {
+  if (a.Y) {
+    float* p = a.Y + row * a.ldy + col;
+    if constexpr (W == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    else p[0] = v[0];
+  }
+  if (a.Yh) {
+    if constexpr (W == 4) {
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[0] - f01.x, v[1] - f01.y);
+      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[2] - f23.x, v[3] - f23.y);
+      uint2 uh, ul;
+      uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+      ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+      *reinterpret_cast<uint2*>(a.Yh + row * a.ldyp + col) = uh;
+      *reinterpret_cast<uint2*>(a.Yl + row * a.ldyp + col) = ul;
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v[0]);
+      const __nv_bfloat16 l = __float2bfloat16_rn(v[0] - __bfloat162float(h));
+      a.Yh[row * a.ldyp + col] = *reinterpret_cast<const uint16_t*>(&h);
+      a.Yl[row * a.ldyp + col] = *reinterpret_cast<const uint16_t*>(&l);
+    }
   }
 }
 
@@ -138,7 +188,43 @@ __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int64_t row, i
       if (a.relu == 1) x = fmaxf(x, 0.f);
       out[w] = x;
     }
-    store_chunk<W>(a.Y + row * a.ldy + col, out);
+    store_chunk<W>(a, row, col, out);
+  }
+}
+
+template <int VPL, int W>
+__device__ __forceinline__ void zero_acc(float (&acc)[VPL][W]) {
+#pragma unroll
+  for (int p = 0; p < VPL; ++p)
+#pragma unroll
+    for (int w = 0; w < W; ++w) acc[p][w] = 0.f;
+}
+
+// Whole-CTA processing of one edge range: every group takes a fixed sub-range, partials are combined
+// through shared memory in group order; group 0 ends up with the sum in `acc`.
+template <int G, int VPL, int W, bool HAS_SS, int NG>
+__device__ __forceinline__ void cta_gather(const SpmmArgs& a, int64_t beg, int64_t end, int gidx, int gl,
+                                           int lane_base, unsigned gmask, float (*s_part)[G * VPL * W],
+                                           float (&acc)[VPL][W]) {
+  const int64_t len = end - beg;
+  const int64_t seg = ((len + NG - 1) / NG + G - 1) / G * G;
+  const int64_t sb = min(end, beg + gidx * seg), se = min(end, sb + seg);
+  zero_acc<VPL, W>(acc);
+  gather_range<G, VPL, W, HAS_SS>(a, sb, se, gl, lane_base, gmask, acc);
+#pragma unroll
+  for (int p = 0; p < VPL; ++p)
+#pragma unroll
+    for (int w = 0; w < W; ++w) s_part[gidx][(gl + p * G) * W + w] = acc[p][w];
+  __syncthreads();
+  if (gidx == 0) {
+#pragma unroll
+    for (int p = 0; p < VPL; ++p)
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        float t = 0.f;
+        for (int g = 0; g < NG; ++g) t += s_part[g][(gl + p * G) * W + w];
+        acc[p][w] = t;
+      }
   }
 }
 
@@ -147,8 +233,7 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_csr_kernel(const SpmmArgs a)
   constexpr int W = VEC ? 4 : 1;
   constexpr int RPW = 32 / G;          // rows per warp
   constexpr int NG = kWarps * RPW;     // groups (= rows) per CTA
-  constexpr int PW = G * VPL * W;      // padded row width held by a group
-  __shared__ float s_part[NG][PW];
+  __shared__ float s_part[NG][G * VPL * W];
   __shared__ int s_hub[NG];
   __shared__ int s_nhub;
 
@@ -168,51 +253,121 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_csr_kernel(const SpmmArgs a)
     const int64_t row = row0 + gidx;
     if (row < a.n_dst) {
       const int64_t beg = load_ptr(a, row), end = load_ptr(a, row + 1);
-      if (end - beg > kHubT) {
-        if (gl == 0) s_hub[atomicAdd(&s_nhub, 1)] = gidx;
+      const int64_t deg = end - beg;
+      if (deg > kHubT) {
+        // register the row in the device task list (one lane), fall back to this CTA when full
+        int slot = -1;
+        if (gl == 0) {
+          const int ntask = static_cast<int>((deg + kHubSeg - 1) / kHubSeg);
+          const int s = atomicAdd(a.hub_ctr + 1, 1);
+          if (s < a.cap_rows) {
+            const int t0 = atomicAdd(a.hub_ctr + 0, ntask);
+            if (t0 + ntask <= a.cap_tasks) {
+              slot = s;
+              a.hub_rows[s] = row;
+              for (int t = 0; t < ntask; ++t) {
+                HubTask tk;
+                tk.beg = beg + static_cast<int64_t>(t) * kHubSeg;
+                tk.len = static_cast<int32_t>(min(static_cast<int64_t>(kHubSeg), end - tk.beg));
+                tk.slot = s;
+                a.hub_tasks[t0 + t] = tk;
+              }
+            } else {
+              a.hub_rows[s] = -1;  // slot burnt: the finish kernel skips it
+              for (int t = t0; t < min(t0 + ntask, a.cap_tasks); ++t) {
+                HubTask tk;
+                tk.beg = 0; tk.len = 0; tk.slot = s;  // empty filler so the drain sees valid entries
+                a.hub_tasks[t] = tk;
+              }
+            }
+          }
+        }
+        slot = __shfl_sync(gmask, slot, lane_base);
+        if (slot >= 0) {
+          for (int c = gl; c < kHubAccLd; c += G)
+            a.hub_acc[static_cast<int64_t>(slot) * kHubAccLd + c] = 0.f;
+        } else if (gl == 0) {
+          s_hub[atomicAdd(&s_nhub, 1)] = gidx;
+        }
       } else {
         float acc[VPL][W];
-#pragma unroll
-        for (int p = 0; p < VPL; ++p)
-#pragma unroll
-          for (int w = 0; w < W; ++w) acc[p][w] = 0.f;
+        zero_acc<VPL, W>(acc);
         gather_range<G, VPL, W, HAS_SS>(a, beg, end, gl, lane_base, gmask, acc);
-        epilogue_store<G, VPL, W>(a, row, end - beg, gl, acc);
+        epilogue_store<G, VPL, W>(a, row, deg, gl, acc);
       }
     }
   }
   __syncthreads();
 
-  const int nhub = s_nhub;
+  const int nhub = s_nhub;  // only when the task list overflowed
   for (int h = 0; h < nhub; ++h) {
     const int64_t row = row0 + s_hub[h];
     const int64_t beg = load_ptr(a, row), end = load_ptr(a, row + 1);
-    const int64_t deg = end - beg;
-    const int64_t seg = ((deg + NG - 1) / NG + G - 1) / G * G;
-    const int64_t sb = min(end, beg + gidx * seg), se = min(end, sb + seg);
     float acc[VPL][W];
-#pragma unroll
-    for (int p = 0; p < VPL; ++p)
-#pragma unroll
-      for (int w = 0; w < W; ++w) acc[p][w] = 0.f;
-    gather_range<G, VPL, W, HAS_SS>(a, sb, se, gl, lane_base, gmask, acc);
-#pragma unroll
-    for (int p = 0; p < VPL; ++p)
-#pragma unroll
-      for (int w = 0; w < W; ++w) s_part[gidx][(gl + p * G) * W + w] = acc[p][w];
+    cta_gather<G, VPL, W, HAS_SS, NG>(a, beg, end, gidx, gl, lane_base, gmask, s_part, acc);
+    if (gidx == 0) epilogue_store<G, VPL, W>(a, row, end - beg, gl, acc);
     __syncthreads();
-    if (gidx == 0) {
+  }
+}
+
+// Persistent drain of the hub task list: one task per CTA iteration.
+template <int G, int VPL, bool VEC, bool HAS_SS>
+__global__ void __launch_bounds__(kWarps * 32) spmm_hub_kernel(const SpmmArgs a) {
+  constexpr int W = VEC ? 4 : 1;
+  constexpr int RPW = 32 / G;
+  constexpr int NG = kWarps * RPW;
+  __shared__ float s_part[NG][G * VPL * W];
+  __shared__ int s_task;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / G, gl = lane % G, lane_base = sub * G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << lane_base);
+  const int gidx = warp * RPW + sub;
+  const int ntasks = min(a.hub_ctr[0], a.cap_tasks);
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) s_task = atomicAdd(a.hub_ctr + 2, 1);
+    __syncthreads();
+    const int t = s_task;
+    if (t >= ntasks) break;
+    const HubTask tk = a.hub_tasks[t];
+    float acc[VPL][W];
+    cta_gather<G, VPL, W, HAS_SS, NG>(a, tk.beg, tk.beg + tk.len, gidx, gl, lane_base, gmask, s_part,
+                                      acc);
+    if (gidx == 0 && tk.len > 0) {
 #pragma unroll
       for (int p = 0; p < VPL; ++p)
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-          float t = 0.f;
-          for (int g = 0; g < NG; ++g) t += s_part[g][(gl + p * G) * W + w];
-          acc[p][w] = t;
+          const int col = (gl + p * G) * W + w;
+          if (col < a.d) atomicAdd(a.hub_acc + static_cast<int64_t>(tk.slot) * kHubAccLd + col, acc[p][w]);
         }
-      epilogue_store<G, VPL, W>(a, row, deg, gl, acc);
     }
-    __syncthreads();
+  }
+}
+
+// Epilogue of the registered hub rows (one group per row).
+template <int G, int VPL, bool VEC>
+__global__ void __launch_bounds__(kWarps * 32) spmm_hub_finish_kernel(const SpmmArgs a) {
+  constexpr int W = VEC ? 4 : 1;
+  constexpr int RPW = 32 / G;
+  constexpr int NG = kWarps * RPW;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane / G, gl = lane % G;
+  const int gidx = warp * RPW + sub;
+  const int nrows = min(a.hub_ctr[1], a.cap_rows);
+  for (int s = blockIdx.x * NG + gidx; s < nrows; s += gridDim.x * NG) {
+    const int64_t row = a.hub_rows[s];
+    if (row < 0) continue;
+    const int64_t beg = load_ptr(a, row), end = load_ptr(a, row + 1);
+    float acc[VPL][W];
+#pragma unroll
+    for (int p = 0; p < VPL; ++p)
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const int col = (gl + p * G) * W + w;
+        acc[p][w] = col < a.d ? a.hub_acc[static_cast<int64_t>(s) * kHubAccLd + col] : 0.f;
+      }
+    epilogue_store<G, VPL, W>(a, row, end - beg, gl, acc);
   }
 }
 
@@ -222,10 +377,16 @@ static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
   const int64_t blocks = (a.n_dst + NG - 1) / NG;
   if (blocks == 0) return 0;
   GLNN_REQUIRE(blocks < (1LL << 31), GLNN_ERR_SHAPE, "spmm: too many rows (%lld)", (long long)a.n_dst);
-  if (a.src_scale)
-    spmm_csr_kernel<G, VPL, VEC, true><<<static_cast<unsigned>(blocks), kWarps * 32, 0, st>>>(a);
-  else
-    spmm_csr_kernel<G, VPL, VEC, false><<<static_cast<unsigned>(blocks), kWarps * 32, 0, st>>>(a);
+  GLNN_CUDA_OK(cudaMemsetAsync(a.hub_ctr, 0, 4 * sizeof(int), st));
+  const unsigned nb = static_cast<unsigned>(blocks), hub_grid = static_cast<unsigned>(4 * sm_count());
+  if (a.src_scale) {
+    spmm_csr_kernel<G, VPL, VEC, true><<<nb, kWarps * 32, 0, st>>>(a);
+    spmm_hub_kernel<G, VPL, VEC, true><<<hub_grid, kWarps * 32, 0, st>>>(a);
+  } else {
+    spmm_csr_kernel<G, VPL, VEC, false><<<nb, kWarps * 32, 0, st>>>(a);
+    spmm_hub_kernel<G, VPL, VEC, false><<<hub_grid, kWarps * 32, 0, st>>>(a);
+  }
+  spmm_hub_finish_kernel<G, VPL, VEC><<<32, kWarps * 32, 0, st>>>(a);
   GLNN_LAUNCH_OK("spmm_csr_kernel");
   return 0;
 }
@@ -243,27 +404,59 @@ static int launch_width(const SpmmArgs& a, cudaStream_t st) {
   return launch_cfg<32, 4, VEC>(a, st);
 }
 
-}  // namespace glnn
+// Hub scratch: one per (device, stream) so that concurrent streams never share counters.
+struct HubScratch {
+  int* ctr = nullptr;
+  HubTask* tasks = nullptr;
+  int64_t* rows = nullptr;
+  float* acc = nullptr;
+};
+static std::mutex g_hub_mu;
+static std::map<std::pair<int, cudaStream_t>, HubScratch> g_hub;
 
-extern "C" int glnn_spmm_csr_f32(const void* indptr, int indptr64, const int32_t* indices,
-                                 const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n_dst,
-                                 int64_t n_src, int d, int self_add, int mean_plus_one,
-                                 const float* src_scale, const float* dst_scale, const float* bias,
-                                 const float* col_scale, const float* col_shift, int relu,
-                                 glnn_stream_t stream) {
-  using namespace glnn;
+static int hub_scratch(cudaStream_t st, HubScratch* out) {
+  int dev = 0;
+  GLNN_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(g_hub_mu);
+  auto key = std::make_pair(dev, st);
+  auto it = g_hub.find(key);
+  if (it == g_hub.end()) {
+    HubScratch h;
+    GLNN_CUDA_OK(cudaMalloc(&h.ctr, 4 * sizeof(int)));
+    GLNN_CUDA_OK(cudaMalloc(&h.tasks, sizeof(HubTask) * kCapTasks));
+    GLNN_CUDA_OK(cudaMalloc(&h.rows, sizeof(int64_t) * kCapRows));
+    GLNN_CUDA_OK(cudaMalloc(&h.acc, sizeof(float) * kCapRows * kHubAccLd));
+    it = g_hub.emplace(key, h).first;
+  }
+  *out = it->second;
+  return 0;
+}
+
+int spmm_run(const void* indptr, int indptr64, const int32_t* indices, const float* X, int64_t ldx,
+             float* Y, int64_t ldy, uint16_t* Yh, uint16_t* Yl, int64_t ldyp, int64_t n_dst,
+             int64_t n_src, int d, int self_add, int mean_plus_one, const float* src_scale,
+             const float* dst_scale, const float* bias, const float* col_scale,
+             const float* col_shift, int relu, cudaStream_t st) {
   GLNN_REQUIRE(n_dst >= 0 && n_src >= 0 && d >= 0, GLNN_ERR_ARG, "spmm: negative size");
   if (n_dst == 0 || d == 0) return 0;
-  GLNN_REQUIRE(indptr && X && Y, GLNN_ERR_ARG, "spmm: null indptr/X/Y");
-  GLNN_REQUIRE(ldx >= d && ldy >= d, GLNN_ERR_SHAPE, "spmm: leading dimension smaller than d=%d", d);
+  GLNN_REQUIRE(indptr && X && (Y || Yh), GLNN_ERR_ARG, "spmm: null indptr/X/Y");
+  GLNN_REQUIRE((Yh == nullptr) == (Yl == nullptr), GLNN_ERR_ARG, "spmm: output planes come in pairs");
+  GLNN_REQUIRE(ldx >= d && (!Y || ldy >= d) && (!Yh || ldyp >= d), GLNN_ERR_SHAPE,
+               "spmm: leading dimension smaller than d=%d", d);
   GLNN_REQUIRE(!self_add || n_src >= n_dst, GLNN_ERR_SHAPE,
                "spmm: self_add needs dst nodes to be a prefix of src nodes (n_src=%lld < n_dst=%lld)",
                (long long)n_src, (long long)n_dst);
   GLNN_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), GLNN_ERR_ARG,
                "spmm: col_scale and col_shift must be given together");
   GLNN_REQUIRE(relu >= 0 && relu <= 2, GLNN_ERR_ARG, "spmm: relu must be 0, 1 or 2");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && aligned16(X) && aligned16(Y);
+  GLNN_REQUIRE(!Yh || (ldyp % 4 == 0 && (reinterpret_cast<uintptr_t>(Yh) & 7) == 0 &&
+                       (reinterpret_cast<uintptr_t>(Yl) & 7) == 0),
+               GLNN_ERR_ALIGN, "spmm: output planes need ldyp %% 4 == 0 and 8-byte alignment");
+  HubScratch hs;
+  int rc = hub_scratch(st, &hs);
+  if (rc != 0) return rc;
+  const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && (!Y || (ldy % 4 == 0 && aligned16(Y))) &&
+                   aligned16(X);
   const int chunk = vec ? 512 : 128;
   for (int c0 = 0; c0 < d; c0 += chunk) {
     SpmmArgs a;
@@ -271,8 +464,11 @@ extern "C" int glnn_spmm_csr_f32(const void* indptr, int indptr64, const int32_t
     a.indices = indices;
     a.X = X + c0;
     a.ldx = ldx;
-    a.Y = Y + c0;
+    a.Y = Y ? Y + c0 : nullptr;
     a.ldy = ldy;
+    a.Yh = Yh ? Yh + c0 : nullptr;
+    a.Yl = Yl ? Yl + c0 : nullptr;
+    a.ldyp = ldyp;
     a.n_dst = n_dst;
     a.d = min(chunk, d - c0);
     a.indptr64 = indptr64;
@@ -284,8 +480,40 @@ extern "C" int glnn_spmm_csr_f32(const void* indptr, int indptr64, const int32_t
     a.col_scale = col_scale ? col_scale + c0 : nullptr;
     a.col_shift = col_shift ? col_shift + c0 : nullptr;
     a.relu = relu;
-    int rc = vec ? launch_width<true>(a, st) : launch_width<false>(a, st);
+    a.hub_ctr = hs.ctr;
+    a.hub_tasks = hs.tasks;
+    a.hub_rows = hs.rows;
+    a.hub_acc = hs.acc;
+    a.cap_tasks = kCapTasks;
+    a.cap_rows = kCapRows;
+    rc = vec ? launch_width<true>(a, st) : launch_width<false>(a, st);
     if (rc != 0) return rc;
   }
   return 0;
+}
+
+}  // namespace glnn
+
+extern "C" int glnn_spmm_csr_f32(const void* indptr, int indptr64, const int32_t* indices,
+                                 const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n_dst,
+                                 int64_t n_src, int d, int self_add, int mean_plus_one,
+                                 const float* src_scale, const float* dst_scale, const float* bias,
+                                 const float* col_scale, const float* col_shift, int relu,
+                                 glnn_stream_t stream) {
+  GLNN_REQUIRE(Y != nullptr || n_dst <= 0 || d <= 0, GLNN_ERR_ARG, "spmm: null indptr/X/Y");
+  return glnn::spmm_run(indptr, indptr64, indices, X, ldx, Y, ldy, nullptr, nullptr, 0, n_dst, n_src, d,
+                        self_add, mean_plus_one, src_scale, dst_scale, bias, col_scale, col_shift, relu,
+                        static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int glnn_spmm_csr_planes(const void* indptr, int indptr64, const int32_t* indices,
+                                    const float* X, int64_t ldx, uint16_t* Y_hi, uint16_t* Y_lo,
+                                    int64_t ldyp, int64_t n_dst, int64_t n_src, int d, int self_add,
+                                    int mean_plus_one, const float* src_scale, const float* dst_scale,
+                                    const float* bias, const float* col_scale, const float* col_shift,
+                                    int relu, glnn_stream_t stream) {
+  GLNN_REQUIRE((Y_hi && Y_lo) || n_dst <= 0 || d <= 0, GLNN_ERR_ARG, "spmm_planes: null output plane");
+  return glnn::spmm_run(indptr, indptr64, indices, X, ldx, nullptr, 0, Y_hi, Y_lo, ldyp, n_dst, n_src, d,
+                        self_add, mean_plus_one, src_scale, dst_scale, bias, col_scale, col_shift, relu,
+                        static_cast<cudaStream_t>(stream));
 }

@@ -14,71 +14,109 @@
 
 namespace glnn {
 
+int spmm_run(const void* indptr, int indptr64, const int32_t* indices, const float* X, int64_t ldx,
+             float* Y, int64_t ldy, uint16_t* Yh, uint16_t* Yl, int64_t ldyp, int64_t n_dst,
+             int64_t n_src, int d, int self_add, int mean_plus_one, const float* src_scale,
+             const float* dst_scale, const float* bias, const float* col_scale,
+             const float* col_shift, int relu, cudaStream_t st);                     // spmm.cu
+int split_planes(const float* X, int64_t ldx, int64_t rows, int cols, uint16_t* hi, uint16_t* lo,
+                 int64_t ldp, cudaStream_t st);                                      // planes.cu
+
 static inline int pad4(int d) { return (d + 3) / 4 * 4; }
+static inline int pad8(int d) { return (d + 7) / 8 * 8; }
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 struct Plan {
   int64_t n;
-  int dmax;             // widest padded activation
-  int64_t buf_floats;   // per activation buffer
-  int64_t pad_floats;   // padded weight / epilogue scratch
+  int dmax;             // widest padded activation (multiple of 8)
+  int64_t buf_floats;   // per activation buffer (fp32 matrix OR a hi/lo plane pair: same bytes)
+  int64_t pad_floats;   // weight planes + padded epilogue vectors
   int64_t total_bytes;
 };
 
 static Plan make_plan(int64_t n, const glnn_gnn_layer* layers, int L) {
   Plan p{};
   p.n = n;
-  p.dmax = 4;
+  p.dmax = 8;
   p.pad_floats = 0;
   for (int l = 0; l < L; ++l) {
-    p.dmax = max(p.dmax, max(pad4(layers[l].d_in), pad4(layers[l].d_out)));
-    const int dpad = pad4(layers[l].d_out);
-    p.pad_floats += align_up(static_cast<int64_t>(dpad) * layers[l].d_in, 64) + 3 * align_up(dpad, 64);
+    p.dmax = std::max(p.dmax, std::max(pad8(layers[l].d_in), pad8(layers[l].d_out)));
+    // weight planes (hi + lo, bf16) = one fp32-sized block of pad8 x pad8, + 3 padded vectors
+    p.pad_floats += align_up(static_cast<int64_t>(pad8(layers[l].d_out)) * pad8(layers[l].d_in), 64) +
+                    3 * align_up(pad8(layers[l].d_out), 64);
   }
   p.buf_floats = align_up(n * p.dmax, 64);
   p.total_bytes = (3 * p.buf_floats + p.pad_floats) * static_cast<int64_t>(sizeof(float));
   return p;
 }
 
-struct Padded {
-  const float* w;
+// An activation matrix in the workspace: fp32 (ld elements) or a bf16 hi/lo plane pair (ldp).
+struct Act {
+  const float* f32 = nullptr;
+  int64_t ld = 0;
+  const uint16_t* hi = nullptr;
+  const uint16_t* lo = nullptr;
+  int64_t ldp = 0;
+  int d = 0;
+};
+
+struct PlaneBuf {
+  uint16_t *hi, *lo;
+  int64_t ldp;
+};
+static PlaneBuf planes_in(float* buf, int64_t n, int d) {
+  PlaneBuf p;
+  p.ldp = pad8(d);
+  p.hi = reinterpret_cast<uint16_t*>(buf);
+  p.lo = p.hi + n * p.ldp;
+  return p;
+}
+
+struct Epi {
   const float* bias;
   const float* scale;
   const float* shift;
 };
 
-// Pads the weight and the epilogue vectors of one layer to dpad output columns (zero fill).
-// w_rows_are_out: SAGE weight [d_out, d_in] (pad rows); else GCN weight [d_in, d_out] (pad columns).
-static int pad_layer(const glnn_gnn_layer& ly, bool w_rows_are_out, float*& scratch, Padded* out,
-                     cudaStream_t st) {
-  const int dpad = pad4(ly.d_out);
-  out->w = ly.weight;
+// Zero-pads the epilogue vectors of a layer to dpad entries when d_out is not a multiple of 4.
+static int pad_epilogue(const glnn_gnn_layer& ly, int dpad, float*& scratch, Epi* out, cudaStream_t st) {
   out->bias = ly.bias;
   out->scale = ly.bn_scale;
   out->shift = ly.bn_shift;
-  if (dpad == ly.d_out) return 0;
-  float* w = scratch;
-  scratch += align_up(static_cast<int64_t>(dpad) * ly.d_in, 64);
-  GLNN_CUDA_OK(cudaMemsetAsync(w, 0, sizeof(float) * dpad * ly.d_in, st));
-  if (w_rows_are_out) {
-    GLNN_CUDA_OK(cudaMemcpyAsync(w, ly.weight, sizeof(float) * ly.d_out * ly.d_in,
-                                 cudaMemcpyDeviceToDevice, st));
-  } else {
-    GLNN_CUDA_OK(cudaMemcpy2DAsync(w, sizeof(float) * dpad, ly.weight, sizeof(float) * ly.d_out,
-                                   sizeof(float) * ly.d_out, ly.d_in, cudaMemcpyDeviceToDevice, st));
-  }
-  out->w = w;
   const float* src[3] = {ly.bias, ly.bn_scale, ly.bn_shift};
   const float** dst[3] = {&out->bias, &out->scale, &out->shift};
   for (int i = 0; i < 3; ++i) {
     float* v = scratch;
-    scratch += align_up(dpad, 64);
-    if (!src[i]) continue;
+    scratch += align_up(pad8(ly.d_out), 64);
+    if (!src[i] || dpad == ly.d_out) continue;
     GLNN_CUDA_OK(cudaMemsetAsync(v, 0, sizeof(float) * dpad, st));
     GLNN_CUDA_OK(cudaMemcpyAsync(v, src[i], sizeof(float) * ly.d_out, cudaMemcpyDeviceToDevice, st));
     *dst[i] = v;
   }
   return 0;
+}
+
+// Weight -> bf16 planes in the scratch area.  SAGE: W [d_out, d_in] (K-major B operand, rows padded
+// to n_rows with zeros); GCN: W [d_in, d_out] (MN-major B operand, columns padded by the splitter).
+static int weight_planes(const glnn_gnn_layer& ly, bool out_in, int n_rows, float*& scratch,
+                         PlaneBuf* w, cudaStream_t st) {
+  const int rows = out_in ? ly.d_out : ly.d_in, cols = out_in ? ly.d_in : ly.d_out;
+  const int64_t ldp = pad8(cols);
+  uint16_t* base = reinterpret_cast<uint16_t*>(scratch);
+  scratch += align_up(static_cast<int64_t>(pad8(ly.d_out)) * pad8(ly.d_in), 64);
+  const int64_t plane = static_cast<int64_t>(std::max(rows, n_rows)) * ldp;
+  w->hi = base;
+  w->lo = base + plane;
+  w->ldp = ldp;
+  if (n_rows > rows) GLNN_CUDA_OK(cudaMemsetAsync(base, 0, sizeof(uint16_t) * 2 * plane, st));
+  return split_planes(ly.weight, cols, rows, cols, w->hi, w->lo, ldp, st);
+}
+
+static int gemm_planes_call(const Act& a, const PlaneBuf& w, int transB, float* C, int64_t ldc,
+                            uint16_t* Ch, uint16_t* Cl, int64_t ldcp, int64_t M, int64_t N, int64_t K,
+                            const float* row_scale, const Epi& e, int relu, cudaStream_t st) {
+  return glnn_gemm_bf16x3_planes(a.hi, a.lo, a.ldp, 0, w.hi, w.lo, w.ldp, transB, C, ldc, Ch, Cl, ldcp,
+                                 M, N, K, row_scale, e.bias, e.scale, e.shift, relu, st);
 }
 
 static int check_common(const void* indptr, const int32_t* indices, int64_t n, const float* X,
@@ -105,12 +143,100 @@ static int check_common(const void* indptr, const int32_t* indices, int64_t n, c
   return 0;
 }
 
-static int finish(const float* H, int64_t ldh, int64_t n, int c, float* out, int64_t ldo,
-                  int log_softmax, cudaStream_t st) {
-  if (log_softmax) return glnn_log_softmax_f32(H, ldh, out, ldo, n, c, st);
-  GLNN_CUDA_OK(cudaMemcpy2DAsync(out, sizeof(float) * ldo, H, sizeof(float) * ldh, sizeof(float) * c,
-                                 n, cudaMemcpyDeviceToDevice, st));
+static int finish(const Act& h, int64_t n, int c, float* out, int64_t ldo, int log_softmax,
+                  cudaStream_t st) {
+  if (log_softmax) return glnn_log_softmax_f32(h.f32, h.ld, out, ldo, n, c, st);
+  GLNN_CUDA_OK(cudaMemcpy2DAsync(out, sizeof(float) * ldo, h.f32, sizeof(float) * h.ld,
+                                 sizeof(float) * c, n, cudaMemcpyDeviceToDevice, st));
   return 0;
+}
+
+// Shared layer loop of SAGE("gcn") and GCN.  `gcn` selects GraphConv semantics (degree-norm vectors,
+// W stored [in, out], ReLU before the norm layer, DGL's strict in > out rule).
+//   aggregate-first : T = agg(H) -> bf16 planes ; Y = epi(T W + b)     (tcgen05 GEMM epilogue)
+//   project-first   : Z = H W (H as planes)     ; Y = epi(agg(Z) + b)  (gather epilogue)
+// A layer's output is produced directly in the format its consumer reads: fp32 for a gather or the
+// final result, planes for a following projection.
+static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t* indices, int64_t n,
+                       const float* src_norm, const float* dst_norm, const float* X, int64_t ldx,
+                       const glnn_gnn_layer* layers, int L, float* out, int64_t ldo, int log_softmax,
+                       void* workspace, cudaStream_t st) {
+  const Plan p = make_plan(n, layers, L);
+  float* buf[3];
+  for (int i = 0; i < 3; ++i) buf[i] = static_cast<float*>(workspace) + i * p.buf_floats;
+  float* scratch = static_cast<float*>(workspace) + 3 * p.buf_floats;
+  auto project_first = [&](int l) {
+    const glnn_gnn_layer& ly = layers[l];
+    return gcn ? (ly.d_in > ly.d_out) : (pad4(ly.d_out) < ly.d_in);
+  };
+
+  Act h;
+  h.f32 = X; h.ld = ldx; h.d = layers[0].d_in;
+  int hb = -1;  // workspace buffer holding h (-1 = caller memory)
+  int rc;
+  for (int l = 0; l < L; ++l) {
+    const glnn_gnn_layer& ly = layers[l];
+    const bool last = (l == L - 1);
+    const int dpad = pad4(ly.d_out);
+    const int relu = last ? 0 : (gcn ? 2 : 1);
+    const bool out_planes = !last && project_first(l + 1);
+    int ib = 0;
+    while (ib == hb) ++ib;
+    int ob = 0;
+    while (ob == hb || ob == ib) ++ob;
+    Epi epi;
+    if ((rc = pad_epilogue(ly, dpad, scratch, &epi, st))) return rc;
+    PlaneBuf w;
+    Act y;
+    y.d = ly.d_out;
+    if (project_first(l)) {
+      if (!h.hi) {  // fp32 input (caller features or a gather output): split once
+        PlaneBuf hp = planes_in(buf[ob], n, ly.d_in);
+        if ((rc = split_planes(h.f32, h.ld, n, ly.d_in, hp.hi, hp.lo, hp.ldp, st))) return rc;
+        h.hi = hp.hi; h.lo = hp.lo; h.ldp = hp.ldp;
+        // note: the planes live in buf[ob]; the gather below writes its result over them only after
+        // the projection has consumed them (stream order)
+      }
+      if ((rc = weight_planes(ly, !gcn, gcn ? 0 : dpad, scratch, &w, st))) return rc;
+      Epi none{nullptr, nullptr, nullptr};
+      rc = gemm_planes_call(h, w, gcn ? 0 : 1, buf[ib], dpad, nullptr, nullptr, 0, n, dpad, ly.d_in,
+                            gcn ? src_norm : nullptr, none, 0, st);
+      if (rc != 0) return rc;
+      PlaneBuf yp = planes_in(buf[ob], n, dpad);
+      rc = spmm_run(indptr, indptr64, indices, buf[ib], dpad, out_planes ? nullptr : buf[ob], dpad,
+                    out_planes ? yp.hi : nullptr, out_planes ? yp.lo : nullptr, yp.ldp, n, n, dpad,
+                    gcn ? 0 : 1, gcn ? 0 : 1, nullptr, gcn ? dst_norm : nullptr, epi.bias, epi.scale,
+                    epi.shift, relu, st);
+      if (rc != 0) return rc;
+      if (out_planes) { y.hi = yp.hi; y.lo = yp.lo; y.ldp = yp.ldp; }
+      else { y.f32 = buf[ob]; y.ld = dpad; }
+    } else {
+      // aggregate (fp32 gather) straight into planes
+      const float* hin = h.f32;
+      GLNN_REQUIRE(hin != nullptr, GLNN_ERR_ARG, "gnn_forward: internal: gather input must be fp32");
+      PlaneBuf tp = planes_in(buf[ib], n, ly.d_in);
+      rc = spmm_run(indptr, indptr64, indices, hin, h.ld, nullptr, 0, tp.hi, tp.lo, tp.ldp, n, n,
+                    ly.d_in, gcn ? 0 : 1, gcn ? 0 : 1, gcn ? src_norm : nullptr, nullptr, nullptr,
+                    nullptr, nullptr, 0, st);
+      if (rc != 0) return rc;
+      if (pad8(ly.d_in) != ly.d_in) {
+        // pad columns of the planes are never read (the GEMM zero-fills past K)
+      }
+      if ((rc = weight_planes(ly, !gcn, 0, scratch, &w, st))) return rc;
+      Act t;
+      t.hi = tp.hi; t.lo = tp.lo; t.ldp = tp.ldp; t.d = ly.d_in;
+      PlaneBuf yp = planes_in(buf[ob], n, ly.d_out);
+      rc = gemm_planes_call(t, w, gcn ? 0 : 1, out_planes ? nullptr : buf[ob], dpad,
+                            out_planes ? yp.hi : nullptr, out_planes ? yp.lo : nullptr, yp.ldp, n,
+                            ly.d_out, ly.d_in, gcn ? dst_norm : nullptr, epi, relu, st);
+      if (rc != 0) return rc;
+      if (out_planes) { y.hi = yp.hi; y.lo = yp.lo; y.ldp = yp.ldp; }
+      else { y.f32 = buf[ob]; y.ld = dpad; }
+    }
+    h = y;
+    hb = ob;
+  }
+  return finish(h, n, layers[L - 1].d_out, out, ldo, log_softmax, st);
 }
 
 }  // namespace glnn
@@ -126,52 +252,12 @@ extern "C" int glnn_sage_forward(const void* indptr, int indptr64, const int32_t
                                  int num_layers, float* out, int64_t ldo, int log_softmax,
                                  void* workspace, int64_t workspace_bytes, glnn_stream_t stream) {
   using namespace glnn;
-  const int L = num_layers;
-  int rc = check_common(indptr, indices, n, X, ldx, layers, L, out, ldo, workspace, workspace_bytes);
+  int rc = check_common(indptr, indices, n, X, ldx, layers, num_layers, out, ldo, workspace,
+                        workspace_bytes);
   if (rc != 0) return rc;
   if (n == 0) return 0;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const Plan p = make_plan(n, layers, L);
-  float* buf[3];
-  for (int i = 0; i < 3; ++i) buf[i] = static_cast<float*>(workspace) + i * p.buf_floats;
-  float* scratch = static_cast<float*>(workspace) + 3 * p.buf_floats;
-
-  const float* H = X;
-  int64_t ldh = ldx;
-  int hb = -1;  // buffer index holding H (-1 = caller's X)
-  for (int l = 0; l < L; ++l) {
-    const glnn_gnn_layer& ly = layers[l];
-    const bool last = (l == L - 1);
-    const int dpad = pad4(ly.d_out);
-    const int relu = last ? 0 : 1;
-    int ib = 0;
-    while (ib == hb) ++ib;
-    int ob = 0;
-    while (ob == hb || ob == ib) ++ob;
-    if (dpad < ly.d_in) {  // project first
-      Padded pd;
-      rc = pad_layer(ly, true, scratch, &pd, st);
-      if (rc != 0) return rc;
-      rc = glnn_gemm_f32(H, ldh, 0, pd.w, ly.d_in, 1, buf[ib], dpad, n, dpad, ly.d_in, nullptr,
-                         nullptr, nullptr, nullptr, 0, 0, st);
-      if (rc != 0) return rc;
-      rc = glnn_spmm_csr_f32(indptr, indptr64, indices, buf[ib], dpad, buf[ob], dpad, n, n, dpad, 1,
-                             1, nullptr, nullptr, pd.bias, pd.scale, pd.shift, relu, st);
-      if (rc != 0) return rc;
-    } else {  // aggregate first (DGL 0.6.1 order)
-      const int ldt = pad4(ly.d_in);
-      rc = glnn_spmm_csr_f32(indptr, indptr64, indices, H, ldh, buf[ib], ldt, n, n, ly.d_in, 1, 1,
-                             nullptr, nullptr, nullptr, nullptr, nullptr, 0, st);
-      if (rc != 0) return rc;
-      rc = glnn_gemm_f32(buf[ib], ldt, 0, ly.weight, ly.d_in, 1, buf[ob], dpad, n, ly.d_out, ly.d_in,
-                         nullptr, ly.bias, ly.bn_scale, ly.bn_shift, relu, 0, st);
-      if (rc != 0) return rc;
-    }
-    H = buf[ob];
-    ldh = dpad;
-    hb = ob;
-  }
-  return finish(H, ldh, n, layers[L - 1].d_out, out, ldo, log_softmax, st);
+  return gnn_forward(false, indptr, indptr64, indices, n, nullptr, nullptr, X, ldx, layers, num_layers,
+                     out, ldo, log_softmax, workspace, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int glnn_gcn_forward(const void* indptr, int indptr64, const int32_t* indices, int64_t n,
@@ -180,53 +266,13 @@ extern "C" int glnn_gcn_forward(const void* indptr, int indptr64, const int32_t*
                                 int64_t ldo, int log_softmax, void* workspace,
                                 int64_t workspace_bytes, glnn_stream_t stream) {
   using namespace glnn;
-  const int L = num_layers;
-  int rc = check_common(indptr, indices, n, X, ldx, layers, L, out, ldo, workspace, workspace_bytes);
+  int rc = check_common(indptr, indices, n, X, ldx, layers, num_layers, out, ldo, workspace,
+                        workspace_bytes);
   if (rc != 0) return rc;
   GLNN_REQUIRE(src_norm && dst_norm, GLNN_ERR_ARG, "gcn_forward: null degree-norm vector");
   if (n == 0) return 0;
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const Plan p = make_plan(n, layers, L);
-  float* buf[3];
-  for (int i = 0; i < 3; ++i) buf[i] = static_cast<float*>(workspace) + i * p.buf_floats;
-  float* scratch = static_cast<float*>(workspace) + 3 * p.buf_floats;
-
-  const float* H = X;
-  int64_t ldh = ldx;
-  int hb = -1;
-  for (int l = 0; l < L; ++l) {
-    const glnn_gnn_layer& ly = layers[l];
-    const bool last = (l == L - 1);
-    const int dpad = pad4(ly.d_out);
-    const int relu = last ? 0 : 2;  // GraphConv applies the activation before the norm layer
-    int ib = 0;
-    while (ib == hb) ++ib;
-    int ob = 0;
-    while (ob == hb || ob == ib) ++ob;
-    if (ly.d_in > ly.d_out) {  // DGL: multiply by W first when it shrinks the rows
-      Padded pd;
-      rc = pad_layer(ly, false, scratch, &pd, st);
-      if (rc != 0) return rc;
-      rc = glnn_gemm_f32(H, ldh, 0, pd.w, dpad, 0, buf[ib], dpad, n, dpad, ly.d_in, src_norm, nullptr,
-                         nullptr, nullptr, 0, 0, st);
-      if (rc != 0) return rc;
-      rc = glnn_spmm_csr_f32(indptr, indptr64, indices, buf[ib], dpad, buf[ob], dpad, n, n, dpad, 0,
-                             0, nullptr, dst_norm, pd.bias, pd.scale, pd.shift, relu, st);
-      if (rc != 0) return rc;
-    } else {
-      const int ldt = pad4(ly.d_in);
-      rc = glnn_spmm_csr_f32(indptr, indptr64, indices, H, ldh, buf[ib], ldt, n, n, ly.d_in, 0, 0,
-                             src_norm, nullptr, nullptr, nullptr, nullptr, 0, st);
-      if (rc != 0) return rc;
-      rc = glnn_gemm_f32(buf[ib], ldt, 0, ly.weight, ly.d_out, 0, buf[ob], dpad, n, ly.d_out, ly.d_in,
-                         dst_norm, ly.bias, ly.bn_scale, ly.bn_shift, relu, 0, st);
-      if (rc != 0) return rc;
-    }
-    H = buf[ob];
-    ldh = dpad;
-    hb = ob;
-  }
-  return finish(H, ldh, n, layers[L - 1].d_out, out, ldo, log_softmax, st);
+  return gnn_forward(true, indptr, indptr64, indices, n, src_norm, dst_norm, X, ldx, layers, num_layers,
+                     out, ldo, log_softmax, workspace, static_cast<cudaStream_t>(stream));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -18,11 +18,17 @@ import torch.distributed as dist
 from . import ops
 
 
-def nnz_balanced_cuts(indptr, world):
-    """Row boundaries cut[0..world] with ~equal nnz (+ rows, so empty rows also spread)."""
+ROW_COST = 16  # cost of one row (projection + output write + exchange) in units of one gathered edge
+
+
+def nnz_balanced_cuts(indptr, world, row_cost=ROW_COST):
+    """Row boundaries cut[0..world] with ~equal (nnz + row_cost * rows): the gather scales with the
+    edges, the projection / stores / all-gather slab with the rows (measured on products: ~0.15 ns
+    per edge at d=256 vs ~3 ns per row), so balancing edges alone leaves the low-degree shards with
+    2.4x the rows of the hub shard and inflates the padded slab."""
     p = indptr.to(torch.int64).cpu()
     n = p.numel() - 1
-    weight = p + torch.arange(n + 1, dtype=torch.int64)  # nnz + rows, monotone
+    weight = p + row_cost * torch.arange(n + 1, dtype=torch.int64)  # monotone
     total = int(weight[-1])
     targets = torch.tensor([total * g // world for g in range(1, world)], dtype=torch.int64)
     inner = torch.searchsorted(weight, targets).clamp_(0, n)
@@ -102,7 +108,8 @@ def _buffer(sg, key, rows, cols, like):
     return t
 
 
-def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None, log_softmax=True):
+def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None, log_softmax=True,
+                         timings=None):
     """layers: [(W [out,in], b)], norms: [(scale, shift)] folded eval-BN per hidden layer (or []).
     feats_pad: padded replica of the input features (valid on every rank).  Returns the padded
     replica [world * rows_max, label_dim] of the output (log-probabilities when log_softmax); the
@@ -117,9 +124,18 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
     world, rm = sg.world, sg.rows_max
     lo, hi = sg.rank * rm, sg.rank * rm + sg.rows
 
+    def mark(name):
+        if timings is not None and feats_pad.is_cuda:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            timings.append((name, ev))
+
     def gather(buf):
         if world > 1:  # in place: this rank's slab already sits at its offset in the output
             dist.all_gather_into_tensor(buf, buf[lo: lo + rm], group=group)
+        mark(f"all_gather {tuple(buf.shape)}")
+
+    mark("start")
 
     h, h_full = feats_pad, True
     L = len(layers)
@@ -133,19 +149,36 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
             wp, bp = _pad_rows(w, b, dpad)
             z = _buffer(sg, ("z", l), world * rm, dpad, h)
             k.gemm(h[lo:hi, :d_in], wp, trans_b=True, out=z[lo:hi])
+            mark(f"L{l} gemm {d_in}->{dpad}")
             gather(z)
             y = _buffer(sg, ("y", l), world * rm, dpad, h)
             k.spmm_csr(sg.indptr, sg.indices, z, d=dpad, out=y[lo:hi], dst_scale=sg.inv_deg1,
                        bias=bp, col_scale=scale, col_shift=shift, relu=relu)
+            mark(f"L{l} spmm d={dpad}")
         else:
             if not h_full:
                 gather(h)
-            agg = _buffer(sg, ("agg", l), max(sg.rows, 1), (d_in + 3) // 4 * 4, h)
-            k.spmm_csr(sg.indptr, sg.indices, h, d=d_in, out=agg[: sg.rows, :d_in],
-                       dst_scale=sg.inv_deg1)
             y = _buffer(sg, ("y", l), world * rm, dpad, h)
-            k.gemm(agg[: sg.rows, :d_in], w, trans_b=True, out=y[lo:hi, :d_out], bias=b,
-                   col_scale=scale, col_shift=shift, relu=relu)
+            if hasattr(k, "spmm_csr_planes"):
+                # gather straight into bf16 hi/lo planes, the tensor-core projection's operand format
+                ldp = (d_in + 7) // 8 * 8
+                pl = sg.__dict__.setdefault("_planes", {}).get(l)
+                if pl is None or pl.hi.shape != (max(sg.rows, 1), ldp):
+                    mk = lambda: torch.zeros(max(sg.rows, 1), ldp, dtype=torch.int16, device=h.device)
+                    pl = k.Planes(mk(), mk(), d_in)
+                    sg._planes[l] = pl
+                k.spmm_csr_planes(sg.indptr, sg.indices, h, d=d_in, dst_scale=sg.inv_deg1, out=pl)
+                mark(f"L{l} spmm d={d_in}")
+                k.gemm_planes(pl, k.split_planes(w), trans_b=True, out=y[lo:hi, :d_out], bias=b,
+                              col_scale=scale, col_shift=shift, relu=relu)
+            else:
+                agg = _buffer(sg, ("agg", l), max(sg.rows, 1), (d_in + 3) // 4 * 4, h)
+                k.spmm_csr(sg.indptr, sg.indices, h, d=d_in, out=agg[: sg.rows, :d_in],
+                           dst_scale=sg.inv_deg1)
+                mark(f"L{l} spmm d={d_in}")
+                k.gemm(agg[: sg.rows, :d_in], w, trans_b=True, out=y[lo:hi, :d_out], bias=b,
+                       col_scale=scale, col_shift=shift, relu=relu)
+            mark(f"L{l} gemm {d_in}->{d_out}")
         h, h_full = y, False
     c = layers[-1][0].shape[0]
     out = _buffer(sg, ("out",), world * rm, c, h)
@@ -153,5 +186,6 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
         k.log_softmax(h[lo:hi, :c], out=out[lo:hi])
     else:
         out[lo:hi] = h[lo:hi, :c]
+    mark("log_softmax")
     gather(out)
     return out

@@ -219,3 +219,19 @@ def eval_forward(mlp, feats, rows_per_chunk=None, log_softmax=True):
 
 def eval_logits(mlp, feats):
     return eval_forward(mlp, feats, log_softmax=False)
+
+
+def flat_grads(mlp):
+    """Gradients of the LAST fused step as {state_dict-style name: tensor view} (diagnostics and
+    parity tests; the fused path never materialises p.grad)."""
+    fl = ensure_flat(mlp)
+    names = []
+    for i in range(len(mlp.layers)):
+        names += [f"layers.{i}.weight", f"layers.{i}.bias"]
+    if mlp.norm_type == "batch":
+        for i in range(len(mlp.norms)):
+            names += [f"norms.{i}.weight", f"norms.{i}.bias"]
+    out = {}
+    for name, p, (off, n) in zip(names, _param_order(mlp), fl.views):
+        out[name] = fl.grads[off:off + n].view(p.shape)
+    return out

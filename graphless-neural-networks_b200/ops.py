@@ -91,3 +91,79 @@ def nll_acc(logp, labels, idx=None):
     check(lib.glnn_nll_acc_f32(ptr(logp), _ld(logp), logp.shape[1], ptr(labels), ptr(idx), n,
                                ptr(out), stream()), "glnn_nll_acc_f32")
     return out
+
+
+class Planes:
+    """fp32 matrix kept as bf16 hi / lo planes (see include/glnn_b200.h): .hi/.lo int16 tensors
+    [rows, ldp], logical width .cols."""
+
+    def __init__(self, hi, lo, cols):
+        self.hi, self.lo, self.cols = hi, lo, cols
+
+    @property
+    def shape(self):
+        return (self.hi.shape[0], self.cols)
+
+    def float(self):
+        f = lambda t: (t.view(torch.int16).to(torch.int32) << 16).view(torch.float32)
+        return (f(self.hi) + f(self.lo))[:, :self.cols]
+
+
+def split_planes(x):
+    """glnn_split_planes_f32: fp32 [rows, cols] -> Planes with ldp = cols rounded up to 8."""
+    lib = _lib.load()
+    require_cuda(x)
+    _f32(x)
+    rows, cols = x.shape
+    ldp = (cols + 7) // 8 * 8
+    hi = torch.empty(rows, ldp, dtype=torch.int16, device=x.device)
+    lo = torch.empty(rows, ldp, dtype=torch.int16, device=x.device)
+    check(lib.glnn_split_planes_f32(ptr(x), _ld(x), rows, cols, ptr(hi), ptr(lo), ldp, stream()),
+          "glnn_split_planes_f32")
+    return Planes(hi, lo, cols)
+
+
+def gemm_planes(a, b, trans_a=False, trans_b=False, out=None, out_planes=False, row_scale=None,
+                bias=None, col_scale=None, col_shift=None, relu=0):
+    """glnn_gemm_bf16x3_planes on Planes operands.  Returns fp32 C, or Planes when out_planes."""
+    lib = _lib.load()
+    m, k = (a.cols, a.hi.shape[0]) if trans_a else (a.hi.shape[0], a.cols)
+    kb, n = (b.cols, b.hi.shape[0]) if trans_b else (b.hi.shape[0], b.cols)
+    if k != kb:
+        raise ValueError(f"gemm_planes: inner dimensions differ ({k} vs {kb})")
+    dev = a.hi.device
+    c = ch = cl = None
+    ldcp = 0
+    if out_planes:
+        ldcp = (n + 7) // 8 * 8
+        ch = torch.zeros(m, ldcp, dtype=torch.int16, device=dev)
+        cl = torch.zeros(m, ldcp, dtype=torch.int16, device=dev)
+    else:
+        c = out if out is not None else torch.empty(m, n, dtype=torch.float32, device=dev)
+    check(lib.glnn_gemm_bf16x3_planes(ptr(a.hi), ptr(a.lo), a.hi.stride(0), int(trans_a), ptr(b.hi),
+                                      ptr(b.lo), b.hi.stride(0), int(trans_b), ptr(c),
+                                      0 if c is None else _ld(c), ptr(ch), ptr(cl), ldcp, m, n, k,
+                                      ptr(row_scale), ptr(bias), ptr(col_scale), ptr(col_shift),
+                                      int(relu), stream()), "glnn_gemm_bf16x3_planes")
+    return Planes(ch, cl, n) if out_planes else c
+
+
+def spmm_csr_planes(indptr, indices, x, d=None, self_add=False, mean_plus_one=False, src_scale=None,
+                    dst_scale=None, bias=None, col_scale=None, col_shift=None, relu=0, out=None):
+    """glnn_spmm_csr_planes: the aggregation with its result written as Planes (operand of a
+    following tensor-core projection)."""
+    lib = _lib.load()
+    require_cuda(indptr, indices, x, src_scale, dst_scale, bias, col_scale, col_shift)
+    _f32(x, src_scale, dst_scale, bias, col_scale, col_shift)
+    n_dst = indptr.numel() - 1
+    d = x.shape[1] if d is None else d
+    if out is None:
+        ldp = (d + 7) // 8 * 8
+        out = Planes(torch.zeros(n_dst, ldp, dtype=torch.int16, device=x.device),
+                     torch.zeros(n_dst, ldp, dtype=torch.int16, device=x.device), d)
+    check(lib.glnn_spmm_csr_planes(ptr(indptr), int(indptr.dtype == torch.int64), ptr(indices), ptr(x),
+                                   _ld(x), ptr(out.hi), ptr(out.lo), out.hi.stride(0), n_dst,
+                                   x.shape[0], d, int(self_add), int(mean_plus_one), ptr(src_scale),
+                                   ptr(dst_scale), ptr(bias), ptr(col_scale), ptr(col_shift),
+                                   int(relu), stream()), "glnn_spmm_csr_planes")
+    return out

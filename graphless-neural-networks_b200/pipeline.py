@@ -1,0 +1,56 @@
+"""Host-facing throughput path for the teacher forward: host (pinned) CSR + features in, host
+log-probabilities out, with the PCIe copies of neighbouring steps overlapped with compute.
+
+A step needs all of its inputs before the first aggregation (random row gathers), so nothing inside
+ONE forward can overlap with its own upload; across steps, however, step i+1's upload and step i-1's
+download run on copy streams while step i computes (double-buffered device inputs, full-duplex
+PCIe).  Every step still copies its own inputs and reads back its own result."""
+import torch
+
+from .graph import CSRGraph, FullNeighborLoader
+
+
+class HostTeacherPipeline:
+    def __init__(self, encoder, n, indptr_like, indices_like, feat_dim, label_dim, device, depth=2):
+        self.enc, self.n, self.dev, self.depth = encoder, n, device, depth
+        self.h2d, self.d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        self.slots = []
+        for _ in range(depth):
+            slot = dict(
+                indptr=torch.empty_like(indptr_like, device=device),
+                indices=torch.empty_like(indices_like, device=device),
+                feats=torch.empty(n, feat_dim, dtype=torch.float32, device=device),
+                uploaded=torch.cuda.Event(), computed=torch.cuda.Event(), downloaded=torch.cuda.Event())
+            slot["loader"] = FullNeighborLoader(CSRGraph(slot["indptr"], slot["indices"], n))
+            self.slots.append(slot)
+        self.step = 0
+        self.label_dim = label_dim
+
+    def submit(self, h_indptr, h_indices, h_feats, h_out):
+        """Enqueues one forward: upload -> SAGE.inference + log_softmax -> download into h_out
+        (pinned).  Returns immediately; call drain() before reading h_out."""
+        s = self.slots[self.step % self.depth]
+        cur = torch.cuda.current_stream(self.dev)
+        if self.step >= self.depth:
+            self.h2d.wait_event(s["computed"])  # the slot's previous forward has consumed its inputs
+        with torch.cuda.stream(self.h2d):
+            s["indptr"].copy_(h_indptr, non_blocking=True)
+            s["indices"].copy_(h_indices, non_blocking=True)
+            s["feats"].copy_(h_feats, non_blocking=True)
+            s["uploaded"].record(self.h2d)
+        cur.wait_event(s["uploaded"])
+        with torch.no_grad():
+            out = self.enc.inference(s["loader"], s["feats"], log_softmax=True)
+        s["computed"].record(cur)
+        self.d2h.wait_event(s["computed"])
+        with torch.cuda.stream(self.d2h):
+            out.record_stream(self.d2h)
+            h_out.copy_(out, non_blocking=True)
+            s["downloaded"].record(self.d2h)
+        self.step += 1
+
+    def drain(self):
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.slots:
+            cur.wait_event(s["downloaded"])
+            cur.wait_event(s["computed"])

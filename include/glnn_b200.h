@@ -71,6 +71,15 @@ GLNN_API int glnn_spmm_csr_f32(const void* indptr, int indptr64, const int32_t* 
                       const float* dst_scale, const float* bias, const float* col_scale,
                       const float* col_shift, int relu, glnn_stream_t stream);
 
+/* Same aggregation, result written as bf16 hi / lo planes (see "tensor-core operand format" below)
+ * for a projection that follows: Y_hi / Y_lo are [n_dst, ldyp] uint16, ldyp % 4 == 0. */
+GLNN_API int glnn_spmm_csr_planes(const void* indptr, int indptr64, const int32_t* indices, const float* X,
+                         int64_t ldx, uint16_t* Y_hi, uint16_t* Y_lo, int64_t ldyp, int64_t n_dst,
+                         int64_t n_src, int d, int self_add, int mean_plus_one,
+                         const float* src_scale, const float* dst_scale, const float* bias,
+                         const float* col_scale, const float* col_shift, int relu,
+                         glnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K4: fp32-faithful dense projection with fused epilogue
  *
@@ -90,6 +99,25 @@ GLNN_API int glnn_gemm_f32(const float* A, int64_t lda, int transA, const float*
                   float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* row_scale,
                   const float* bias, const float* col_scale, const float* col_shift, int relu,
                   int impl, glnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4, tensor-core operand format.  A "planes" matrix is an fp32 matrix kept as two bf16 matrices
+ * hi = bf16(x), lo = bf16(x - hi) (uint16_t storage) with a common leading dimension ldp that is
+ * a multiple of 8 elements and zeros in the pad columns; x ~ hi + lo to 2^-18 relative, same
+ * bytes as fp32.  glnn_split_planes_f32 converts; glnn_gemm_bf16x3_planes computes the same
+ * C = epilogue(op(A) op(B)) as glnn_gemm_f32 from planes (tcgen05, hi*hi + hi*lo + lo*hi in fp32)
+ * and writes C as fp32 (C != NULL) and/or as planes (C_hi/C_lo != NULL, for a following GEMM).
+ * Kernels of this library that only feed GEMMs write planes directly.
+ */
+GLNN_API int glnn_split_planes_f32(const float* X, int64_t ldx, int64_t rows, int cols, uint16_t* hi,
+                          uint16_t* lo, int64_t ldp, glnn_stream_t stream);
+
+GLNN_API int glnn_gemm_bf16x3_planes(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, int transA,
+                            const uint16_t* B_hi, const uint16_t* B_lo, int64_t ldb, int transB,
+                            float* C, int64_t ldc, uint16_t* C_hi, uint16_t* C_lo, int64_t ldcp,
+                            int64_t M, int64_t N, int64_t K, const float* row_scale,
+                            const float* bias, const float* col_scale, const float* col_shift,
+                            int relu, glnn_stream_t stream);
 
 /* K5 (eval): folds BatchNorm1d running statistics into a per-column affine for the epilogues
  * above: scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (models.py:139-141). */

@@ -71,7 +71,10 @@ def test_nnz_balanced_cuts():
     from glnn_b200.dist_teacher import nnz_balanced_cuts
     deg = torch.tensor([1000] + [1] * 999)
     indptr = torch.cat([torch.zeros(1, dtype=torch.int64), deg.cumsum(0)])
-    cuts = nnz_balanced_cuts(indptr, 4)
+    cuts = nnz_balanced_cuts(indptr, 4, row_cost=1)
     loads = [int(indptr[cuts[i + 1]] - indptr[cuts[i]]) + cuts[i + 1] - cuts[i] for i in range(4)]
     assert cuts[0] == 0 and cuts[-1] == 1000 and cuts == sorted(cuts)
     assert max(loads) <= 1001 + 2 * 500  # the hub row dominates one shard, the rest stay even
+    even = nnz_balanced_cuts(indptr, 4, row_cost=16)
+    sizes = [even[i + 1] - even[i] for i in range(4)]
+    assert max(sizes) - min(sizes) < 80   # row-weighted cuts keep the slabs (and the padding) even

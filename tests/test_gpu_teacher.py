@@ -98,6 +98,23 @@ def test_spmm_epilogues(dev, d, opts, iptr32):
     assert relerr(got.cpu(), acc) < 1e-5
 
 
+def test_spmm_many_hubs_and_plane_output(dev):
+    """Hub rows go through the device task list (split over the grid, atomically combined); the
+    plane output is what the tensor-core projection consumes."""
+    from glnn_b200 import ops
+    n, d = 3000, 100
+    indptr, indices = _rand_graph(n, n, 30000, seed=3, hubs=40, empty=5)   # 40 rows x 3000 edges
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(9))
+    want = (O.spmm_sum(indptr, indices, x.double()) + x.double()) / \
+        (torch.from_numpy(np.diff(indptr)).double().unsqueeze(1) + 1)
+    ip, ix = torch.from_numpy(indptr).int().to(dev), torch.from_numpy(indices).int().to(dev)
+    got = ops.spmm_csr(ip, ix, x.to(dev), self_add=True, mean_plus_one=True)
+    assert relerr(got.cpu(), want) < 1e-5
+    pl = ops.spmm_csr_planes(ip, ix, x.to(dev), self_add=True, mean_plus_one=True)
+    assert pl.hi.shape == (n, 104)
+    assert relerr(pl.float().cpu(), want) < 2e-5
+
+
 def test_spmm_strided_views_and_bipartite(dev):
     """Column-sliced input/output (leading dimension > d) and n_src != n_dst (a block)."""
     from glnn_b200 import ops
@@ -162,6 +179,26 @@ def test_gemm_tcgen05_bf16x3_vs_fp64(dev, m, n, k, ta, tb):
     want = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
     got = ops.gemm(a.to(dev), b.to(dev), trans_a=ta, trans_b=tb, impl=2)
     assert relerr(got.cpu(), want) < 3e-5
+
+
+@pytest.mark.parametrize("m,n,k,ta,tb", [
+    (300, 256, 100, False, True), (1000, 47, 256, False, True), (4096, 2048, 2048, False, True),
+    (4096, 2048, 2048, False, False), (2048, 2048, 4096, True, False), (47, 2048, 4096, True, False),
+    (2048, 100, 4096, True, False), (4096, 100, 47, False, False), (130, 70, 9, False, True)])
+def test_gemm_planes_vs_fp64(dev, m, n, k, ta, tb):
+    """bf16 hi/lo plane operands (cp.async producers, split-K for skinny outputs), all four majors."""
+    from glnn_b200 import ops
+    g = torch.Generator().manual_seed(m + 5 * n + k)
+    a = torch.randn((k, m) if ta else (m, k), generator=g)
+    b = torch.randn((n, k) if tb else (k, n), generator=g)
+    want = (a.double().t() if ta else a.double()) @ (b.double().t() if tb else b.double())
+    pa, pb = ops.split_planes(a.to(dev)), ops.split_planes(b.to(dev))
+    assert relerr(pa.float().cpu(), a) < 2e-5        # hi + lo reproduces x to ~2^-17
+    got = ops.gemm_planes(pa, pb, trans_a=ta, trans_b=tb)
+    assert relerr(got.cpu(), want) < 3e-5
+    if not ta:                                        # plane output feeds a following GEMM
+        gp = ops.gemm_planes(pa, pb, trans_a=ta, trans_b=tb, out_planes=True, relu=1)
+        assert relerr(gp.float().cpu(), want.clamp(min=0)) < 3e-5
 
 
 def test_gemm_tcgen05_declines_unaligned_operands(dev):
