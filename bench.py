@@ -24,6 +24,26 @@ METRIC = "nodes/sec teacher-fwd (SAGE full-graph forward, ogbn-products shape)"
 DIMS = {"ogbn-products": [100, 256, 256, 47], "ogbn-arxiv": [128, 256, 256, 40]}
 
 
+def _ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes, one launch) from a committed
+    `ncu --set full` raw page under profiles/, or None."""
+    import csv
+    path = os.path.join(ROOT, "profiles", name)
+    if not os.path.exists(path):
+        return None
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(key)
+            tot += float(vals[i].replace(",", "")) * mult[units[i]]
+        return tot
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -349,8 +369,8 @@ def run_b200(args):
 
         def step():
             with torch.no_grad():
-                return DT.sage_forward_sharded(sg, feats_pad, layers, norms)
-        launches_per_step = 3 + 3 + 1
+                return DT.sage_forward_sharded(sg, feats_pad, layers, norms, gather_output=False)
+        launches_per_step = 9 + 3 + 3 + 1
 
     def barrier():
         if world > 1:
@@ -378,7 +398,7 @@ def run_b200(args):
     if world > 1:  # per-phase device times of one sharded forward on every rank (diagnostic)
         tm = []
         with torch.no_grad():
-            DT.sage_forward_sharded(sg, feats_pad, layers, norms, timings=tm)
+            DT.sage_forward_sharded(sg, feats_pad, layers, norms, timings=tm, gather_output=False)
         torch.cuda.synchronize()
         phases = [(tm[i][0], round(tm[i - 1][1].elapsed_time(tm[i][1]), 3)) for i in range(1, len(tm))]
         info = {"rank": rank, "rows": sg.rows, "nnz": int(sg.indices.numel()), "phases_ms": phases}
@@ -426,7 +446,7 @@ def run_b200(args):
             keep = (sg.indptr, sg.indices)
             sg.indptr, sg.indices = d_ptr, d_idx
             with torch.no_grad():
-                o = DT.sage_forward_sharded(sg, d_feats, layers, norms)
+                o = DT.sage_forward_sharded(sg, d_feats, layers, norms, gather_output=False)
             sg.indptr, sg.indices = keep
             h_out.copy_(o[lo: lo + sg.rows], non_blocking=True)
 
@@ -462,8 +482,8 @@ def run_b200(args):
         "data": "synthetic",
         "config": {"workload": f"{workload} SAGE teacher full-graph forward + log_softmax",
                    "nodes": n, "edges": e, "dims": dims, "norm": "batch(eval)",
-                   "parallelism": "single GPU" if world == 1 else f"dst-row sharded x{world}, "
-                   "NCCL all-gather per layer",
+                   "parallelism": "single GPU" if world == 1 else f"dst-row sharded x{world}, one NCCL "
+                   "all-gather per layer exchange, output left sharded by rows",
                    "l2": "inputs (features 0.98 GB, CSR 0.5 GB, activations 2.5 GB) far exceed the "
                          "126 MB L2; no flush needed"},
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "nodes/s", "ms_per_step": e2e_ms,
@@ -487,7 +507,10 @@ def run_b200(args):
         gather_gbps = (dom[3] / 2 * 4) / (dom[1] * 1e-3) / 1e9  # 4 bytes per gathered element
         line["roofline"] = {
             "bound": "hbm", "kernel": "spmm_csr_kernel / " + dom[0], "achieved": achieved,
-            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None,
+            "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+            "traffic": _ncu_traffic("r1_spmm_d256.raw.csv"),
+            "traffic_source": "profiles/r1_spmm_d256.raw.csv (ncu --set full, same kernel, d=256, "
+                              "same graph generator)",
             "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[2],
             "gather_bytes_per_launch": dom[3] * 2, "gather_GBps": gather_gbps,
             "gather_frac_of_peak": gather_gbps / hbm_peak,

@@ -109,11 +109,13 @@ def _buffer(sg, key, rows, cols, like):
 
 
 def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None, log_softmax=True,
-                         timings=None):
+                         timings=None, gather_output=True):
     """layers: [(W [out,in], b)], norms: [(scale, shift)] folded eval-BN per hidden layer (or []).
     feats_pad: padded replica of the input features (valid on every rank).  Returns the padded
     replica [world * rows_max, label_dim] of the output (log-probabilities when log_softmax); the
-    returned tensor is a cached buffer that the next call overwrites.
+    returned tensor is a cached buffer that the next call overwrites.  With gather_output=False
+    the result stays sharded: only this rank's slab [rank*rows_max, +rows) of it is valid (what a
+    sharded consumer -- loss/accuracy reduction, a sharded student -- needs).
 
     Exchange plan: an aggregate-first layer needs the full replica of its input (all-gather of the
     previous output, d_in wide); a project-first layer (4-padded d_out < d_in) projects only the
@@ -187,5 +189,6 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
     else:
         out[lo:hi] = h[lo:hi, :c]
     mark("log_softmax")
-    gather(out)
+    if gather_output:  # otherwise every rank keeps only its own slab valid (rows lo:hi)
+        gather(out)
     return out
