@@ -267,13 +267,27 @@ def teacher_kernel_breakdown(g, feats, model, iters, torch):
                          2.0 * e * dpad, "spmm"))
             h = y[:, :d_out]
         else:
-            tp = ops.spmm_csr_planes(g.indptr, g.indices, h, d=d_in, self_add=True, mean_plus_one=True)
-            t = _event_ms(lambda: ops.spmm_csr_planes(g.indptr, g.indices, h, d=d_in, self_add=True,
-                                                      mean_plus_one=True, out=tp), iters, torch)
-            rows.append((f"L{l} spmm d={d_in} (-> planes)", t, idx_bytes + 8 * n * d_in,
-                         2.0 * e * d_in, "spmm"))
+            out_q24 = (not last) and (not out_planes) and d_out % 16 == 0 and d_out <= 512
+            if isinstance(h, ops.Q24):
+                tp = ops.spmm_csr_q24_planes(g.indptr, g.indices, h, self_add=True, mean_plus_one=True)
+                t = _event_ms(lambda: ops.spmm_csr_q24_planes(g.indptr, g.indices, h, self_add=True,
+                                                              mean_plus_one=True, out=tp), iters, torch)
+                rows.append((f"L{l} spmm d={d_in} (q24 -> planes)", t, idx_bytes + 8 * n * d_in,
+                             2.0 * e * d_in, "spmm"))
+            else:
+                tp = ops.spmm_csr_planes(g.indptr, g.indices, h, d=d_in, self_add=True,
+                                         mean_plus_one=True)
+                t = _event_ms(lambda: ops.spmm_csr_planes(g.indptr, g.indices, h, d=d_in, self_add=True,
+                                                          mean_plus_one=True, out=tp), iters, torch)
+                rows.append((f"L{l} spmm d={d_in} (-> planes)", t, idx_bytes + 8 * n * d_in,
+                             2.0 * e * d_in, "spmm"))
             wpl = ops.split_planes(w)
-            if out_planes:
+            if out_q24:
+                hq = ops.gemm_planes_q24(tp, wpl, bias=b, col_scale=scale, col_shift=shift, relu=relu)
+                t = _event_ms(lambda: ops.gemm_planes_q24(tp, wpl, out=hq, bias=b, col_scale=scale,
+                                                          col_shift=shift, relu=relu), iters, torch)
+                h = hq
+            elif out_planes:
                 t = _event_ms(lambda: ops.gemm_planes(tp, wpl, trans_b=True, out_planes=True, bias=b,
                                                       col_scale=scale, col_shift=shift, relu=relu),
                               iters, torch)
@@ -285,7 +299,8 @@ def teacher_kernel_breakdown(g, feats, model, iters, torch):
                                                       col_scale=scale, col_shift=shift, relu=relu),
                               iters, torch)
                 h = y[:, :d_out]
-            rows.append((f"L{l} gemm {d_in}->{d_out} (tcgen05 bf16x3, +BN+ReLU)", t,
+            rows.append((f"L{l} gemm {d_in}->{d_out} (tcgen05 bf16x3, +BN+ReLU"
+                         + (", q24 out)" if out_q24 else ")"), t,
                          4 * n * (d_in + d_out) + 4 * d_in * d_out, 2.0 * n * d_in * d_out, "gemm"))
     out = torch.empty(n, h.shape[1], device=feats.device)
     t = _event_ms(lambda: ops.log_softmax(h, out=out), iters, torch)

@@ -51,6 +51,10 @@ SIGNATURES = {
     "glnn_gemm_bf16x3_planes": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_i64, C.c_int, c_vp,
                                           c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp,
                                           c_vp, c_vp, C.c_int, c_vp]),
+    "glnn_gemm_bf16x3_planes_q24": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64,
+                                              c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp]),
+    "glnn_spmm_csr_q24_planes": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
+                                           C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "glnn_bn_fold_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, C.c_int, c_vp]),
     "glnn_log_softmax_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int, c_vp]),
     "glnn_nll_acc_f32": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -26,6 +26,9 @@ struct GemmArgs {
   const uint16_t *Ah, *Al, *Bh, *Bl;
   uint16_t *Ch, *Cl;
   int64_t ldcp;
+  // optional 24-bit row-packed output ("q24": per row N x hi16 then N x mid8, 3N bytes): the format
+  // a following neighbour GATHER reads when the layer output feeds an aggregate-first layer
+  uint8_t* Cq;
   int kb_per_split;
 };
 

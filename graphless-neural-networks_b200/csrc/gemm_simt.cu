@@ -249,6 +249,7 @@ extern "C" int glnn_gemm_f32(const float* A, int64_t lda, int transA, const floa
   g.Ah = g.Al = g.Bh = g.Bl = nullptr;
   g.Ch = g.Cl = nullptr;
   g.ldcp = 0;
+  g.Cq = nullptr;
   g.kb_per_split = 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (impl != 1) {

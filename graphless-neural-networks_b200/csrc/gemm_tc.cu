@@ -421,6 +421,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
             *reinterpret_cast<uint2*>(g.Ch + mr * g.ldcp + n) = hi;
             *reinterpret_cast<uint2*>(g.Cl + mr * g.ldcp + n) = lo;
           }
+          if (g.Cq && n + 3 < g.N) {  // q24: round to 24 bits, hi16 block then mid8 block of the row
+            const uint32_t b0 = __float_as_uint(v.x) + 0x80u, b1 = __float_as_uint(v.y) + 0x80u,
+                           b2 = __float_as_uint(v.z) + 0x80u, b3 = __float_as_uint(v.w) + 0x80u;
+            uint8_t* row = g.Cq + mr * (3 * g.N);
+            uint2 hi;
+            hi.x = (b0 >> 16) | (b1 & 0xFFFF0000u);
+            hi.y = (b2 >> 16) | (b3 & 0xFFFF0000u);
+            *reinterpret_cast<uint2*>(row + 2 * n) = hi;
+            *reinterpret_cast<uint32_t*>(row + 2 * g.N + n) =
+                ((b0 >> 8) & 0xFFu) | (((b1 >> 8) & 0xFFu) << 8) | (((b2 >> 8) & 0xFFu) << 16) |
+                (((b3 >> 8) & 0xFFu) << 24);
+          }
         }
       }
     }
@@ -488,7 +500,9 @@ int gemm_tc(const GemmArgs& g0, cudaStream_t st, bool force, bool* taken) {
 // idle.
 int gemm_tc_planes(GemmArgs g, cudaStream_t st) {
   GLNN_REQUIRE(g.Ah && g.Al && g.Bh && g.Bl, GLNN_ERR_ARG, "gemm_planes: null operand plane");
-  GLNN_REQUIRE(g.C || g.Ch, GLNN_ERR_ARG, "gemm_planes: no output");
+  GLNN_REQUIRE(g.C || g.Ch || g.Cq, GLNN_ERR_ARG, "gemm_planes: no output");
+  GLNN_REQUIRE(!g.Cq || (g.N % 16 == 0 && (reinterpret_cast<uintptr_t>(g.Cq) & 15) == 0), GLNN_ERR_ALIGN,
+               "gemm_planes: q24 output needs N %% 16 == 0 and a 16-byte aligned buffer");
   GLNN_REQUIRE((g.Ch == nullptr) == (g.Cl == nullptr), GLNN_ERR_ARG, "gemm_planes: C planes come in pairs");
   GLNN_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0 && aligned16(g.Ah) && aligned16(g.Al) &&
                    aligned16(g.Bh) && aligned16(g.Bl),
@@ -499,7 +513,7 @@ int gemm_tc_planes(GemmArgs g, cudaStream_t st) {
   const int64_t tiles = ((g.M + tc::BM - 1) / tc::BM) * ((g.N + bn - 1) / bn);
   const int nkb = static_cast<int>((g.K + tc::BK - 1) / tc::BK);
   int splits = 1;
-  const bool linear = !g.relu && !g.col_scale && !g.Ch && g.C;
+  const bool linear = !g.relu && !g.col_scale && !g.Ch && !g.Cq && g.C;
   if (linear && tiles * 2 <= sm_count() && nkb >= 16) {
     splits = static_cast<int>(std::min<int64_t>((sm_count() + tiles - 1) / tiles, nkb / 4));
     if (splits < 1) splits = 1;

@@ -45,6 +45,25 @@ int split_planes(const float* X, int64_t ldx, int64_t rows, int cols, uint16_t* 
   return 0;
 }
 
+// Projection whose result is written only in the 24-bit row-packed format read by a following gather.
+int gemm_planes_q24(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, const uint16_t* B_hi,
+                    const uint16_t* B_lo, int64_t ldb, int transB, uint8_t* Cq, int64_t M, int64_t N,
+                    int64_t K, const float* row_scale, const float* bias, const float* col_scale,
+                    const float* col_shift, int relu, cudaStream_t st) {
+  GemmArgs g;
+  g.A = nullptr; g.B = nullptr;
+  g.lda = lda; g.transA = 0; g.ldb = ldb; g.transB = transB ? 1 : 0;
+  g.C = nullptr; g.ldc = 0; g.M = M; g.N = N; g.K = K;
+  g.row_scale = row_scale; g.bias = bias; g.col_scale = col_scale; g.col_shift = col_shift;
+  g.relu = relu;
+  g.vecA = g.vecB = g.vecC = 0;
+  g.k_per_split = 0;
+  g.Ah = A_hi; g.Al = A_lo; g.Bh = B_hi; g.Bl = B_lo; g.Ch = nullptr; g.Cl = nullptr; g.ldcp = 0;
+  g.Cq = Cq;
+  g.kb_per_split = 0;
+  return gemm_tc_planes(g, st);
+}
+
 }  // namespace glnn
 
 extern "C" int glnn_split_planes_f32(const float* X, int64_t ldx, int64_t rows, int cols, uint16_t* hi,
@@ -83,6 +102,24 @@ extern "C" int glnn_gemm_bf16x3_planes(const uint16_t* A_hi, const uint16_t* A_l
   g.vecA = g.vecB = g.vecC = 0;
   g.k_per_split = 0;
   g.Ah = A_hi; g.Al = A_lo; g.Bh = B_hi; g.Bl = B_lo; g.Ch = C_hi; g.Cl = C_lo; g.ldcp = ldcp;
+  g.Cq = nullptr;
   g.kb_per_split = 0;
   return gemm_tc_planes(g, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int glnn_gemm_bf16x3_planes_q24(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda,
+                                           const uint16_t* B_hi, const uint16_t* B_lo, int64_t ldb,
+                                           int transB, uint8_t* C_q24, int64_t M, int64_t N, int64_t K,
+                                           const float* row_scale, const float* bias,
+                                           const float* col_scale, const float* col_shift, int relu,
+                                           glnn_stream_t stream) {
+  using namespace glnn;
+  GLNN_REQUIRE(M >= 0 && N >= 0 && K >= 0, GLNN_ERR_ARG, "gemm_planes_q24: negative size");
+  if (M == 0 || N == 0) return 0;
+  GLNN_REQUIRE(C_q24 != nullptr, GLNN_ERR_ARG, "gemm_planes_q24: null output");
+  GLNN_REQUIRE(lda >= K && ldb >= (transB ? K : N), GLNN_ERR_SHAPE, "gemm_planes_q24: leading dimension");
+  GLNN_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), GLNN_ERR_ARG,
+               "gemm_planes_q24: col_scale and col_shift must be given together");
+  return gemm_planes_q24(A_hi, A_lo, lda, B_hi, B_lo, ldb, transB, C_q24, M, N, K, row_scale, bias,
+                         col_scale, col_shift, relu, static_cast<cudaStream_t>(stream));
 }

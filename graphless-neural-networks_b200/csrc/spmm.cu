@@ -39,6 +39,7 @@ struct SpmmArgs {
   const int32_t* indices;
   const float* X;
   int64_t ldx;
+  const uint8_t* Xq;  // optional q24 input (row = d x hi16 then d x mid8, 3d bytes) instead of X
   float* Y;        // fp32 output (may be null when planes are written)
   int64_t ldy;
   uint16_t* Yh;    // optional bf16 hi / lo plane output
@@ -75,36 +76,56 @@ __device__ __forceinline__ int64_t load_ptr(const SpmmArgs& a, int64_t i) {
                     : static_cast<int64_t>(__ldg(reinterpret_cast<const int32_t*>(a.indptr) + i));
 }
 
+// W consecutive columns of source row `r`: W = 4 / 1 from the fp32 matrix, W = 8 from a q24 matrix
+// (16 bytes of hi16 + 8 bytes of mid8, value = (hi16 << 16 | mid8 << 8) as fp32 bits).
 template <int W>
-__device__ __forceinline__ void load_chunk(const float* p, float (&v)[W]) {
-  if constexpr (W == 4) {
-    float4 t = ldg4(p);
+__device__ __forceinline__ void load_chunk(const SpmmArgs& a, int64_t r, int col, float (&v)[W]) {
+  if constexpr (W == 8) {
+    const uint8_t* row = a.Xq + r * (3 * static_cast<int64_t>(a.d));
+    const uint4 h = __ldg(reinterpret_cast<const uint4*>(row + 2 * col));
+    const uint2 m = __ldg(reinterpret_cast<const uint2*>(row + 2 * a.d + col));
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+    const uint32_t mw[2] = {m.x, m.y};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const uint32_t hi = (i & 1) ? (hw[i >> 1] & 0xFFFF0000u) : (hw[i >> 1] << 16);
+      const uint32_t mid = ((mw[i >> 2] >> ((i & 3) * 8)) & 0xFFu) << 8;
+      v[i] = __uint_as_float(hi | mid);
+    }
+  } else if constexpr (W == 4) {
+    const float4 t = ldg4(a.X + r * a.ldx + col);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   } else {
-    v[0] = __ldg(p);
+    v[0] = __ldg(a.X + r * a.ldx + col);
+  }
+}
+
+__device__ __forceinline__ void store4(const SpmmArgs& a, int64_t row, int col, const float* v) {
+  if (a.Y) *reinterpret_cast<float4*>(a.Y + row * a.ldy + col) = make_float4(v[0], v[1], v[2], v[3]);
+  if (a.Yh) {
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[0] - f01.x, v[1] - f01.y);
+    const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[2] - f23.x, v[3] - f23.y);
+    uint2 uh, ul;
+    uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
+    ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(a.Yh + row * a.ldyp + col) = uh;
+    *reinterpret_cast<uint2*>(a.Yl + row * a.ldyp + col) = ul;
   }
 }
 
 template <int W>
 __device__ __forceinline__ void store_chunk(const SpmmArgs& a, int64_t row, int col,
                                             const float (&v)[W]) {
-  if (a.Y) {
-    float* p = a.Y + row * a.ldy + col;
-    if constexpr (W == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-    else p[0] = v[0];
-  }
-  if (a.Yh) {
-    if constexpr (W == 4) {
-      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
-      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-      const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[0] - f01.x, v[1] - f01.y);
-      const __nv_bfloat162 l23 = __floats2bfloat162_rn(v[2] - f23.x, v[3] - f23.y);
-      uint2 uh, ul;
-      uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
-      ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
-      *reinterpret_cast<uint2*>(a.Yh + row * a.ldyp + col) = uh;
-      *reinterpret_cast<uint2*>(a.Yl + row * a.ldyp + col) = ul;
-    } else {
+  if constexpr (W == 8) {
+    store4(a, row, col, v);
+    store4(a, row, col + 4, v + 4);
+  } else if constexpr (W == 4) {
+    store4(a, row, col, v);
+  } else {
+    if (a.Y) a.Y[row * a.ldy + col] = v[0];
+    if (a.Yh) {
       const __nv_bfloat16 h = __float2bfloat16_rn(v[0]);
       const __nv_bfloat16 l = __float2bfloat16_rn(v[0] - __bfloat162float(h));
       a.Yh[row * a.ldyp + col] = *reinterpret_cast<const uint16_t*>(&h);
@@ -117,7 +138,9 @@ __device__ __forceinline__ void store_chunk(const SpmmArgs& a, int64_t row, int 
 template <int G, int VPL, int W, bool HAS_SS>
 __device__ __forceinline__ void gather_range(const SpmmArgs& a, int64_t beg, int64_t end, int gl,
                                              int lane_base, unsigned gmask, float (&acc)[VPL][W]) {
-  constexpr int U = (G >= 4) ? 4 : G;
+  // neighbours in flight per group iteration: q24 rows are 25 % smaller and their decode costs
+  // registers, so keep 8 of them in flight as RAW words (6 registers each) and decode afterwards
+  constexpr int U = (W == 8) ? (G >= 8 ? 8 : G) : ((G >= 4) ? 4 : G);
   for (int64_t base = beg; base < end; base += G) {
     const int64_t e = base + gl;
     int my = -1;
@@ -130,33 +153,69 @@ __device__ __forceinline__ void gather_range(const SpmmArgs& a, int64_t beg, int
     for (int j = 0; j < cnt; j += U) {
       int u[U];
       float s[U];
-      float v[U][VPL][W];
 #pragma unroll
       for (int t = 0; t < U; ++t) {
         u[t] = __shfl_sync(gmask, my, lane_base + j + t);
         if constexpr (HAS_SS) s[t] = __shfl_sync(gmask, mys, lane_base + j + t);
       }
+      if constexpr (W == 8) {
+        uint4 hw[U][VPL];
+        uint2 mw[U][VPL];
 #pragma unroll
-      for (int t = 0; t < U; ++t) {
+        for (int t = 0; t < U; ++t) {
 #pragma unroll
-        for (int p = 0; p < VPL; ++p) {
-          const int col = (gl + p * G) * W;
-          if (u[t] >= 0 && col < a.d) {
-            load_chunk<W>(a.X + static_cast<int64_t>(u[t]) * a.ldx + col, v[t][p]);
-          } else {
-#pragma unroll
-            for (int w = 0; w < W; ++w) v[t][p][w] = 0.f;
+          for (int p = 0; p < VPL; ++p) {
+            const int col = (gl + p * G) * 8;
+            if (u[t] >= 0 && col < a.d) {
+              const uint8_t* row = a.Xq + static_cast<int64_t>(u[t]) * (3 * static_cast<int64_t>(a.d));
+              hw[t][p] = __ldg(reinterpret_cast<const uint4*>(row + 2 * col));
+              mw[t][p] = __ldg(reinterpret_cast<const uint2*>(row + 2 * a.d + col));
+            } else {
+              hw[t][p] = make_uint4(0u, 0u, 0u, 0u);
+              mw[t][p] = make_uint2(0u, 0u);
+            }
           }
         }
-      }
 #pragma unroll
-      for (int t = 0; t < U; ++t) {
+        for (int t = 0; t < U; ++t) {
 #pragma unroll
-        for (int p = 0; p < VPL; ++p) {
+          for (int p = 0; p < VPL; ++p) {
+            const uint32_t h4[4] = {hw[t][p].x, hw[t][p].y, hw[t][p].z, hw[t][p].w};
+            const uint32_t m2[2] = {mw[t][p].x, mw[t][p].y};
 #pragma unroll
-          for (int w = 0; w < W; ++w) {
-            if constexpr (HAS_SS) acc[p][w] = fmaf(v[t][p][w], s[t], acc[p][w]);
-            else acc[p][w] += v[t][p][w];
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t hi = (i & 1) ? (h4[i >> 1] & 0xFFFF0000u) : (h4[i >> 1] << 16);
+              const uint32_t mid = ((m2[i >> 2] >> ((i & 3) * 8)) & 0xFFu) << 8;
+              const float x = __uint_as_float(hi | mid);
+              if constexpr (HAS_SS) acc[p][i] = fmaf(x, s[t], acc[p][i]);
+              else acc[p][i] += x;
+            }
+          }
+        }
+      } else {
+        float v[U][VPL][W];
+#pragma unroll
+        for (int t = 0; t < U; ++t) {
+#pragma unroll
+          for (int p = 0; p < VPL; ++p) {
+            const int col = (gl + p * G) * W;
+            if (u[t] >= 0 && col < a.d) {
+              load_chunk<W>(a, static_cast<int64_t>(u[t]), col, v[t][p]);
+            } else {
+#pragma unroll
+              for (int w = 0; w < W; ++w) v[t][p][w] = 0.f;
+            }
+          }
+        }
+#pragma unroll
+        for (int t = 0; t < U; ++t) {
+#pragma unroll
+          for (int p = 0; p < VPL; ++p) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+              if constexpr (HAS_SS) acc[p][w] = fmaf(v[t][p][w], s[t], acc[p][w]);
+              else acc[p][w] += v[t][p][w];
+            }
           }
         }
       }
@@ -174,7 +233,7 @@ __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int64_t row, i
     const int col = (gl + p * G) * W;
     if (col >= a.d) continue;
     float self[W];
-    if (a.self_add) load_chunk<W>(a.X + row * a.ldx + col, self);
+    if (a.self_add) load_chunk<W>(a, row, col, self);
     float out[W];
 #pragma unroll
     for (int w = 0; w < W; ++w) {
@@ -228,9 +287,8 @@ __device__ __forceinline__ void cta_gather(const SpmmArgs& a, int64_t beg, int64
   }
 }
 
-template <int G, int VPL, bool VEC, bool HAS_SS>
-__global__ void __launch_bounds__(kWarps * 32) spmm_csr_kernel(const SpmmArgs a) {
-  constexpr int W = VEC ? 4 : 1;
+template <int G, int VPL, int W, bool HAS_SS>
+__global__ void __launch_bounds__(kWarps * 32, (VPL * W <= 8 ? 4 : 1)) spmm_csr_kernel(const SpmmArgs a) {
   constexpr int RPW = 32 / G;          // rows per warp
   constexpr int NG = kWarps * RPW;     // groups (= rows) per CTA
   __shared__ float s_part[NG][G * VPL * W];
@@ -311,9 +369,8 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_csr_kernel(const SpmmArgs a)
 }
 
 // Persistent drain of the hub task list: one task per CTA iteration.
-template <int G, int VPL, bool VEC, bool HAS_SS>
+template <int G, int VPL, int W, bool HAS_SS>
 __global__ void __launch_bounds__(kWarps * 32) spmm_hub_kernel(const SpmmArgs a) {
-  constexpr int W = VEC ? 4 : 1;
   constexpr int RPW = 32 / G;
   constexpr int NG = kWarps * RPW;
   __shared__ float s_part[NG][G * VPL * W];
@@ -346,9 +403,8 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_hub_kernel(const SpmmArgs a)
 }
 
 // Epilogue of the registered hub rows (one group per row).
-template <int G, int VPL, bool VEC>
+template <int G, int VPL, int W>
 __global__ void __launch_bounds__(kWarps * 32) spmm_hub_finish_kernel(const SpmmArgs a) {
-  constexpr int W = VEC ? 4 : 1;
   constexpr int RPW = 32 / G;
   constexpr int NG = kWarps * RPW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -371,7 +427,7 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_hub_finish_kernel(const Spmm
   }
 }
 
-template <int G, int VPL, bool VEC>
+template <int G, int VPL, int W>
 static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
   constexpr int NG = kWarps * (32 / G);
   const int64_t blocks = (a.n_dst + NG - 1) / NG;
@@ -380,28 +436,32 @@ static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
   GLNN_CUDA_OK(cudaMemsetAsync(a.hub_ctr, 0, 4 * sizeof(int), st));
   const unsigned nb = static_cast<unsigned>(blocks), hub_grid = static_cast<unsigned>(4 * sm_count());
   if (a.src_scale) {
-    spmm_csr_kernel<G, VPL, VEC, true><<<nb, kWarps * 32, 0, st>>>(a);
-    spmm_hub_kernel<G, VPL, VEC, true><<<hub_grid, kWarps * 32, 0, st>>>(a);
+    spmm_csr_kernel<G, VPL, W, true><<<nb, kWarps * 32, 0, st>>>(a);
+    spmm_hub_kernel<G, VPL, W, true><<<hub_grid, kWarps * 32, 0, st>>>(a);
   } else {
-    spmm_csr_kernel<G, VPL, VEC, false><<<nb, kWarps * 32, 0, st>>>(a);
-    spmm_hub_kernel<G, VPL, VEC, false><<<hub_grid, kWarps * 32, 0, st>>>(a);
+    spmm_csr_kernel<G, VPL, W, false><<<nb, kWarps * 32, 0, st>>>(a);
+    spmm_hub_kernel<G, VPL, W, false><<<hub_grid, kWarps * 32, 0, st>>>(a);
   }
-  spmm_hub_finish_kernel<G, VPL, VEC><<<32, kWarps * 32, 0, st>>>(a);
+  spmm_hub_finish_kernel<G, VPL, W><<<32, kWarps * 32, 0, st>>>(a);
   GLNN_LAUNCH_OK("spmm_csr_kernel");
   return 0;
 }
 
-template <bool VEC>
+template <int W>
 static int launch_width(const SpmmArgs& a, cudaStream_t st) {
-  const int lanes = VEC ? (a.d + 3) / 4 : a.d;  // column chunks per row
-  if (lanes <= 2) return launch_cfg<2, 1, VEC>(a, st);
-  if (lanes <= 4) return launch_cfg<4, 1, VEC>(a, st);
-  if (lanes <= 8) return launch_cfg<8, 1, VEC>(a, st);
-  if (lanes <= 16) return launch_cfg<16, 1, VEC>(a, st);
-  if (lanes <= 32) return launch_cfg<32, 1, VEC>(a, st);
-  if (lanes <= 64) return launch_cfg<32, 2, VEC>(a, st);
-  if (lanes <= 96) return launch_cfg<32, 3, VEC>(a, st);
-  return launch_cfg<32, 4, VEC>(a, st);
+  const int lanes = (a.d + W - 1) / W;  // column chunks per row
+  if (lanes <= 2) return launch_cfg<2, 1, W>(a, st);
+  if (lanes <= 4) return launch_cfg<4, 1, W>(a, st);
+  if (lanes <= 8) return launch_cfg<8, 1, W>(a, st);
+  if (lanes <= 16) return launch_cfg<16, 1, W>(a, st);
+  if (lanes <= 32) return launch_cfg<32, 1, W>(a, st);
+  if (lanes <= 64) return launch_cfg<32, 2, W>(a, st);
+  if constexpr (W == 8) {
+    return GLNN_ERR_SHAPE;  // q24 rows wider than 512 are not produced
+  } else {
+    if (lanes <= 96) return launch_cfg<32, 3, W>(a, st);
+    return launch_cfg<32, 4, W>(a, st);
+  }
 }
 
 // Hub scratch: one per (device, stream) so that concurrent streams never share counters.
@@ -433,15 +493,18 @@ static int hub_scratch(cudaStream_t st, HubScratch* out) {
 }
 
 int spmm_run(const void* indptr, int indptr64, const int32_t* indices, const float* X, int64_t ldx,
-             float* Y, int64_t ldy, uint16_t* Yh, uint16_t* Yl, int64_t ldyp, int64_t n_dst,
+             const uint8_t* Xq, float* Y, int64_t ldy, uint16_t* Yh, uint16_t* Yl, int64_t ldyp, int64_t n_dst,
              int64_t n_src, int d, int self_add, int mean_plus_one, const float* src_scale,
              const float* dst_scale, const float* bias, const float* col_scale,
              const float* col_shift, int relu, cudaStream_t st) {
   GLNN_REQUIRE(n_dst >= 0 && n_src >= 0 && d >= 0, GLNN_ERR_ARG, "spmm: negative size");
   if (n_dst == 0 || d == 0) return 0;
-  GLNN_REQUIRE(indptr && X && (Y || Yh), GLNN_ERR_ARG, "spmm: null indptr/X/Y");
+  GLNN_REQUIRE(indptr && (X || Xq) && (Y || Yh), GLNN_ERR_ARG, "spmm: null indptr/X/Y");
+  GLNN_REQUIRE(!Xq || (d % 16 == 0 && d <= 512 && aligned16(Xq)), GLNN_ERR_SHAPE,
+               "spmm: q24 input needs d %% 16 == 0 (16-byte aligned 3d-byte rows), d <= 512 and a "
+               "16-byte aligned buffer");
   GLNN_REQUIRE((Yh == nullptr) == (Yl == nullptr), GLNN_ERR_ARG, "spmm: output planes come in pairs");
-  GLNN_REQUIRE(ldx >= d && (!Y || ldy >= d) && (!Yh || ldyp >= d), GLNN_ERR_SHAPE,
+  GLNN_REQUIRE((Xq || ldx >= d) && (!Y || ldy >= d) && (!Yh || ldyp >= d), GLNN_ERR_SHAPE,
                "spmm: leading dimension smaller than d=%d", d);
   GLNN_REQUIRE(!self_add || n_src >= n_dst, GLNN_ERR_SHAPE,
                "spmm: self_add needs dst nodes to be a prefix of src nodes (n_src=%lld < n_dst=%lld)",
@@ -455,15 +518,19 @@ int spmm_run(const void* indptr, int indptr64, const int32_t* indices, const flo
   HubScratch hs;
   int rc = hub_scratch(st, &hs);
   if (rc != 0) return rc;
-  const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && (!Y || (ldy % 4 == 0 && aligned16(Y))) &&
-                   aligned16(X);
-  const int chunk = vec ? 512 : 128;
+  const bool q24 = Xq != nullptr;
+  const bool vec = q24 || ((d % 4 == 0) && (ldx % 4 == 0) && aligned16(X));
+  GLNN_REQUIRE(!q24 || ((!Y || (ldy % 4 == 0 && aligned16(Y))) && (!Yh || ldyp % 8 == 0)), GLNN_ERR_ALIGN,
+               "spmm: q24 input needs 16-byte aligned output rows");
+  const bool vec_out = (!Y || (ldy % 4 == 0 && aligned16(Y)));
+  const int chunk = (vec && vec_out) ? 512 : 128;
   for (int c0 = 0; c0 < d; c0 += chunk) {
     SpmmArgs a;
     a.indptr = indptr;
     a.indices = indices;
-    a.X = X + c0;
+    a.X = X ? X + c0 : nullptr;
     a.ldx = ldx;
+    a.Xq = Xq;
     a.Y = Y ? Y + c0 : nullptr;
     a.ldy = ldy;
     a.Yh = Yh ? Yh + c0 : nullptr;
@@ -486,7 +553,7 @@ int spmm_run(const void* indptr, int indptr64, const int32_t* indices, const flo
     a.hub_acc = hs.acc;
     a.cap_tasks = kCapTasks;
     a.cap_rows = kCapRows;
-    rc = vec ? launch_width<true>(a, st) : launch_width<false>(a, st);
+    rc = q24 ? launch_width<8>(a, st) : ((vec && vec_out) ? launch_width<4>(a, st) : launch_width<1>(a, st));
     if (rc != 0) return rc;
   }
   return 0;
@@ -501,7 +568,7 @@ extern "C" int glnn_spmm_csr_f32(const void* indptr, int indptr64, const int32_t
                                  const float* col_scale, const float* col_shift, int relu,
                                  glnn_stream_t stream) {
   GLNN_REQUIRE(Y != nullptr || n_dst <= 0 || d <= 0, GLNN_ERR_ARG, "spmm: null indptr/X/Y");
-  return glnn::spmm_run(indptr, indptr64, indices, X, ldx, Y, ldy, nullptr, nullptr, 0, n_dst, n_src, d,
+  return glnn::spmm_run(indptr, indptr64, indices, X, ldx, nullptr, Y, ldy, nullptr, nullptr, 0, n_dst, n_src, d,
                         self_add, mean_plus_one, src_scale, dst_scale, bias, col_scale, col_shift, relu,
                         static_cast<cudaStream_t>(stream));
 }
@@ -513,7 +580,18 @@ extern "C" int glnn_spmm_csr_planes(const void* indptr, int indptr64, const int3
                                     const float* bias, const float* col_scale, const float* col_shift,
                                     int relu, glnn_stream_t stream) {
   GLNN_REQUIRE((Y_hi && Y_lo) || n_dst <= 0 || d <= 0, GLNN_ERR_ARG, "spmm_planes: null output plane");
-  return glnn::spmm_run(indptr, indptr64, indices, X, ldx, nullptr, 0, Y_hi, Y_lo, ldyp, n_dst, n_src, d,
+  return glnn::spmm_run(indptr, indptr64, indices, X, ldx, nullptr, nullptr, 0, Y_hi, Y_lo, ldyp, n_dst, n_src, d,
                         self_add, mean_plus_one, src_scale, dst_scale, bias, col_scale, col_shift, relu,
                         static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int glnn_spmm_csr_q24_planes(const void* indptr, int indptr64, const int32_t* indices,
+                                        const uint8_t* X_q24, uint16_t* Y_hi, uint16_t* Y_lo,
+                                        int64_t ldyp, int64_t n_dst, int64_t n_src, int d, int self_add,
+                                        int mean_plus_one, const float* src_scale,
+                                        const float* dst_scale, glnn_stream_t stream) {
+  GLNN_REQUIRE((X_q24 && Y_hi && Y_lo) || n_dst <= 0 || d <= 0, GLNN_ERR_ARG, "spmm_q24: null pointer");
+  return glnn::spmm_run(indptr, indptr64, indices, nullptr, 0, X_q24, nullptr, 0, Y_hi, Y_lo, ldyp, n_dst,
+                        n_src, d, self_add, mean_plus_one, src_scale, dst_scale, nullptr, nullptr, nullptr,
+                        0, static_cast<cudaStream_t>(stream));
 }

@@ -15,7 +15,7 @@
 namespace glnn {
 
 int spmm_run(const void* indptr, int indptr64, const int32_t* indices, const float* X, int64_t ldx,
-             float* Y, int64_t ldy, uint16_t* Yh, uint16_t* Yl, int64_t ldyp, int64_t n_dst,
+             const uint8_t* Xq, float* Y, int64_t ldy, uint16_t* Yh, uint16_t* Yl, int64_t ldyp, int64_t n_dst,
              int64_t n_src, int d, int self_add, int mean_plus_one, const float* src_scale,
              const float* dst_scale, const float* bias, const float* col_scale,
              const float* col_shift, int relu, cudaStream_t st);                     // spmm.cu
@@ -57,6 +57,7 @@ struct Act {
   const uint16_t* hi = nullptr;
   const uint16_t* lo = nullptr;
   int64_t ldp = 0;
+  const uint8_t* q24 = nullptr;  // 24-bit row-packed copy for a following gather (3 d bytes per row)
   int d = 0;
 };
 
@@ -111,6 +112,11 @@ static int weight_planes(const glnn_gnn_layer& ly, bool out_in, int n_rows, floa
   if (n_rows > rows) GLNN_CUDA_OK(cudaMemsetAsync(base, 0, sizeof(uint16_t) * 2 * plane, st));
   return split_planes(ly.weight, cols, rows, cols, w->hi, w->lo, ldp, st);
 }
+
+int gemm_planes_q24(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, const uint16_t* B_hi,
+                    const uint16_t* B_lo, int64_t ldb, int transB, uint8_t* Cq, int64_t M, int64_t N,
+                    int64_t K, const float* row_scale, const float* bias, const float* col_scale,
+                    const float* col_shift, int relu, cudaStream_t st);  // planes.cu
 
 static int gemm_planes_call(const Act& a, const PlaneBuf& w, int transB, float* C, int64_t ldc,
                             uint16_t* Ch, uint16_t* Cl, int64_t ldcp, int64_t M, int64_t N, int64_t K,
@@ -180,6 +186,10 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
     const int dpad = pad4(ly.d_out);
     const int relu = last ? 0 : (gcn ? 2 : 1);
     const bool out_planes = !last && project_first(l + 1);
+    // a hidden output that only feeds the NEXT layer's gather is stored as 24-bit row-packed values
+    // (2^-17 relative, 3 instead of 4 bytes per gathered element -- the gather is DRAM-bound)
+    const bool out_q24 = !last && !out_planes && !project_first(l) && ly.d_out % 16 == 0 &&
+                         ly.d_out <= 512;
     int ib = 0;
     while (ib == hb) ++ib;
     int ob = 0;
@@ -203,7 +213,7 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
                             gcn ? src_norm : nullptr, none, 0, st);
       if (rc != 0) return rc;
       PlaneBuf yp = planes_in(buf[ob], n, dpad);
-      rc = spmm_run(indptr, indptr64, indices, buf[ib], dpad, out_planes ? nullptr : buf[ob], dpad,
+      rc = spmm_run(indptr, indptr64, indices, buf[ib], dpad, nullptr, out_planes ? nullptr : buf[ob], dpad,
                     out_planes ? yp.hi : nullptr, out_planes ? yp.lo : nullptr, yp.ldp, n, n, dpad,
                     gcn ? 0 : 1, gcn ? 0 : 1, nullptr, gcn ? dst_norm : nullptr, epi.bias, epi.scale,
                     epi.shift, relu, st);
@@ -213,9 +223,10 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
     } else {
       // aggregate (fp32 gather) straight into planes
       const float* hin = h.f32;
-      GLNN_REQUIRE(hin != nullptr, GLNN_ERR_ARG, "gnn_forward: internal: gather input must be fp32");
+      GLNN_REQUIRE(hin != nullptr || h.q24 != nullptr, GLNN_ERR_ARG,
+                   "gnn_forward: internal: gather input must be fp32 or q24");
       PlaneBuf tp = planes_in(buf[ib], n, ly.d_in);
-      rc = spmm_run(indptr, indptr64, indices, hin, h.ld, nullptr, 0, tp.hi, tp.lo, tp.ldp, n, n,
+      rc = spmm_run(indptr, indptr64, indices, hin, h.ld, h.q24, nullptr, 0, tp.hi, tp.lo, tp.ldp, n, n,
                     ly.d_in, gcn ? 0 : 1, gcn ? 0 : 1, gcn ? src_norm : nullptr, nullptr, nullptr,
                     nullptr, nullptr, 0, st);
       if (rc != 0) return rc;
@@ -226,12 +237,20 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
       Act t;
       t.hi = tp.hi; t.lo = tp.lo; t.ldp = tp.ldp; t.d = ly.d_in;
       PlaneBuf yp = planes_in(buf[ob], n, ly.d_out);
-      rc = gemm_planes_call(t, w, gcn ? 0 : 1, out_planes ? nullptr : buf[ob], dpad,
-                            out_planes ? yp.hi : nullptr, out_planes ? yp.lo : nullptr, yp.ldp, n,
-                            ly.d_out, ly.d_in, gcn ? dst_norm : nullptr, epi, relu, st);
-      if (rc != 0) return rc;
-      if (out_planes) { y.hi = yp.hi; y.lo = yp.lo; y.ldp = yp.ldp; }
-      else { y.f32 = buf[ob]; y.ld = dpad; }
+      if (out_q24) {
+        uint8_t* q = reinterpret_cast<uint8_t*>(buf[ob]);
+        rc = gemm_planes_q24(t.hi, t.lo, t.ldp, w.hi, w.lo, w.ldp, gcn ? 0 : 1, q, n, ly.d_out, ly.d_in,
+                             gcn ? dst_norm : nullptr, epi.bias, epi.scale, epi.shift, relu, st);
+        if (rc != 0) return rc;
+        y.q24 = q;
+      } else {
+        rc = gemm_planes_call(t, w, gcn ? 0 : 1, out_planes ? nullptr : buf[ob], dpad,
+                              out_planes ? yp.hi : nullptr, out_planes ? yp.lo : nullptr, yp.ldp, n,
+                              ly.d_out, ly.d_in, gcn ? dst_norm : nullptr, epi, relu, st);
+        if (rc != 0) return rc;
+        if (out_planes) { y.hi = yp.hi; y.lo = yp.lo; y.ldp = yp.ldp; }
+        else { y.f32 = buf[ob]; y.ld = dpad; }
+      }
     }
     h = y;
     hb = ob;

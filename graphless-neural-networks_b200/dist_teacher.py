@@ -135,45 +135,72 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
     def gather(buf):
         if world > 1:  # in place: this rank's slab already sits at its offset in the output
             dist.all_gather_into_tensor(buf, buf[lo: lo + rm], group=group)
-        mark(f"all_gather {tuple(buf.shape)}")
+        mark(f"all_gather {tuple(buf.shape)} {buf.dtype}".replace("torch.", ""))
 
     mark("start")
 
-    h, h_full = feats_pad, True
+    h, h_full = feats_pad, True   # h: fp32 replica, or ops.Q24 replica after a q24 hand-off
     L = len(layers)
+    planes_ok = hasattr(k, "spmm_csr_planes")
+
+    def proj_first(i):
+        d_o, d_i = layers[i][0].shape
+        sc = norms[i][0] if (norms and i != L - 1) else None
+        return ((d_o + 3) // 4 * 4) < d_i and (sc is None or d_o % 4 == 0)
+
     for l, (w, b) in enumerate(layers):
         last = l == L - 1
         scale, shift = (norms[l] if (norms and not last) else (None, None))
         relu = 0 if last else 1
         d_out, d_in = w.shape
         dpad = (d_out + 3) // 4 * 4
-        if dpad < d_in and (scale is None or dpad == d_out):
+        if proj_first(l):
             wp, bp = _pad_rows(w, b, dpad)
-            z = _buffer(sg, ("z", l), world * rm, dpad, h)
+            z = _buffer(sg, ("z", l), world * rm, dpad, feats_pad)
             k.gemm(h[lo:hi, :d_in], wp, trans_b=True, out=z[lo:hi])
             mark(f"L{l} gemm {d_in}->{dpad}")
             gather(z)
-            y = _buffer(sg, ("y", l), world * rm, dpad, h)
+            y = _buffer(sg, ("y", l), world * rm, dpad, feats_pad)
             k.spmm_csr(sg.indptr, sg.indices, z, d=dpad, out=y[lo:hi], dst_scale=sg.inv_deg1,
                        bias=bp, col_scale=scale, col_shift=shift, relu=relu)
             mark(f"L{l} spmm d={dpad}")
         else:
+            is_q24 = planes_ok and isinstance(h, k.Q24)
             if not h_full:
-                gather(h)
-            y = _buffer(sg, ("y", l), world * rm, dpad, h)
-            if hasattr(k, "spmm_csr_planes"):
+                gather(h.data if is_q24 else h)
+            # the output feeds another gather and nothing else -> exchange it as 24-bit rows
+            out_q24 = planes_ok and not last and not proj_first(l + 1) and d_out % 16 == 0 \
+                and d_out <= 512
+            if planes_ok:
                 # gather straight into bf16 hi/lo planes, the tensor-core projection's operand format
                 ldp = (d_in + 7) // 8 * 8
                 pl = sg.__dict__.setdefault("_planes", {}).get(l)
                 if pl is None or pl.hi.shape != (max(sg.rows, 1), ldp):
-                    mk = lambda: torch.zeros(max(sg.rows, 1), ldp, dtype=torch.int16, device=h.device)
+                    mk = lambda: torch.zeros(max(sg.rows, 1), ldp, dtype=torch.int16,
+                                             device=feats_pad.device)
                     pl = k.Planes(mk(), mk(), d_in)
                     sg._planes[l] = pl
-                k.spmm_csr_planes(sg.indptr, sg.indices, h, d=d_in, dst_scale=sg.inv_deg1, out=pl)
+                if is_q24:
+                    k.spmm_csr_q24_planes(sg.indptr, sg.indices, h, dst_scale=sg.inv_deg1, out=pl)
+                else:
+                    k.spmm_csr_planes(sg.indptr, sg.indices, h, d=d_in, dst_scale=sg.inv_deg1, out=pl)
                 mark(f"L{l} spmm d={d_in}")
-                k.gemm_planes(pl, k.split_planes(w), trans_b=True, out=y[lo:hi, :d_out], bias=b,
-                              col_scale=scale, col_shift=shift, relu=relu)
+                wpl = k.split_planes(w)
+                if out_q24:
+                    cache = sg.__dict__.setdefault("_bufs", {})
+                    yq = cache.get(("yq", l))
+                    if yq is None or yq.shape != (world * rm, 3 * d_out):
+                        yq = torch.zeros(world * rm, 3 * d_out, dtype=torch.uint8, device=feats_pad.device)
+                        cache[("yq", l)] = yq
+                    k.gemm_planes_q24(pl, wpl, out=k.Q24(yq[lo:hi], d_out), bias=b, col_scale=scale,
+                                      col_shift=shift, relu=relu)
+                    y = k.Q24(yq, d_out)
+                else:
+                    y = _buffer(sg, ("y", l), world * rm, dpad, feats_pad)
+                    k.gemm_planes(pl, wpl, trans_b=True, out=y[lo:hi, :d_out], bias=b, col_scale=scale,
+                                  col_shift=shift, relu=relu)
             else:
+                y = _buffer(sg, ("y", l), world * rm, dpad, h)
                 agg = _buffer(sg, ("agg", l), max(sg.rows, 1), (d_in + 3) // 4 * 4, h)
                 k.spmm_csr(sg.indptr, sg.indices, h, d=d_in, out=agg[: sg.rows, :d_in],
                            dst_scale=sg.inv_deg1)

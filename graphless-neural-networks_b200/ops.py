@@ -167,3 +167,54 @@ def spmm_csr_planes(indptr, indices, x, d=None, self_add=False, mean_plus_one=Fa
                                    ptr(dst_scale), ptr(bias), ptr(col_scale), ptr(col_shift),
                                    int(relu), stream()), "glnn_spmm_csr_planes")
     return out
+
+
+class Q24:
+    """24-bit row-packed matrix (see include/glnn_b200.h): .data uint8 [rows, 3 * cols]."""
+
+    def __init__(self, data, cols):
+        self.data, self.cols = data, cols
+
+    @property
+    def shape(self):
+        return (self.data.shape[0], self.cols)
+
+    def float(self):
+        n = self.cols
+        hi = self.data[:, :2 * n].contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
+        mid = self.data[:, 2 * n:].to(torch.int32)
+        return ((hi << 16) | (mid << 8)).view(torch.float32)
+
+
+def gemm_planes_q24(a, b, trans_b=True, out=None, row_scale=None, bias=None, col_scale=None,
+                    col_shift=None, relu=0):
+    """glnn_gemm_bf16x3_planes_q24: projection of Planes operands written as Q24."""
+    lib = _lib.load()
+    m, k = a.hi.shape[0], a.cols
+    kb, n = (b.cols, b.hi.shape[0]) if trans_b else (b.hi.shape[0], b.cols)
+    if k != kb:
+        raise ValueError("gemm_planes_q24: inner dimensions differ")
+    if out is None:
+        out = Q24(torch.empty(m, 3 * n, dtype=torch.uint8, device=a.hi.device), n)
+    check(lib.glnn_gemm_bf16x3_planes_q24(ptr(a.hi), ptr(a.lo), a.hi.stride(0), ptr(b.hi), ptr(b.lo),
+                                          b.hi.stride(0), int(trans_b), ptr(out.data), m, n, k,
+                                          ptr(row_scale), ptr(bias), ptr(col_scale), ptr(col_shift),
+                                          int(relu), stream()), "glnn_gemm_bf16x3_planes_q24")
+    return out
+
+
+def spmm_csr_q24_planes(indptr, indices, xq, self_add=False, mean_plus_one=False, src_scale=None,
+                        dst_scale=None, out=None):
+    """glnn_spmm_csr_q24_planes: aggregation of a Q24 matrix into Planes."""
+    lib = _lib.load()
+    n_dst, d = indptr.numel() - 1, xq.cols
+    if out is None:
+        ldp = (d + 7) // 8 * 8
+        out = Planes(torch.zeros(n_dst, ldp, dtype=torch.int16, device=xq.data.device),
+                     torch.zeros(n_dst, ldp, dtype=torch.int16, device=xq.data.device), d)
+    check(lib.glnn_spmm_csr_q24_planes(ptr(indptr), int(indptr.dtype == torch.int64), ptr(indices),
+                                       ptr(xq.data), ptr(out.hi), ptr(out.lo), out.hi.stride(0), n_dst,
+                                       xq.data.shape[0], d, int(self_add), int(mean_plus_one),
+                                       ptr(src_scale), ptr(dst_scale), stream()),
+          "glnn_spmm_csr_q24_planes")
+    return out

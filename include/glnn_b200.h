@@ -119,6 +119,23 @@ GLNN_API int glnn_gemm_bf16x3_planes(const uint16_t* A_hi, const uint16_t* A_lo,
                             const float* bias, const float* col_scale, const float* col_shift,
                             int relu, glnn_stream_t stream);
 
+/* 24-bit row-packed embeddings ("q24"): a hidden-layer output that is only read by the NEXT layer's
+ * neighbour gather is stored per row as N hi16 values followed by N mid8 values (the top 24 bits of
+ * each fp32, rounded to nearest: 2^-17 relative), 3N bytes per row, N % 16 == 0, N <= 512.  The
+ * gather is DRAM-bound on bytes per neighbour row, so this is 25 % less traffic on that kernel.
+ * glnn_gemm_bf16x3_planes_q24 = glnn_gemm_bf16x3_planes (transA = 0) with the q24 output only;
+ * glnn_spmm_csr_q24_planes = the aggregation reading q24 and writing bf16 hi/lo planes. */
+GLNN_API int glnn_gemm_bf16x3_planes_q24(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda,
+                                const uint16_t* B_hi, const uint16_t* B_lo, int64_t ldb, int transB,
+                                uint8_t* C_q24, int64_t M, int64_t N, int64_t K,
+                                const float* row_scale, const float* bias, const float* col_scale,
+                                const float* col_shift, int relu, glnn_stream_t stream);
+
+GLNN_API int glnn_spmm_csr_q24_planes(const void* indptr, int indptr64, const int32_t* indices,
+                             const uint8_t* X_q24, uint16_t* Y_hi, uint16_t* Y_lo, int64_t ldyp,
+                             int64_t n_dst, int64_t n_src, int d, int self_add, int mean_plus_one,
+                             const float* src_scale, const float* dst_scale, glnn_stream_t stream);
+
 /* K5 (eval): folds BatchNorm1d running statistics into a per-column affine for the epilogues
  * above: scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (models.py:139-141). */
 GLNN_API int glnn_bn_fold_f32(const float* gamma, const float* beta, const float* mean, const float* var,

@@ -115,6 +115,25 @@ def test_spmm_many_hubs_and_plane_output(dev):
     assert relerr(pl.float().cpu(), want) < 2e-5
 
 
+@pytest.mark.parametrize("d", [64, 128, 256, 512])
+def test_q24_projection_then_gather(dev, d):
+    """Hidden-layer hand-off in the 24-bit row-packed format: projection epilogue -> q24 -> gather."""
+    from glnn_b200 import ops
+    n, k = 3000, 72
+    indptr, indices = _rand_graph(n, n, 40000, seed=d, hubs=3, empty=4)
+    g = torch.Generator().manual_seed(d)
+    a, w, bias = torch.randn(n, k, generator=g), torch.randn(d, k, generator=g), torch.randn(d, generator=g)
+    h = (a.double() @ w.double().t() + bias.double()).clamp(min=0)
+    q = ops.gemm_planes_q24(ops.split_planes(a.to(dev)), ops.split_planes(w.to(dev)), bias=bias.to(dev),
+                            relu=1)
+    assert q.data.shape == (n, 3 * d)
+    assert relerr(q.float().cpu(), h) < 3e-5                      # bf16x3 GEMM + 2^-17 rounding
+    want = (O.spmm_sum(indptr, indices, h) + h) / (torch.from_numpy(np.diff(indptr)).double().unsqueeze(1) + 1)
+    ip, ix = torch.from_numpy(indptr).int().to(dev), torch.from_numpy(indices).int().to(dev)
+    got = ops.spmm_csr_q24_planes(ip, ix, q, self_add=True, mean_plus_one=True)
+    assert relerr(got.float().cpu(), want) < 5e-5
+
+
 def test_spmm_strided_views_and_bipartite(dev):
     """Column-sliced input/output (leading dimension > d) and n_src != n_dst (a block)."""
     from glnn_b200 import ops
