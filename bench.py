@@ -226,17 +226,28 @@ def _event_ms(fn, iters, torch):
 
 def teacher_kernel_breakdown(g, feats, model, iters, torch):
     """Per-stage CUDA-event times of one forward, launched through the same C-ABI calls, in the same
-    order and with the same operand formats as glnn_sage_forward (csrc/teacher.cu): aggregate-first
-    layers gather straight into bf16 hi/lo planes and project on tcgen05; a project-first layer
-    projects planes and gathers the narrow result with the epilogue fused."""
+    order and with the same operand formats as glnn_sage_forward (csrc/teacher.cu): every matrix a
+    gather reads is q24 (the caller's features are quantised once, projections write q24), an
+    aggregate-first layer gathers straight into bf16 hi/lo planes and projects on tcgen05, a
+    project-first layer projects planes -> q24 and gathers the narrow result with bias (and on the
+    last layer log_softmax) fused into the gather epilogue.  All outputs are preallocated."""
     from glnn_b200 import ops
     n, e = g.num_nodes(), g.num_edges()
+    dev = feats.device
     enc = model.encoder
     L = enc.num_layers
+    hot_mb = float(os.environ.get("GLNN_L2_HOT_MB", "0") or 0)
+    hot = lambda row_bytes: int(min(n, hot_mb * 1e6 / row_bytes))
     pf = [((c.fc_neigh.weight.shape[0] + 3) // 4 * 4) < c.fc_neigh.weight.shape[1] for c in enc.layers]
     rows = []
-    h = feats            # fp32 tensor or ops.Planes
     idx_bytes = 4 * (n + 1) + 4 * e
+    h = None  # Q24 or Planes
+    xq = ops.Q24.empty(n, feats.shape[1], dev)
+    t = _event_ms(lambda: ops.quantize_q24(feats, out=xq), iters, torch)
+    rows.append((f"L0 features fp32 -> q24 ({xq.ldq} B rows)", t, 4 * n * feats.shape[1] + n * xq.ldq,
+                 0.0, "rowwise"))
+    h = xq
+    out = None
     for l, conv in enumerate(enc.layers):
         w, b = conv.fc_neigh.weight.detach(), conv.fc_neigh.bias.detach()
         d_out, d_in = w.shape
@@ -249,62 +260,50 @@ def teacher_kernel_breakdown(g, feats, model, iters, torch):
             scale, shift = ops.bn_fold(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
         relu = 0 if last else 1
         if pf[l]:
-            wp = torch.zeros(dpad, d_in, device=w.device)
+            wp = torch.zeros(dpad, d_in, device=dev)
             wp[:d_out] = w
-            bp = torch.zeros(dpad, device=w.device)
+            bp = torch.zeros(dpad, device=dev)
             bp[:d_out] = b
             wpl = ops.split_planes(wp)
-            hp = h if isinstance(h, ops.Planes) else ops.split_planes(h)
-            z = torch.empty(n, dpad, device=w.device)
-            t = _event_ms(lambda: ops.gemm_planes(hp, wpl, trans_b=True, out=z), iters, torch)
-            rows.append((f"L{l} gemm {d_in}->{dpad} (project first, tcgen05 bf16x3)", t,
+            assert isinstance(h, ops.Planes)
+            zq = ops.Q24.empty(n, dpad, dev)
+            t = _event_ms(lambda: ops.gemm_planes_q24(h, wpl, out=zq), iters, torch)
+            rows.append((f"L{l} gemm {d_in}->{dpad} (project first, tcgen05 bf16x3, q24 out)", t,
                          4 * n * (d_in + dpad) + 4 * d_in * dpad, 2.0 * n * d_in * dpad, "gemm"))
-            y = torch.empty(n, dpad, device=w.device)
-            t = _event_ms(lambda: ops.spmm_csr(g.indptr, g.indices, z, out=y, self_add=True,
-                                               mean_plus_one=True, bias=bp, col_scale=scale,
-                                               col_shift=shift, relu=relu), iters, torch)
-            rows.append((f"L{l} spmm d={dpad} (+bias epilogue)", t, idx_bytes + 8 * n * dpad,
-                         2.0 * e * dpad, "spmm"))
-            h = y[:, :d_out]
+            out = torch.empty(n, d_out, device=dev)
+            t = _event_ms(lambda: ops.spmm(g.indptr, g.indices, zq, out=out, self_add=True,
+                                           mean_plus_one=True, bias=bp, col_scale=scale,
+                                           col_shift=shift, relu=relu,
+                                           log_softmax=d_out if last else 0,
+                                           hot_below=hot(zq.ldq)), iters, torch)
+            rows.append((f"L{l} spmm d={dpad} (q24 {zq.ldq} B rows, +bias"
+                         + (" +log_softmax" if last else "") + " epilogue)", t,
+                         idx_bytes + 8 * n * dpad, 2.0 * e * dpad, "spmm", zq.ldq))
+            h = out
         else:
-            out_q24 = (not last) and (not out_planes) and d_out % 16 == 0 and d_out <= 512
-            if isinstance(h, ops.Q24):
-                tp = ops.spmm_csr_q24_planes(g.indptr, g.indices, h, self_add=True, mean_plus_one=True)
-                t = _event_ms(lambda: ops.spmm_csr_q24_planes(g.indptr, g.indices, h, self_add=True,
-                                                              mean_plus_one=True, out=tp), iters, torch)
-                rows.append((f"L{l} spmm d={d_in} (q24 -> planes)", t, idx_bytes + 8 * n * d_in,
-                             2.0 * e * d_in, "spmm"))
-            else:
-                tp = ops.spmm_csr_planes(g.indptr, g.indices, h, d=d_in, self_add=True,
-                                         mean_plus_one=True)
-                t = _event_ms(lambda: ops.spmm_csr_planes(g.indptr, g.indices, h, d=d_in, self_add=True,
-                                                          mean_plus_one=True, out=tp), iters, torch)
-                rows.append((f"L{l} spmm d={d_in} (-> planes)", t, idx_bytes + 8 * n * d_in,
-                             2.0 * e * d_in, "spmm"))
+            assert isinstance(h, ops.Q24)
+            tp = ops.new_planes(n, d_in, dev)
+            hq = h
+            t = _event_ms(lambda: ops.spmm(g.indptr, g.indices, hq, out_planes=tp, self_add=True,
+                                           mean_plus_one=True, hot_below=hot(hq.ldq)), iters, torch)
+            rows.append((f"L{l} spmm d={d_in} (q24 {hq.ldq} B rows -> planes)", t,
+                         idx_bytes + 8 * n * d_in, 2.0 * e * d_in, "spmm", hq.ldq))
             wpl = ops.split_planes(w)
-            if out_q24:
-                hq = ops.gemm_planes_q24(tp, wpl, bias=b, col_scale=scale, col_shift=shift, relu=relu)
-                t = _event_ms(lambda: ops.gemm_planes_q24(tp, wpl, out=hq, bias=b, col_scale=scale,
-                                                          col_shift=shift, relu=relu), iters, torch)
-                h = hq
-            elif out_planes:
-                t = _event_ms(lambda: ops.gemm_planes(tp, wpl, trans_b=True, out_planes=True, bias=b,
+            if out_planes:
+                yp = ops.new_planes(n, d_out, dev)
+                t = _event_ms(lambda: ops.gemm_planes(tp, wpl, trans_b=True, out_planes=yp, bias=b,
                                                       col_scale=scale, col_shift=shift, relu=relu),
                               iters, torch)
-                h = ops.gemm_planes(tp, wpl, trans_b=True, out_planes=True, bias=b, col_scale=scale,
-                                    col_shift=shift, relu=relu)
+                h = yp
+                fmt = "planes out"
             else:
-                y = torch.empty(n, dpad, device=w.device)
-                t = _event_ms(lambda: ops.gemm_planes(tp, wpl, trans_b=True, out=y[:, :d_out], bias=b,
-                                                      col_scale=scale, col_shift=shift, relu=relu),
-                              iters, torch)
-                h = y[:, :d_out]
-            rows.append((f"L{l} gemm {d_in}->{d_out} (tcgen05 bf16x3, +BN+ReLU"
-                         + (", q24 out)" if out_q24 else ")"), t,
+                yq = ops.Q24.empty(n, d_out, dev)
+                t = _event_ms(lambda: ops.gemm_planes_q24(tp, wpl, out=yq, bias=b, col_scale=scale,
+                                                          col_shift=shift, relu=relu), iters, torch)
+                h = yq
+                fmt = "q24 out"
+            rows.append((f"L{l} gemm {d_in}->{d_out} (tcgen05 bf16x3, +BN+ReLU, {fmt})", t,
                          4 * n * (d_in + d_out) + 4 * d_in * d_out, 2.0 * n * d_in * d_out, "gemm"))
-    out = torch.empty(n, h.shape[1], device=feats.device)
-    t = _event_ms(lambda: ops.log_softmax(h, out=out), iters, torch)
-    rows.append(("log_softmax", t, 8 * n * h.shape[1], 0.0, "rowwise"))
     return rows
 
 
@@ -519,7 +518,8 @@ def run_b200(args):
                             "alg_GBps": round(r[2] / (r[1] * 1e-3) / 1e9, 1),
                             "TFLOPs": round(r[3] / (r[1] * 1e-3) / 1e12, 2)} for r in rows]
         achieved = dom[2] / (dom[1] * 1e-3) / 1e9
-        gather_gbps = (dom[3] / 2 * 4) / (dom[1] * 1e-3) / 1e9  # 4 bytes per gathered element
+        gather_bytes = e * dom[5] if len(dom) > 5 else dom[3] / 2 * 4  # E x bytes per gathered row
+        gather_gbps = gather_bytes / (dom[1] * 1e-3) / 1e9
         line["roofline"] = {
             "bound": "hbm", "kernel": "spmm_csr_kernel / " + dom[0], "achieved": achieved,
             "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -527,7 +527,7 @@ def run_b200(args):
             "traffic_source": "profiles/r1_spmm_d256.raw.csv (ncu --set full, same kernel, d=256, "
                               "same graph generator)",
             "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[2],
-            "gather_bytes_per_launch": dom[3] * 2, "gather_GBps": gather_gbps,
+            "gather_bytes_per_launch": gather_bytes, "gather_GBps": gather_gbps,
             "gather_frac_of_peak": gather_gbps / hbm_peak,
             "whole_forward": {"algorithmic_bytes": alg_bytes,
                               "achieved_GBps": alg_bytes / (ms * 1e-3) / 1e9,

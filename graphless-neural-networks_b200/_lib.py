@@ -29,6 +29,15 @@ class GnnLayer(C.Structure):
                 ("d_in", c_i32), ("d_out", c_i32)]
 
 
+class SpmmDesc(C.Structure):
+    _fields_ = [("indptr", c_vp), ("indices", c_vp), ("indptr64", c_i32), ("d", c_i32),
+                ("n_dst", c_i64), ("n_src", c_i64), ("X", c_vp), ("ldx", c_i64), ("X_q24", c_vp),
+                ("ldq", c_i64), ("Y", c_vp), ("ldy", c_i64), ("Y_hi", c_vp), ("Y_lo", c_vp),
+                ("ldyp", c_i64), ("self_add", c_i32), ("mean_plus_one", c_i32), ("src_scale", c_vp),
+                ("dst_scale", c_vp), ("bias", c_vp), ("col_scale", c_vp), ("col_shift", c_vp),
+                ("relu", c_i32), ("log_softmax", c_i32), ("hot_below", c_i32), ("reserved", c_i32)]
+
+
 class SageLayerHost(C.Structure):
     _fields_ = [("weight", c_vp), ("bias", c_vp), ("bn_gamma", c_vp), ("bn_beta", c_vp),
                 ("bn_mean", c_vp), ("bn_var", c_vp), ("d_in", c_i32), ("d_out", c_i32)]
@@ -51,10 +60,14 @@ SIGNATURES = {
     "glnn_gemm_bf16x3_planes": (C.c_int, [c_vp, c_vp, c_i64, C.c_int, c_vp, c_vp, c_i64, C.c_int, c_vp,
                                           c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp,
                                           c_vp, c_vp, C.c_int, c_vp]),
+    "glnn_q24_row_bytes": (c_i64, [C.c_int]),
+    "glnn_quantize_q24_f32": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, c_vp]),
     "glnn_gemm_bf16x3_planes_q24": (C.c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, C.c_int, c_vp, c_i64,
-                                              c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp]),
+                                              c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, C.c_int,
+                                              c_vp]),
     "glnn_spmm_csr_q24_planes": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
                                            C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
+    "glnn_spmm_csr": (C.c_int, [C.POINTER(SpmmDesc), c_vp]),
     "glnn_bn_fold_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, C.c_int, c_vp]),
     "glnn_log_softmax_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int, c_vp]),
     "glnn_nll_acc_f32": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),

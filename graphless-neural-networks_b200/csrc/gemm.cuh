@@ -29,11 +29,13 @@ struct GemmArgs {
   // optional 24-bit row-packed output ("q24": per row N x hi16 then N x mid8, 3N bytes): the format
   // a following neighbour GATHER reads when the layer output feeds an aggregate-first layer
   uint8_t* Cq;
+  int64_t ldcq;  // bytes between q24 rows (>= 3 N, multiple of 16); N % 8 == 0
   int kb_per_split;
 };
 
 int gemm_simt(GemmArgs g, cudaStream_t st);                    // gemm_simt.cu
 int gemm_tc(const GemmArgs& g, cudaStream_t st, bool force, bool* taken);  // gemm_tc.cu
 int gemm_tc_planes(GemmArgs g, cudaStream_t st);                             // gemm_tc.cu
+int gemm_tall_planes(const GemmArgs& g, cudaStream_t st, bool* taken);       // gemm_tall.cu
 
 }  // namespace glnn

@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "gemm.cuh"
+#include "tc_common.cuh"
 
 namespace glnn {
 namespace tc {
@@ -31,77 +32,6 @@ constexpr int BK = 64;          // fp32 elements per stage along K (= one 128-by
 constexpr int NPROD = 512;      // producer threads (16 warps)
 constexpr int NPWARPS = NPROD / 32;
 constexpr int NTHREADS = NPROD + 32;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// Bounded spin: a protocol bug must trap instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) return;
-    if (spin > (1u << 26)) __trap();
-  }
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// SWIZZLE_128B shared-memory matrix descriptor (version 1 = Blackwell).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
-  return d;
-}
-
-__device__ __forceinline__ void split4(const float4 v, uint2& hi, uint2& lo) {
-  const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y);
-  const __nv_bfloat162 h23 = __floats2bfloat162_rn(v.z, v.w);
-  const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-  const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y);
-  const __nv_bfloat162 l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
-  hi.x = *reinterpret_cast<const uint32_t*>(&h01);
-  hi.y = *reinterpret_cast<const uint32_t*>(&h23);
-  lo.x = *reinterpret_cast<const uint32_t*>(&l01);
-  lo.y = *reinterpret_cast<const uint32_t*>(&l23);
-}
 
 __device__ __forceinline__ float4 load4_guard(const float* p, int64_t i, int64_t lim) {
   if (i + 3 < lim) return ldg4(p + i);
@@ -231,9 +161,10 @@ struct Smem {
 template <int BN, bool A_K, bool B_K, bool PLANES, bool SPLIT>
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs g) {
   using S = Smem<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                              ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // pointer arithmetic on the array itself keeps the shared address space visible to the compiler
+  // (STS / LDS instead of generic ST / LD for the register-staged tiles and the epilogue staging)
+  uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + S::STAGES * S::STAGE);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + S::STAGES;    // [STAGES]
@@ -404,35 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
           const int64_t n = n0 + c4 * 4;
           if (n >= g.N) continue;
           const float4 v = *reinterpret_cast<const float4*>(cs + rr * (BN + 4) + c4 * 4);
-          if (g.C) {
-            float* cp = g.C + mr * g.ldc + n;
-            if (g.vecC && n + 3 < g.N) {
-              *reinterpret_cast<float4*>(cp) = v;
-            } else {
-              cp[0] = v.x;
-              if (n + 1 < g.N) cp[1] = v.y;
-              if (n + 2 < g.N) cp[2] = v.z;
-              if (n + 3 < g.N) cp[3] = v.w;
-            }
-          }
-          if (g.Ch && n + 3 < g.ldcp) {  // bf16 hi / lo planes of C (pad columns hold 0)
-            uint2 hi, lo;
-            split4(v, hi, lo);
-            *reinterpret_cast<uint2*>(g.Ch + mr * g.ldcp + n) = hi;
-            *reinterpret_cast<uint2*>(g.Cl + mr * g.ldcp + n) = lo;
-          }
-          if (g.Cq && n + 3 < g.N) {  // q24: round to 24 bits, hi16 block then mid8 block of the row
-            const uint32_t b0 = __float_as_uint(v.x) + 0x80u, b1 = __float_as_uint(v.y) + 0x80u,
-                           b2 = __float_as_uint(v.z) + 0x80u, b3 = __float_as_uint(v.w) + 0x80u;
-            uint8_t* row = g.Cq + mr * (3 * g.N);
-            uint2 hi;
-            hi.x = (b0 >> 16) | (b1 & 0xFFFF0000u);
-            hi.y = (b2 >> 16) | (b3 & 0xFFFF0000u);
-            *reinterpret_cast<uint2*>(row + 2 * n) = hi;
-            *reinterpret_cast<uint32_t*>(row + 2 * g.N + n) =
-                ((b0 >> 8) & 0xFFu) | (((b1 >> 8) & 0xFFu) << 8) | (((b2 >> 8) & 0xFFu) << 16) |
-                (((b3 >> 8) & 0xFFu) << 24);
-          }
+          emit4(g, mr, n, v);
         }
       }
     }
@@ -501,14 +404,22 @@ int gemm_tc(const GemmArgs& g0, cudaStream_t st, bool force, bool* taken) {
 int gemm_tc_planes(GemmArgs g, cudaStream_t st) {
   GLNN_REQUIRE(g.Ah && g.Al && g.Bh && g.Bl, GLNN_ERR_ARG, "gemm_planes: null operand plane");
   GLNN_REQUIRE(g.C || g.Ch || g.Cq, GLNN_ERR_ARG, "gemm_planes: no output");
-  GLNN_REQUIRE(!g.Cq || (g.N % 16 == 0 && (reinterpret_cast<uintptr_t>(g.Cq) & 15) == 0), GLNN_ERR_ALIGN,
-               "gemm_planes: q24 output needs N %% 16 == 0 and a 16-byte aligned buffer");
+  GLNN_REQUIRE(!g.Cq || (g.N % 8 == 0 && aligned16(g.Cq) && g.ldcq % 16 == 0 && g.ldcq >= 3 * g.N),
+               GLNN_ERR_ALIGN,
+               "gemm_planes: q24 output needs N %% 8 == 0, a 16-byte aligned buffer, ldq %% 16 == 0 and "
+               "ldq >= 3 N");
   GLNN_REQUIRE((g.Ch == nullptr) == (g.Cl == nullptr), GLNN_ERR_ARG, "gemm_planes: C planes come in pairs");
   GLNN_REQUIRE(g.lda % 8 == 0 && g.ldb % 8 == 0 && aligned16(g.Ah) && aligned16(g.Al) &&
                    aligned16(g.Bh) && aligned16(g.Bl),
                GLNN_ERR_ALIGN, "gemm_planes: operand planes need 16-byte aligned rows (ld %% 8 == 0)");
   GLNN_REQUIRE(!g.Ch || (g.ldcp % 4 == 0 && g.ldcp >= g.N), GLNN_ERR_ALIGN, "gemm_planes: bad ldcp");
   g.vecC = g.C && (g.ldc % 4 == 0) && aligned16(g.C);
+  {  // tall operands (the teacher's per-layer projection): persistent TMA-fed kernel
+    g.kb_per_split = 0;
+    bool taken = false;
+    const int rc = gemm_tall_planes(g, st, &taken);
+    if (rc != 0 || taken) return rc;
+  }
   const int bn = g.N > 128 ? 256 : 128;
   const int64_t tiles = ((g.M + tc::BM - 1) / tc::BM) * ((g.N + bn - 1) / bn);
   const int nkb = static_cast<int>((g.K + tc::BK - 1) / tc::BK);

@@ -47,8 +47,8 @@ int split_planes(const float* X, int64_t ldx, int64_t rows, int cols, uint16_t* 
 
 // Projection whose result is written only in the 24-bit row-packed format read by a following gather.
 int gemm_planes_q24(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, const uint16_t* B_hi,
-                    const uint16_t* B_lo, int64_t ldb, int transB, uint8_t* Cq, int64_t M, int64_t N,
-                    int64_t K, const float* row_scale, const float* bias, const float* col_scale,
+                    const uint16_t* B_lo, int64_t ldb, int transB, uint8_t* Cq, int64_t ldq, int64_t M,
+                    int64_t N, int64_t K, const float* row_scale, const float* bias, const float* col_scale,
                     const float* col_shift, int relu, cudaStream_t st) {
   GemmArgs g;
   g.A = nullptr; g.B = nullptr;
@@ -60,6 +60,7 @@ int gemm_planes_q24(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, con
   g.k_per_split = 0;
   g.Ah = A_hi; g.Al = A_lo; g.Bh = B_hi; g.Bl = B_lo; g.Ch = nullptr; g.Cl = nullptr; g.ldcp = 0;
   g.Cq = Cq;
+  g.ldcq = ldq;
   g.kb_per_split = 0;
   return gemm_tc_planes(g, st);
 }
@@ -103,13 +104,15 @@ extern "C" int glnn_gemm_bf16x3_planes(const uint16_t* A_hi, const uint16_t* A_l
   g.k_per_split = 0;
   g.Ah = A_hi; g.Al = A_lo; g.Bh = B_hi; g.Bl = B_lo; g.Ch = C_hi; g.Cl = C_lo; g.ldcp = ldcp;
   g.Cq = nullptr;
+  g.ldcq = 0;
   g.kb_per_split = 0;
   return gemm_tc_planes(g, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int glnn_gemm_bf16x3_planes_q24(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda,
                                            const uint16_t* B_hi, const uint16_t* B_lo, int64_t ldb,
-                                           int transB, uint8_t* C_q24, int64_t M, int64_t N, int64_t K,
+                                           int transB, uint8_t* C_q24, int64_t ldq, int64_t M, int64_t N,
+                                           int64_t K,
                                            const float* row_scale, const float* bias,
                                            const float* col_scale, const float* col_shift, int relu,
                                            glnn_stream_t stream) {
@@ -120,6 +123,6 @@ extern "C" int glnn_gemm_bf16x3_planes_q24(const uint16_t* A_hi, const uint16_t*
   GLNN_REQUIRE(lda >= K && ldb >= (transB ? K : N), GLNN_ERR_SHAPE, "gemm_planes_q24: leading dimension");
   GLNN_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), GLNN_ERR_ARG,
                "gemm_planes_q24: col_scale and col_shift must be given together");
-  return gemm_planes_q24(A_hi, A_lo, lda, B_hi, B_lo, ldb, transB, C_q24, M, N, K, row_scale, bias,
+  return gemm_planes_q24(A_hi, A_lo, lda, B_hi, B_lo, ldb, transB, C_q24, ldq, M, N, K, row_scale, bias,
                          col_scale, col_shift, relu, static_cast<cudaStream_t>(stream));
 }

@@ -21,6 +21,7 @@
 // tensor-core projection that follows an aggregate-first layer.
 #include <cuda_bf16.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 
@@ -39,7 +40,10 @@ struct SpmmArgs {
   const int32_t* indices;
   const float* X;
   int64_t ldx;
-  const uint8_t* Xq;  // optional q24 input (row = d x hi16 then d x mid8, 3d bytes) instead of X
+  const uint8_t* Xq;  // optional q24 input instead of X: row = dq x hi16 then dq x mid8 (dq = d
+                      // rounded up to 8), rows ldq bytes apart
+  int64_t ldq;
+  int dq;
   float* Y;        // fp32 output (may be null when planes are written)
   int64_t ldy;
   uint16_t* Yh;    // optional bf16 hi / lo plane output
@@ -56,6 +60,11 @@ struct SpmmArgs {
   const float* col_scale;
   const float* col_shift;
   int relu;
+  int log_softmax;       // epilogue ends with log_softmax over the first d_valid columns (scalar stores)
+  int d_valid;
+  // L2 residency hints: gathered rows of source ids < hot_below are loaded evict_last, all other
+  // gathered rows, the index stream and the output stream evict_first (0 = no hints)
+  int hot_below;
   // hub scratch (library-owned, per device and stream)
   int* hub_ctr;          // [0] tasks registered, [1] hub rows registered, [2] next task to run
   HubTask* hub_tasks;
@@ -76,32 +85,89 @@ __device__ __forceinline__ int64_t load_ptr(const SpmmArgs& a, int64_t i) {
                     : static_cast<int64_t>(__ldg(reinterpret_cast<const int32_t*>(a.indptr) + i));
 }
 
-// W consecutive columns of source row `r`: W = 4 / 1 from the fp32 matrix, W = 8 from a q24 matrix
-// (16 bytes of hi16 + 8 bytes of mid8, value = (hi16 << 16 | mid8 << 8) as fp32 bits).
-template <int W>
-__device__ __forceinline__ void load_chunk(const SpmmArgs& a, int64_t r, int col, float (&v)[W]) {
-  if constexpr (W == 8) {
-    const uint8_t* row = a.Xq + r * (3 * static_cast<int64_t>(a.d));
-    const uint4 h = __ldg(reinterpret_cast<const uint4*>(row + 2 * col));
-    const uint2 m = __ldg(reinterpret_cast<const uint2*>(row + 2 * a.d + col));
-    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-    const uint32_t mw[2] = {m.x, m.y};
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const uint32_t hi = (i & 1) ? (hw[i >> 1] & 0xFFFF0000u) : (hw[i >> 1] << 16);
-      const uint32_t mid = ((mw[i >> 2] >> ((i & 3) * 8)) & 0xFFu) << 8;
-      v[i] = __uint_as_float(hi | mid);
-    }
-  } else if constexpr (W == 4) {
-    const float4 t = ldg4(a.X + r * a.ldx + col);
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+// L2 eviction policies.  The gather of a power-law graph re-reads a small set of hub rows many times
+// while most rows are touched once per pass; marking the hub rows evict_last and every streaming
+// access evict_first keeps the hubs resident in the 126 MB L2 instead of letting the stream of cold
+// rows push them out.
+struct Policies {
+  uint64_t hot, cold;
+};
+__device__ __forceinline__ Policies make_policies(bool hints) {
+  Policies p;
+  if (hints) {
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.hot));
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.cold));
   } else {
-    v[0] = __ldg(a.X + r * a.ldx + col);
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p.hot));
+    p.cold = p.hot;
+  }
+  return p;
+}
+__device__ __forceinline__ uint4 ld16(const void* p, uint64_t pol) {
+  uint4 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint2 ld8(const void* p, uint64_t pol) {
+  uint2 r;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;"
+               : "=r"(r.x), "=r"(r.y)
+               : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld4(const void* p, uint64_t pol) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+  return r;
+}
+__device__ __forceinline__ void st16(void* p, const uint4 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w), "l"(pol)
+               : "memory");
+}
+__device__ __forceinline__ void st8(void* p, const uint2 v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y),
+               "l"(pol)
+               : "memory");
+}
+
+// q24 chunk: 8 values from 16 bytes of hi16 + 8 bytes of mid8, value = (hi16 << 16 | mid8 << 8).
+__device__ __forceinline__ void decode_q24(const uint4 h, const uint2 m, float (&v)[8]) {
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+  const uint32_t mw[2] = {m.x, m.y};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint32_t hi = (i & 1) ? (hw[i >> 1] & 0xFFFF0000u) : (hw[i >> 1] << 16);
+    const uint32_t mid = ((mw[i >> 2] >> ((i & 3) * 8)) & 0xFFu) << 8;
+    v[i] = __uint_as_float(hi | mid);
   }
 }
 
-__device__ __forceinline__ void store4(const SpmmArgs& a, int64_t row, int col, const float* v) {
-  if (a.Y) *reinterpret_cast<float4*>(a.Y + row * a.ldy + col) = make_float4(v[0], v[1], v[2], v[3]);
+// W consecutive columns of source row `r`: W = 4 / 1 from the fp32 matrix, W = 8 from a q24 matrix.
+template <int W>
+__device__ __forceinline__ void load_chunk(const SpmmArgs& a, int64_t r, int col, float (&v)[W],
+                                           uint64_t pol) {
+  if constexpr (W == 8) {
+    const uint8_t* row = a.Xq + r * a.ldq;
+    decode_q24(ld16(row + 2 * col, pol), ld8(row + 2 * a.dq + col, pol), v);
+  } else if constexpr (W == 4) {
+    const uint4 t = ld16(a.X + r * a.ldx + col, pol);
+    v[0] = __uint_as_float(t.x); v[1] = __uint_as_float(t.y);
+    v[2] = __uint_as_float(t.z); v[3] = __uint_as_float(t.w);
+  } else {
+    v[0] = __uint_as_float(ld4(a.X + r * a.ldx + col, pol));
+  }
+}
+
+__device__ __forceinline__ void store4(const SpmmArgs& a, int64_t row, int col, const float* v,
+                                       uint64_t pol) {
+  if (a.Y)
+    st16(a.Y + row * a.ldy + col,
+         make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
+                    __float_as_uint(v[3])),
+         pol);
   if (a.Yh) {
     const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
     const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
@@ -110,19 +176,19 @@ __device__ __forceinline__ void store4(const SpmmArgs& a, int64_t row, int col, 
     uint2 uh, ul;
     uh.x = *reinterpret_cast<const uint32_t*>(&h01); uh.y = *reinterpret_cast<const uint32_t*>(&h23);
     ul.x = *reinterpret_cast<const uint32_t*>(&l01); ul.y = *reinterpret_cast<const uint32_t*>(&l23);
-    *reinterpret_cast<uint2*>(a.Yh + row * a.ldyp + col) = uh;
-    *reinterpret_cast<uint2*>(a.Yl + row * a.ldyp + col) = ul;
+    st8(a.Yh + row * a.ldyp + col, uh, pol);
+    st8(a.Yl + row * a.ldyp + col, ul, pol);
   }
 }
 
 template <int W>
 __device__ __forceinline__ void store_chunk(const SpmmArgs& a, int64_t row, int col,
-                                            const float (&v)[W]) {
+                                            const float (&v)[W], uint64_t pol) {
   if constexpr (W == 8) {
-    store4(a, row, col, v);
-    store4(a, row, col + 4, v + 4);
+    store4(a, row, col, v, pol);
+    store4(a, row, col + 4, v + 4, pol);
   } else if constexpr (W == 4) {
-    store4(a, row, col, v);
+    store4(a, row, col, v, pol);
   } else {
     if (a.Y) a.Y[row * a.ldy + col] = v[0];
     if (a.Yh) {
@@ -137,7 +203,8 @@ __device__ __forceinline__ void store_chunk(const SpmmArgs& a, int64_t row, int 
 // acc += sum over edges [beg, end) of (scale *) X[indices[e], my columns]
 template <int G, int VPL, int W, bool HAS_SS>
 __device__ __forceinline__ void gather_range(const SpmmArgs& a, int64_t beg, int64_t end, int gl,
-                                             int lane_base, unsigned gmask, float (&acc)[VPL][W]) {
+                                             int lane_base, unsigned gmask, const Policies& pol,
+                                             float (&acc)[VPL][W]) {
   // neighbours in flight per group iteration: q24 rows are 25 % smaller and their decode costs
   // registers, so keep 8 of them in flight as RAW words (6 registers each) and decode afterwards
   constexpr int U = (W == 8) ? (G >= 8 ? 8 : G) : ((G >= 4) ? 4 : G);
@@ -146,7 +213,7 @@ __device__ __forceinline__ void gather_range(const SpmmArgs& a, int64_t beg, int
     int my = -1;
     float mys = 1.f;
     if (e < end) {
-      my = __ldg(a.indices + e);
+      my = static_cast<int>(ld4(a.indices + e, pol.cold));
       if constexpr (HAS_SS) mys = __ldg(a.src_scale + my);
     }
     const int cnt = static_cast<int>(min(static_cast<int64_t>(G), end - base));
@@ -163,13 +230,14 @@ __device__ __forceinline__ void gather_range(const SpmmArgs& a, int64_t beg, int
         uint2 mw[U][VPL];
 #pragma unroll
         for (int t = 0; t < U; ++t) {
+          const uint64_t pl = (u[t] < a.hot_below) ? pol.hot : pol.cold;
 #pragma unroll
           for (int p = 0; p < VPL; ++p) {
             const int col = (gl + p * G) * 8;
             if (u[t] >= 0 && col < a.d) {
-              const uint8_t* row = a.Xq + static_cast<int64_t>(u[t]) * (3 * static_cast<int64_t>(a.d));
-              hw[t][p] = __ldg(reinterpret_cast<const uint4*>(row + 2 * col));
-              mw[t][p] = __ldg(reinterpret_cast<const uint2*>(row + 2 * a.d + col));
+              const uint8_t* row = a.Xq + static_cast<int64_t>(u[t]) * a.ldq;
+              hw[t][p] = ld16(row + 2 * col, pl);
+              mw[t][p] = ld8(row + 2 * a.dq + col, pl);
             } else {
               hw[t][p] = make_uint4(0u, 0u, 0u, 0u);
               mw[t][p] = make_uint2(0u, 0u);
@@ -180,15 +248,12 @@ __device__ __forceinline__ void gather_range(const SpmmArgs& a, int64_t beg, int
         for (int t = 0; t < U; ++t) {
 #pragma unroll
           for (int p = 0; p < VPL; ++p) {
-            const uint32_t h4[4] = {hw[t][p].x, hw[t][p].y, hw[t][p].z, hw[t][p].w};
-            const uint32_t m2[2] = {mw[t][p].x, mw[t][p].y};
+            float x[8];
+            decode_q24(hw[t][p], mw[t][p], x);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const uint32_t hi = (i & 1) ? (h4[i >> 1] & 0xFFFF0000u) : (h4[i >> 1] << 16);
-              const uint32_t mid = ((m2[i >> 2] >> ((i & 3) * 8)) & 0xFFu) << 8;
-              const float x = __uint_as_float(hi | mid);
-              if constexpr (HAS_SS) acc[p][i] = fmaf(x, s[t], acc[p][i]);
-              else acc[p][i] += x;
+              if constexpr (HAS_SS) acc[p][i] = fmaf(x[i], s[t], acc[p][i]);
+              else acc[p][i] += x[i];
             }
           }
         }
@@ -196,11 +261,12 @@ __device__ __forceinline__ void gather_range(const SpmmArgs& a, int64_t beg, int
         float v[U][VPL][W];
 #pragma unroll
         for (int t = 0; t < U; ++t) {
+          const uint64_t pl = (u[t] < a.hot_below) ? pol.hot : pol.cold;
 #pragma unroll
           for (int p = 0; p < VPL; ++p) {
             const int col = (gl + p * G) * W;
             if (u[t] >= 0 && col < a.d) {
-              load_chunk<W>(a, static_cast<int64_t>(u[t]), col, v[t][p]);
+              load_chunk<W>(a, static_cast<int64_t>(u[t]), col, v[t][p], pl);
             } else {
 #pragma unroll
               for (int w = 0; w < W; ++w) v[t][p][w] = 0.f;
@@ -223,8 +289,23 @@ __device__ __forceinline__ void gather_range(const SpmmArgs& a, int64_t beg, int
   }
 }
 
+template <int G>
+__device__ __forceinline__ float group_max(float v, unsigned gmask) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(gmask, v, o));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v, unsigned gmask) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
+// Must be called by every lane of the group that owns `row` (the log-softmax tail reduces over it).
 template <int G, int VPL, int W>
 __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int64_t row, int64_t deg, int gl,
+                                               unsigned gmask, const Policies& pol,
                                                float (&acc)[VPL][W]) {
   const float inv_den = static_cast<float>(deg + 1);
   const float ds = a.dst_scale ? __ldg(a.dst_scale + row) : 1.f;
@@ -233,21 +314,57 @@ __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int64_t row, i
     const int col = (gl + p * G) * W;
     if (col >= a.d) continue;
     float self[W];
-    if (a.self_add) load_chunk<W>(a, row, col, self);
-    float out[W];
+    if (a.self_add) load_chunk<W>(a, row, col, self, pol.cold);
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       float x = acc[p][w];
       if (a.self_add) x += self[w];
       if (a.mean_plus_one) x = x / inv_den;
       x *= ds;
-      if (a.bias) x += __ldg(a.bias + col + w);
-      if (a.relu == 2) x = fmaxf(x, 0.f);
-      if (a.col_scale) x = fmaf(x, __ldg(a.col_scale + col + w), __ldg(a.col_shift + col + w));
-      if (a.relu == 1) x = fmaxf(x, 0.f);
-      out[w] = x;
+      if (col + w < a.d) {  // a q24 row ends in up to 7 zero pad columns: they stay zero
+        if (a.bias) x += __ldg(a.bias + col + w);
+        if (a.relu == 2) x = fmaxf(x, 0.f);
+        if (a.col_scale) x = fmaf(x, __ldg(a.col_scale + col + w), __ldg(a.col_shift + col + w));
+        if (a.relu == 1) x = fmaxf(x, 0.f);
+      } else {
+        x = 0.f;
+      }
+      acc[p][w] = x;
     }
-    store_chunk<W>(a, row, col, out);
+  }
+  if (a.log_softmax) {
+    // evaluate()'s log_softmax (train_and_eval.py:98) over the first d_valid columns, fused: the
+    // whole row lives in this group's registers
+    float m = -INFINITY;
+#pragma unroll
+    for (int p = 0; p < VPL; ++p)
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+        if ((gl + p * G) * W + w < a.d_valid) m = fmaxf(m, acc[p][w]);
+    m = group_max<G>(m, gmask);
+    float sum = 0.f;
+#pragma unroll
+    for (int p = 0; p < VPL; ++p)
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+        if ((gl + p * G) * W + w < a.d_valid) sum += expf(acc[p][w] - m);
+    sum = group_sum<G>(sum, gmask);
+    const float lse = m + logf(sum);
+    float* y = a.Y + row * a.ldy;
+#pragma unroll
+    for (int p = 0; p < VPL; ++p)
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const int c = (gl + p * G) * W + w;
+        if (c < a.d_valid) y[c] = acc[p][w] - lse;
+      }
+    return;
+  }
+#pragma unroll
+  for (int p = 0; p < VPL; ++p) {
+    const int col = (gl + p * G) * W;
+    if (col >= a.d) continue;
+    store_chunk<W>(a, row, col, acc[p], pol.cold);
   }
 }
 
@@ -263,13 +380,13 @@ __device__ __forceinline__ void zero_acc(float (&acc)[VPL][W]) {
 // through shared memory in group order; group 0 ends up with the sum in `acc`.
 template <int G, int VPL, int W, bool HAS_SS, int NG>
 __device__ __forceinline__ void cta_gather(const SpmmArgs& a, int64_t beg, int64_t end, int gidx, int gl,
-                                           int lane_base, unsigned gmask, float (*s_part)[G * VPL * W],
-                                           float (&acc)[VPL][W]) {
+                                           int lane_base, unsigned gmask, const Policies& pol,
+                                           float (*s_part)[G * VPL * W], float (&acc)[VPL][W]) {
   const int64_t len = end - beg;
   const int64_t seg = ((len + NG - 1) / NG + G - 1) / G * G;
   const int64_t sb = min(end, beg + gidx * seg), se = min(end, sb + seg);
   zero_acc<VPL, W>(acc);
-  gather_range<G, VPL, W, HAS_SS>(a, sb, se, gl, lane_base, gmask, acc);
+  gather_range<G, VPL, W, HAS_SS>(a, sb, se, gl, lane_base, gmask, pol, acc);
 #pragma unroll
   for (int p = 0; p < VPL; ++p)
 #pragma unroll
@@ -303,6 +420,7 @@ __global__ void __launch_bounds__(kWarps * 32, (VPL * W <= 8 ? 4 : 1)) spmm_csr_
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << lane_base);
   const int gidx = warp * RPW + sub;
   const int64_t row0 = static_cast<int64_t>(blockIdx.x) * NG;
+  const Policies pol = make_policies(a.hot_below > 0);
 
   if (threadIdx.x == 0) s_nhub = 0;
   __syncthreads();
@@ -350,8 +468,8 @@ __global__ void __launch_bounds__(kWarps * 32, (VPL * W <= 8 ? 4 : 1)) spmm_csr_
       } else {
         float acc[VPL][W];
         zero_acc<VPL, W>(acc);
-        gather_range<G, VPL, W, HAS_SS>(a, beg, end, gl, lane_base, gmask, acc);
-        epilogue_store<G, VPL, W>(a, row, deg, gl, acc);
+        gather_range<G, VPL, W, HAS_SS>(a, beg, end, gl, lane_base, gmask, pol, acc);
+        epilogue_store<G, VPL, W>(a, row, deg, gl, gmask, pol, acc);
       }
     }
   }
@@ -362,8 +480,8 @@ __global__ void __launch_bounds__(kWarps * 32, (VPL * W <= 8 ? 4 : 1)) spmm_csr_
     const int64_t row = row0 + s_hub[h];
     const int64_t beg = load_ptr(a, row), end = load_ptr(a, row + 1);
     float acc[VPL][W];
-    cta_gather<G, VPL, W, HAS_SS, NG>(a, beg, end, gidx, gl, lane_base, gmask, s_part, acc);
-    if (gidx == 0) epilogue_store<G, VPL, W>(a, row, end - beg, gl, acc);
+    cta_gather<G, VPL, W, HAS_SS, NG>(a, beg, end, gidx, gl, lane_base, gmask, pol, s_part, acc);
+    if (gidx == 0) epilogue_store<G, VPL, W>(a, row, end - beg, gl, gmask, pol, acc);
     __syncthreads();
   }
 }
@@ -379,6 +497,7 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_hub_kernel(const SpmmArgs a)
   const int sub = lane / G, gl = lane % G, lane_base = sub * G;
   const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << lane_base);
   const int gidx = warp * RPW + sub;
+  const Policies pol = make_policies(a.hot_below > 0);
   const int ntasks = min(a.hub_ctr[0], a.cap_tasks);
   for (;;) {
     __syncthreads();
@@ -388,8 +507,8 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_hub_kernel(const SpmmArgs a)
     if (t >= ntasks) break;
     const HubTask tk = a.hub_tasks[t];
     float acc[VPL][W];
-    cta_gather<G, VPL, W, HAS_SS, NG>(a, tk.beg, tk.beg + tk.len, gidx, gl, lane_base, gmask, s_part,
-                                      acc);
+    cta_gather<G, VPL, W, HAS_SS, NG>(a, tk.beg, tk.beg + tk.len, gidx, gl, lane_base, gmask, pol,
+                                      s_part, acc);
     if (gidx == 0 && tk.len > 0) {
 #pragma unroll
       for (int p = 0; p < VPL; ++p)
@@ -408,8 +527,10 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_hub_finish_kernel(const Spmm
   constexpr int RPW = 32 / G;
   constexpr int NG = kWarps * RPW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sub = lane / G, gl = lane % G;
+  const int sub = lane / G, gl = lane % G, lane_base = sub * G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << lane_base);
   const int gidx = warp * RPW + sub;
+  const Policies pol = make_policies(a.hot_below > 0);
   const int nrows = min(a.hub_ctr[1], a.cap_rows);
   for (int s = blockIdx.x * NG + gidx; s < nrows; s += gridDim.x * NG) {
     const int64_t row = a.hub_rows[s];
@@ -423,7 +544,7 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_hub_finish_kernel(const Spmm
         const int col = (gl + p * G) * W + w;
         acc[p][w] = col < a.d ? a.hub_acc[static_cast<int64_t>(s) * kHubAccLd + col] : 0.f;
       }
-    epilogue_store<G, VPL, W>(a, row, end - beg, gl, acc);
+    epilogue_store<G, VPL, W>(a, row, end - beg, gl, gmask, pol, acc);
   }
 }
 
@@ -492,61 +613,77 @@ static int hub_scratch(cudaStream_t st, HubScratch* out) {
   return 0;
 }
 
-int spmm_run(const void* indptr, int indptr64, const int32_t* indices, const float* X, int64_t ldx,
-             const uint8_t* Xq, float* Y, int64_t ldy, uint16_t* Yh, uint16_t* Yl, int64_t ldyp, int64_t n_dst,
-             int64_t n_src, int d, int self_add, int mean_plus_one, const float* src_scale,
-             const float* dst_scale, const float* bias, const float* col_scale,
-             const float* col_shift, int relu, cudaStream_t st) {
-  GLNN_REQUIRE(n_dst >= 0 && n_src >= 0 && d >= 0, GLNN_ERR_ARG, "spmm: negative size");
-  if (n_dst == 0 || d == 0) return 0;
-  GLNN_REQUIRE(indptr && (X || Xq) && (Y || Yh), GLNN_ERR_ARG, "spmm: null indptr/X/Y");
-  GLNN_REQUIRE(!Xq || (d % 16 == 0 && d <= 512 && aligned16(Xq)), GLNN_ERR_SHAPE,
-               "spmm: q24 input needs d %% 16 == 0 (16-byte aligned 3d-byte rows), d <= 512 and a "
-               "16-byte aligned buffer");
-  GLNN_REQUIRE((Yh == nullptr) == (Yl == nullptr), GLNN_ERR_ARG, "spmm: output planes come in pairs");
-  GLNN_REQUIRE((Xq || ldx >= d) && (!Y || ldy >= d) && (!Yh || ldyp >= d), GLNN_ERR_SHAPE,
-               "spmm: leading dimension smaller than d=%d", d);
-  GLNN_REQUIRE(!self_add || n_src >= n_dst, GLNN_ERR_SHAPE,
+int spmm_run(const glnn_spmm_desc& d0, cudaStream_t st) {
+  const glnn_spmm_desc& q = d0;
+  const int d = q.d;
+  GLNN_REQUIRE(q.n_dst >= 0 && q.n_src >= 0 && d >= 0, GLNN_ERR_ARG, "spmm: negative size");
+  if (q.n_dst == 0 || d == 0) return 0;
+  GLNN_REQUIRE(q.indptr && (q.X || q.X_q24) && (q.Y || q.Y_hi), GLNN_ERR_ARG, "spmm: null indptr/X/Y");
+  GLNN_REQUIRE(!(q.X && q.X_q24), GLNN_ERR_ARG, "spmm: give X or X_q24, not both");
+  const bool q24 = q.X_q24 != nullptr;
+  const int dq = (d + 7) / 8 * 8;
+  GLNN_REQUIRE(!q24 || (d <= 512 && aligned16(q.X_q24) && q.ldq % 16 == 0 && q.ldq >= 3 * dq),
+               GLNN_ERR_SHAPE,
+               "spmm: q24 input needs d <= 512, a 16-byte aligned buffer and ldq %% 16 == 0, ldq >= "
+               "3 * roundup(d, 8)");
+  GLNN_REQUIRE((q.Y_hi == nullptr) == (q.Y_lo == nullptr), GLNN_ERR_ARG, "spmm: output planes come in pairs");
+  const int dout = q24 ? dq : d;  // a q24 row is processed in whole 8-column chunks
+  GLNN_REQUIRE((q24 || q.ldx >= d) && (!q.Y || q.log_softmax || q.ldy >= dout) &&
+                   (!q.Y_hi || q.ldyp >= dout),
+               GLNN_ERR_SHAPE, "spmm: leading dimension smaller than d=%d", d);
+  GLNN_REQUIRE(!q.self_add || q.n_src >= q.n_dst, GLNN_ERR_SHAPE,
                "spmm: self_add needs dst nodes to be a prefix of src nodes (n_src=%lld < n_dst=%lld)",
-               (long long)n_src, (long long)n_dst);
-  GLNN_REQUIRE((col_scale == nullptr) == (col_shift == nullptr), GLNN_ERR_ARG,
+               (long long)q.n_src, (long long)q.n_dst);
+  GLNN_REQUIRE((q.col_scale == nullptr) == (q.col_shift == nullptr), GLNN_ERR_ARG,
                "spmm: col_scale and col_shift must be given together");
-  GLNN_REQUIRE(relu >= 0 && relu <= 2, GLNN_ERR_ARG, "spmm: relu must be 0, 1 or 2");
-  GLNN_REQUIRE(!Yh || (ldyp % 4 == 0 && (reinterpret_cast<uintptr_t>(Yh) & 7) == 0 &&
-                       (reinterpret_cast<uintptr_t>(Yl) & 7) == 0),
+  GLNN_REQUIRE(q.relu >= 0 && q.relu <= 2, GLNN_ERR_ARG, "spmm: relu must be 0, 1 or 2");
+  GLNN_REQUIRE(!q.Y_hi || (q.ldyp % 4 == 0 && (reinterpret_cast<uintptr_t>(q.Y_hi) & 7) == 0 &&
+                           (reinterpret_cast<uintptr_t>(q.Y_lo) & 7) == 0),
                GLNN_ERR_ALIGN, "spmm: output planes need ldyp %% 4 == 0 and 8-byte alignment");
+  GLNN_REQUIRE(q.log_softmax >= 0 && q.log_softmax <= d, GLNN_ERR_ARG,
+               "spmm: log_softmax must be 0 or the number of leading columns (<= d)");
+  GLNN_REQUIRE(!q.log_softmax || (q.Y && !q.Y_hi && d <= 512 && q.ldy >= q.log_softmax), GLNN_ERR_ARG,
+               "spmm: the log_softmax epilogue writes fp32 Y only, d <= 512, ldy >= log_softmax");
+  GLNN_REQUIRE(q.hot_below >= 0, GLNN_ERR_ARG, "spmm: hot_below must be >= 0");
   HubScratch hs;
   int rc = hub_scratch(st, &hs);
   if (rc != 0) return rc;
-  const bool q24 = Xq != nullptr;
-  const bool vec = q24 || ((d % 4 == 0) && (ldx % 4 == 0) && aligned16(X));
-  GLNN_REQUIRE(!q24 || ((!Y || (ldy % 4 == 0 && aligned16(Y))) && (!Yh || ldyp % 8 == 0)), GLNN_ERR_ALIGN,
-               "spmm: q24 input needs 16-byte aligned output rows");
-  const bool vec_out = (!Y || (ldy % 4 == 0 && aligned16(Y)));
+  const bool vec = q24 || ((d % 4 == 0) && (q.ldx % 4 == 0) && aligned16(q.X));
+  GLNN_REQUIRE(!q24 || ((!q.Y || q.log_softmax || (q.ldy % 4 == 0 && aligned16(q.Y))) &&
+                        (!q.Y_hi || q.ldyp % 8 == 0)),
+               GLNN_ERR_ALIGN, "spmm: q24 input needs 16-byte aligned output rows");
+  const bool vec_out = (!q.Y || q.log_softmax || (q.ldy % 4 == 0 && aligned16(q.Y)));
   const int chunk = (vec && vec_out) ? 512 : 128;
+  GLNN_REQUIRE(!q.log_softmax || d <= chunk, GLNN_ERR_SHAPE,
+               "spmm: the log_softmax epilogue needs the row in one launch (d <= %d here)", chunk);
   for (int c0 = 0; c0 < d; c0 += chunk) {
     SpmmArgs a;
-    a.indptr = indptr;
-    a.indices = indices;
-    a.X = X ? X + c0 : nullptr;
-    a.ldx = ldx;
-    a.Xq = Xq;
-    a.Y = Y ? Y + c0 : nullptr;
-    a.ldy = ldy;
-    a.Yh = Yh ? Yh + c0 : nullptr;
-    a.Yl = Yl ? Yl + c0 : nullptr;
-    a.ldyp = ldyp;
-    a.n_dst = n_dst;
+    a.indptr = q.indptr;
+    a.indices = q.indices;
+    a.X = q.X ? q.X + c0 : nullptr;
+    a.ldx = q.ldx;
+    a.Xq = q.X_q24;
+    a.ldq = q.ldq;
+    a.dq = dq;
+    a.Y = q.Y ? q.Y + c0 : nullptr;
+    a.ldy = q.ldy;
+    a.Yh = q.Y_hi ? q.Y_hi + c0 : nullptr;
+    a.Yl = q.Y_lo ? q.Y_lo + c0 : nullptr;
+    a.ldyp = q.ldyp;
+    a.n_dst = q.n_dst;
     a.d = min(chunk, d - c0);
-    a.indptr64 = indptr64;
-    a.self_add = self_add;
-    a.mean_plus_one = mean_plus_one;
-    a.src_scale = src_scale;
-    a.dst_scale = dst_scale;
-    a.bias = bias ? bias + c0 : nullptr;
-    a.col_scale = col_scale ? col_scale + c0 : nullptr;
-    a.col_shift = col_shift ? col_shift + c0 : nullptr;
-    a.relu = relu;
+    a.indptr64 = q.indptr64;
+    a.self_add = q.self_add;
+    a.mean_plus_one = q.mean_plus_one;
+    a.src_scale = q.src_scale;
+    a.dst_scale = q.dst_scale;
+    a.bias = q.bias ? q.bias + c0 : nullptr;
+    a.col_scale = q.col_scale ? q.col_scale + c0 : nullptr;
+    a.col_shift = q.col_shift ? q.col_shift + c0 : nullptr;
+    a.relu = q.relu;
+    a.log_softmax = q.log_softmax > 0;
+    a.d_valid = q.log_softmax;
+    a.hot_below = q.hot_below;
     a.hub_ctr = hs.ctr;
     a.hub_tasks = hs.tasks;
     a.hub_rows = hs.rows;
@@ -559,7 +696,80 @@ int spmm_run(const void* indptr, int indptr64, const int32_t* indices, const flo
   return 0;
 }
 
+// fp32 -> q24 (top 24 bits of each value, rounded to nearest; pad columns zero).
+__global__ void __launch_bounds__(256) quantize_q24_kernel(const float* __restrict__ X, int64_t ldx,
+                                                           int64_t rows, int d, int dq,
+                                                           uint8_t* __restrict__ Q, int64_t ldq) {
+  const int cpr = dq / 4;  // 4-column pieces per row
+  const int64_t total = rows * cpr;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / cpr;
+    const int c = static_cast<int>(i % cpr) * 4;
+    uint32_t b[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      b[j] = (c + j < d) ? __float_as_uint(__ldg(X + r * ldx + c + j)) + 0x80u : 0u;
+    uint8_t* row = Q + r * ldq;
+    uint2 hi;
+    hi.x = (b[0] >> 16) | (b[1] & 0xFFFF0000u);
+    hi.y = (b[2] >> 16) | (b[3] & 0xFFFF0000u);
+    *reinterpret_cast<uint2*>(row + 2 * c) = hi;
+    *reinterpret_cast<uint32_t*>(row + 2 * dq + c) = ((b[0] >> 8) & 0xFFu) | (((b[1] >> 8) & 0xFFu) << 8) |
+                                                     (((b[2] >> 8) & 0xFFu) << 16) |
+                                                     (((b[3] >> 8) & 0xFFu) << 24);
+  }
+}
+
+int quantize_q24(const float* X, int64_t ldx, int64_t rows, int d, uint8_t* Q, int64_t ldq,
+                 cudaStream_t st) {
+  if (rows == 0 || d == 0) return 0;
+  const int dq = (d + 7) / 8 * 8;
+  const int64_t total = rows * (dq / 4);
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, 16LL * sm_count()));
+  quantize_q24_kernel<<<blocks, 256, 0, st>>>(X, ldx, rows, d, dq, Q, ldq);
+  GLNN_LAUNCH_OK("quantize_q24_kernel");
+  return 0;
+}
+
 }  // namespace glnn
+
+extern "C" int glnn_spmm_csr(const glnn_spmm_desc* desc, glnn_stream_t stream) {
+  GLNN_REQUIRE(desc != nullptr, GLNN_ERR_ARG, "spmm: null descriptor");
+  return glnn::spmm_run(*desc, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int64_t glnn_q24_row_bytes(int d) {
+  if (d <= 0) return 0;
+  const int64_t dq = (d + 7) / 8 * 8;
+  return (3 * dq + 31) / 32 * 32;
+}
+
+extern "C" int glnn_quantize_q24_f32(const float* X, int64_t ldx, int64_t rows, int d, uint8_t* X_q24,
+                                     int64_t ldq, glnn_stream_t stream) {
+  using namespace glnn;
+  GLNN_REQUIRE(rows >= 0 && d >= 0, GLNN_ERR_ARG, "quantize_q24: negative size");
+  if (rows == 0 || d == 0) return 0;
+  GLNN_REQUIRE(X && X_q24, GLNN_ERR_ARG, "quantize_q24: null pointer");
+  const int dq = (d + 7) / 8 * 8;
+  GLNN_REQUIRE(ldx >= d && ldq >= 3 * dq && ldq % 16 == 0 && aligned16(X_q24), GLNN_ERR_SHAPE,
+               "quantize_q24: need ldx >= d, ldq >= 3 * roundup(d, 8), ldq %% 16 == 0, 16-byte aligned output");
+  return quantize_q24(X, ldx, rows, d, X_q24, ldq, static_cast<cudaStream_t>(stream));
+}
+
+static glnn_spmm_desc spmm_desc_basic(const void* indptr, int indptr64, const int32_t* indices,
+                                      int64_t n_dst, int64_t n_src, int d, int self_add,
+                                      int mean_plus_one, const float* src_scale,
+                                      const float* dst_scale, const float* bias,
+                                      const float* col_scale, const float* col_shift, int relu) {
+  glnn_spmm_desc q{};
+  q.indptr = indptr; q.indptr64 = indptr64; q.indices = indices;
+  q.n_dst = n_dst; q.n_src = n_src; q.d = d;
+  q.self_add = self_add; q.mean_plus_one = mean_plus_one;
+  q.src_scale = src_scale; q.dst_scale = dst_scale; q.bias = bias;
+  q.col_scale = col_scale; q.col_shift = col_shift; q.relu = relu;
+  return q;
+}
 
 extern "C" int glnn_spmm_csr_f32(const void* indptr, int indptr64, const int32_t* indices,
                                  const float* X, int64_t ldx, float* Y, int64_t ldy, int64_t n_dst,
@@ -568,9 +778,10 @@ extern "C" int glnn_spmm_csr_f32(const void* indptr, int indptr64, const int32_t
                                  const float* col_scale, const float* col_shift, int relu,
                                  glnn_stream_t stream) {
   GLNN_REQUIRE(Y != nullptr || n_dst <= 0 || d <= 0, GLNN_ERR_ARG, "spmm: null indptr/X/Y");
-  return glnn::spmm_run(indptr, indptr64, indices, X, ldx, nullptr, Y, ldy, nullptr, nullptr, 0, n_dst, n_src, d,
-                        self_add, mean_plus_one, src_scale, dst_scale, bias, col_scale, col_shift, relu,
-                        static_cast<cudaStream_t>(stream));
+  glnn_spmm_desc q = spmm_desc_basic(indptr, indptr64, indices, n_dst, n_src, d, self_add, mean_plus_one,
+                                     src_scale, dst_scale, bias, col_scale, col_shift, relu);
+  q.X = X; q.ldx = ldx; q.Y = Y; q.ldy = ldy;
+  return glnn::spmm_run(q, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int glnn_spmm_csr_planes(const void* indptr, int indptr64, const int32_t* indices,
@@ -580,9 +791,10 @@ extern "C" int glnn_spmm_csr_planes(const void* indptr, int indptr64, const int3
                                     const float* bias, const float* col_scale, const float* col_shift,
                                     int relu, glnn_stream_t stream) {
   GLNN_REQUIRE((Y_hi && Y_lo) || n_dst <= 0 || d <= 0, GLNN_ERR_ARG, "spmm_planes: null output plane");
-  return glnn::spmm_run(indptr, indptr64, indices, X, ldx, nullptr, nullptr, 0, Y_hi, Y_lo, ldyp, n_dst, n_src, d,
-                        self_add, mean_plus_one, src_scale, dst_scale, bias, col_scale, col_shift, relu,
-                        static_cast<cudaStream_t>(stream));
+  glnn_spmm_desc q = spmm_desc_basic(indptr, indptr64, indices, n_dst, n_src, d, self_add, mean_plus_one,
+                                     src_scale, dst_scale, bias, col_scale, col_shift, relu);
+  q.X = X; q.ldx = ldx; q.Y_hi = Y_hi; q.Y_lo = Y_lo; q.ldyp = ldyp;
+  return glnn::spmm_run(q, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int glnn_spmm_csr_q24_planes(const void* indptr, int indptr64, const int32_t* indices,
@@ -591,7 +803,9 @@ extern "C" int glnn_spmm_csr_q24_planes(const void* indptr, int indptr64, const 
                                         int mean_plus_one, const float* src_scale,
                                         const float* dst_scale, glnn_stream_t stream) {
   GLNN_REQUIRE((X_q24 && Y_hi && Y_lo) || n_dst <= 0 || d <= 0, GLNN_ERR_ARG, "spmm_q24: null pointer");
-  return glnn::spmm_run(indptr, indptr64, indices, nullptr, 0, X_q24, nullptr, 0, Y_hi, Y_lo, ldyp, n_dst,
-                        n_src, d, self_add, mean_plus_one, src_scale, dst_scale, nullptr, nullptr, nullptr,
-                        0, static_cast<cudaStream_t>(stream));
+  glnn_spmm_desc q = spmm_desc_basic(indptr, indptr64, indices, n_dst, n_src, d, self_add, mean_plus_one,
+                                     src_scale, dst_scale, nullptr, nullptr, nullptr, 0);
+  q.X_q24 = X_q24; q.ldq = 3 * static_cast<int64_t>((d + 7) / 8 * 8);
+  q.Y_hi = Y_hi; q.Y_lo = Y_lo; q.ldyp = ldyp;
+  return glnn::spmm_run(q, static_cast<cudaStream_t>(stream));
 }

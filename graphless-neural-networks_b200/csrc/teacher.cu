@@ -6,19 +6,17 @@
 //   project-first   : Z = H W               ; Y = epi(agg(Z) + b)      (epilogue in the gather)
 // Narrow outputs (47 classes, 7 classes) are padded to a multiple of 4 columns inside the
 // workspace so that every gathered row is 16-byte aligned; the pad is stripped at the boundary.
-#include <vector>
-
 #include <algorithm>
+#include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
 namespace glnn {
 
-int spmm_run(const void* indptr, int indptr64, const int32_t* indices, const float* X, int64_t ldx,
-             const uint8_t* Xq, float* Y, int64_t ldy, uint16_t* Yh, uint16_t* Yl, int64_t ldyp, int64_t n_dst,
-             int64_t n_src, int d, int self_add, int mean_plus_one, const float* src_scale,
-             const float* dst_scale, const float* bias, const float* col_scale,
-             const float* col_shift, int relu, cudaStream_t st);                     // spmm.cu
+int spmm_run(const glnn_spmm_desc& d, cudaStream_t st);                                   // spmm.cu
+int quantize_q24(const float* X, int64_t ldx, int64_t rows, int d, uint8_t* Q, int64_t ldq,
+                 cudaStream_t st);                                                    // spmm.cu
 int split_planes(const float* X, int64_t ldx, int64_t rows, int cols, uint16_t* hi, uint16_t* lo,
                  int64_t ldp, cudaStream_t st);                                      // planes.cu
 
@@ -57,7 +55,8 @@ struct Act {
   const uint16_t* hi = nullptr;
   const uint16_t* lo = nullptr;
   int64_t ldp = 0;
-  const uint8_t* q24 = nullptr;  // 24-bit row-packed copy for a following gather (3 d bytes per row)
+  const uint8_t* q24 = nullptr;  // 24-bit row-packed matrix for a following gather
+  int64_t ldq = 0;               // bytes between q24 rows
   int d = 0;
 };
 
@@ -114,9 +113,10 @@ static int weight_planes(const glnn_gnn_layer& ly, bool out_in, int n_rows, floa
 }
 
 int gemm_planes_q24(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda, const uint16_t* B_hi,
-                    const uint16_t* B_lo, int64_t ldb, int transB, uint8_t* Cq, int64_t M, int64_t N,
-                    int64_t K, const float* row_scale, const float* bias, const float* col_scale,
-                    const float* col_shift, int relu, cudaStream_t st);  // planes.cu
+                    const uint16_t* B_lo, int64_t ldb, int transB, uint8_t* Cq, int64_t ldq, int64_t M,
+                    int64_t N, int64_t K, const float* row_scale, const float* bias,
+                    const float* col_scale, const float* col_shift, int relu,
+                    cudaStream_t st);  // planes.cu
 
 static int gemm_planes_call(const Act& a, const PlaneBuf& w, int transB, float* C, int64_t ldc,
                             uint16_t* Ch, uint16_t* Cl, int64_t ldcp, int64_t M, int64_t N, int64_t K,
@@ -176,6 +176,24 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
     return gcn ? (ly.d_in > ly.d_out) : (pad4(ly.d_out) < ly.d_in);
   };
 
+  // Gathers are DRAM-bound on bytes per neighbour row, so every matrix that is read by a gather is
+  // kept as 24-bit row-packed values (2^-17 relative, 3 instead of 4 bytes per element, rows padded
+  // to whole 32-byte sectors): the caller's features are quantised once, projections write q24
+  // directly.  GLNN_NO_Q24=1 keeps fp32 gathers.
+  static const bool use_q24 = getenv("GLNN_NO_Q24") == nullptr;
+  // L2 residency budget for hub rows (see spmm.cu); experiment knob until graph tagging lands
+  static const double hot_mb = getenv("GLNN_L2_HOT_MB") ? atof(getenv("GLNN_L2_HOT_MB")) : 0.0;
+  auto hot_rows = [&](int64_t row_bytes) {
+    return static_cast<int>(std::min<double>(static_cast<double>(n), hot_mb * 1.0e6 / row_bytes));
+  };
+  auto base_desc = [&]() {
+    glnn_spmm_desc q{};
+    q.indptr = indptr; q.indptr64 = indptr64; q.indices = indices;
+    q.n_dst = n; q.n_src = n;
+    q.self_add = gcn ? 0 : 1; q.mean_plus_one = gcn ? 0 : 1;
+    return q;
+  };
+
   Act h;
   h.f32 = X; h.ld = ldx; h.d = layers[0].d_in;
   int hb = -1;  // workspace buffer holding h (-1 = caller memory)
@@ -186,9 +204,8 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
     const int dpad = pad4(ly.d_out);
     const int relu = last ? 0 : (gcn ? 2 : 1);
     const bool out_planes = !last && project_first(l + 1);
-    // a hidden output that only feeds the NEXT layer's gather is stored as 24-bit row-packed values
-    // (2^-17 relative, 3 instead of 4 bytes per gathered element -- the gather is DRAM-bound)
-    const bool out_q24 = !last && !out_planes && !project_first(l) && ly.d_out % 16 == 0 &&
+    // a hidden output that only feeds the NEXT layer's gather is written as q24 by the projection
+    const bool out_q24 = use_q24 && !last && !out_planes && !project_first(l) && ly.d_out % 8 == 0 &&
                          ly.d_out <= 512;
     int ib = 0;
     while (ib == hb) ++ib;
@@ -208,41 +225,69 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
         // the projection has consumed them (stream order)
       }
       if ((rc = weight_planes(ly, !gcn, gcn ? 0 : dpad, scratch, &w, st))) return rc;
-      Epi none{nullptr, nullptr, nullptr};
-      rc = gemm_planes_call(h, w, gcn ? 0 : 1, buf[ib], dpad, nullptr, nullptr, 0, n, dpad, ly.d_in,
-                            gcn ? src_norm : nullptr, none, 0, st);
+      // Z = H W: written as q24 when the width allows, else fp32
+      const bool z_q24 = use_q24 && dpad % 8 == 0 && dpad <= 512;
+      const int64_t zq_ld = glnn_q24_row_bytes(dpad);
+      if (z_q24) {
+        rc = gemm_planes_q24(h.hi, h.lo, h.ldp, w.hi, w.lo, w.ldp, gcn ? 0 : 1,
+                             reinterpret_cast<uint8_t*>(buf[ib]), zq_ld, n, dpad, ly.d_in,
+                             gcn ? src_norm : nullptr, nullptr, nullptr, nullptr, 0, st);
+      } else {
+        Epi none{nullptr, nullptr, nullptr};
+        rc = gemm_planes_call(h, w, gcn ? 0 : 1, buf[ib], dpad, nullptr, nullptr, 0, n, dpad, ly.d_in,
+                              gcn ? src_norm : nullptr, none, 0, st);
+      }
       if (rc != 0) return rc;
       PlaneBuf yp = planes_in(buf[ob], n, dpad);
-      rc = spmm_run(indptr, indptr64, indices, buf[ib], dpad, nullptr, out_planes ? nullptr : buf[ob], dpad,
-                    out_planes ? yp.hi : nullptr, out_planes ? yp.lo : nullptr, yp.ldp, n, n, dpad,
-                    gcn ? 0 : 1, gcn ? 0 : 1, nullptr, gcn ? dst_norm : nullptr, epi.bias, epi.scale,
-                    epi.shift, relu, st);
-      if (rc != 0) return rc;
-      if (out_planes) { y.hi = yp.hi; y.lo = yp.lo; y.ldp = yp.ldp; }
-      else { y.f32 = buf[ob]; y.ld = dpad; }
-    } else {
-      // aggregate (fp32 gather) straight into planes
-      const float* hin = h.f32;
-      GLNN_REQUIRE(hin != nullptr || h.q24 != nullptr, GLNN_ERR_ARG,
-                   "gnn_forward: internal: gather input must be fp32 or q24");
-      PlaneBuf tp = planes_in(buf[ib], n, ly.d_in);
-      rc = spmm_run(indptr, indptr64, indices, hin, h.ld, h.q24, nullptr, 0, tp.hi, tp.lo, tp.ldp, n, n,
-                    ly.d_in, gcn ? 0 : 1, gcn ? 0 : 1, gcn ? src_norm : nullptr, nullptr, nullptr,
-                    nullptr, nullptr, 0, st);
-      if (rc != 0) return rc;
-      if (pad8(ly.d_in) != ly.d_in) {
-        // pad columns of the planes are never read (the GEMM zero-fills past K)
+      glnn_spmm_desc q = base_desc();
+      q.d = dpad;
+      if (z_q24) { q.X_q24 = reinterpret_cast<const uint8_t*>(buf[ib]); q.ldq = zq_ld; }
+      else { q.X = buf[ib]; q.ldx = dpad; }
+      q.hot_below = hot_rows(z_q24 ? zq_ld : 4 * dpad);
+      q.dst_scale = gcn ? dst_norm : nullptr;
+      q.bias = epi.bias; q.col_scale = epi.scale; q.col_shift = epi.shift; q.relu = relu;
+      const bool fuse_lsm = last && log_softmax && dpad <= 512;
+      if (fuse_lsm) {  // evaluate()'s log_softmax in the gather epilogue, straight into `out`
+        q.Y = out; q.ldy = ldo; q.log_softmax = ly.d_out;
+      } else if (out_planes) {
+        q.Y_hi = yp.hi; q.Y_lo = yp.lo; q.ldyp = yp.ldp;
+      } else {
+        q.Y = buf[ob]; q.ldy = pad8(dpad);
       }
+      if ((rc = spmm_run(q, st))) return rc;
+      if (fuse_lsm) return 0;
+      if (out_planes) { y.hi = yp.hi; y.lo = yp.lo; y.ldp = yp.ldp; }
+      else { y.f32 = buf[ob]; y.ld = pad8(dpad); }
+    } else {
+      // aggregate straight into planes
+      GLNN_REQUIRE(h.f32 != nullptr || h.q24 != nullptr, GLNN_ERR_ARG,
+                   "gnn_forward: internal: gather input must be fp32 or q24");
+      if (use_q24 && !h.q24 && ly.d_in <= 512) {  // caller features: quantise once (buf[ob] is free
+        uint8_t* xq = reinterpret_cast<uint8_t*>(buf[ob]);  // until the projection below writes it)
+        const int64_t ldq = glnn_q24_row_bytes(ly.d_in);
+        if ((rc = quantize_q24(h.f32, h.ld, n, ly.d_in, xq, ldq, st))) return rc;
+        h.q24 = xq; h.ldq = ldq;
+      }
+      PlaneBuf tp = planes_in(buf[ib], n, ly.d_in);
+      glnn_spmm_desc q = base_desc();
+      q.d = ly.d_in;
+      if (h.q24) { q.X_q24 = h.q24; q.ldq = h.ldq; }
+      else { q.X = h.f32; q.ldx = h.ld; }
+      q.hot_below = hot_rows(h.q24 ? h.ldq : 4 * h.ld);
+      q.src_scale = gcn ? src_norm : nullptr;
+      q.Y_hi = tp.hi; q.Y_lo = tp.lo; q.ldyp = tp.ldp;
+      if ((rc = spmm_run(q, st))) return rc;
       if ((rc = weight_planes(ly, !gcn, 0, scratch, &w, st))) return rc;
       Act t;
       t.hi = tp.hi; t.lo = tp.lo; t.ldp = tp.ldp; t.d = ly.d_in;
       PlaneBuf yp = planes_in(buf[ob], n, ly.d_out);
       if (out_q24) {
-        uint8_t* q = reinterpret_cast<uint8_t*>(buf[ob]);
-        rc = gemm_planes_q24(t.hi, t.lo, t.ldp, w.hi, w.lo, w.ldp, gcn ? 0 : 1, q, n, ly.d_out, ly.d_in,
-                             gcn ? dst_norm : nullptr, epi.bias, epi.scale, epi.shift, relu, st);
+        uint8_t* yq = reinterpret_cast<uint8_t*>(buf[ob]);
+        const int64_t ldq = glnn_q24_row_bytes(ly.d_out);
+        rc = gemm_planes_q24(t.hi, t.lo, t.ldp, w.hi, w.lo, w.ldp, gcn ? 0 : 1, yq, ldq, n, ly.d_out,
+                             ly.d_in, gcn ? dst_norm : nullptr, epi.bias, epi.scale, epi.shift, relu, st);
         if (rc != 0) return rc;
-        y.q24 = q;
+        y.q24 = yq; y.ldq = ldq;
       } else {
         rc = gemm_planes_call(t, w, gcn ? 0 : 1, out_planes ? nullptr : buf[ob], dpad,
                               out_planes ? yp.hi : nullptr, out_planes ? yp.lo : nullptr, yp.ldp, n,

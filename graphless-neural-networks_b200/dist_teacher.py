@@ -169,7 +169,7 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
             if not h_full:
                 gather(h.data if is_q24 else h)
             # the output feeds another gather and nothing else -> exchange it as 24-bit rows
-            out_q24 = planes_ok and not last and not proj_first(l + 1) and d_out % 16 == 0 \
+            out_q24 = planes_ok and not last and not proj_first(l + 1) and d_out % 8 == 0 \
                 and d_out <= 512
             if planes_ok:
                 # gather straight into bf16 hi/lo planes, the tensor-core projection's operand format
@@ -189,8 +189,9 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
                 if out_q24:
                     cache = sg.__dict__.setdefault("_bufs", {})
                     yq = cache.get(("yq", l))
-                    if yq is None or yq.shape != (world * rm, 3 * d_out):
-                        yq = torch.zeros(world * rm, 3 * d_out, dtype=torch.uint8, device=feats_pad.device)
+                    ldq = k.Q24.row_bytes(d_out)
+                    if yq is None or yq.shape != (world * rm, ldq):
+                        yq = torch.zeros(world * rm, ldq, dtype=torch.uint8, device=feats_pad.device)
                         cache[("yq", l)] = yq
                     k.gemm_planes_q24(pl, wpl, out=k.Q24(yq[lo:hi], d_out), bias=b, col_scale=scale,
                                       col_shift=shift, relu=relu)

@@ -134,7 +134,9 @@ def gemm_planes(a, b, trans_a=False, trans_b=False, out=None, out_planes=False, 
     dev = a.hi.device
     c = ch = cl = None
     ldcp = 0
-    if out_planes:
+    if isinstance(out_planes, Planes):  # preallocated (pad columns must already be zero)
+        ch, cl, ldcp = out_planes.hi, out_planes.lo, out_planes.hi.stride(0)
+    elif out_planes:
         ldcp = (n + 7) // 8 * 8
         ch = torch.zeros(m, ldcp, dtype=torch.int16, device=dev)
         cl = torch.zeros(m, ldcp, dtype=torch.int16, device=dev)
@@ -145,6 +147,8 @@ def gemm_planes(a, b, trans_a=False, trans_b=False, out=None, out_planes=False, 
                                       0 if c is None else _ld(c), ptr(ch), ptr(cl), ldcp, m, n, k,
                                       ptr(row_scale), ptr(bias), ptr(col_scale), ptr(col_shift),
                                       int(relu), stream()), "glnn_gemm_bf16x3_planes")
+    if isinstance(out_planes, Planes):
+        return out_planes
     return Planes(ch, cl, n) if out_planes else c
 
 
@@ -170,51 +174,121 @@ def spmm_csr_planes(indptr, indices, x, d=None, self_add=False, mean_plus_one=Fa
 
 
 class Q24:
-    """24-bit row-packed matrix (see include/glnn_b200.h): .data uint8 [rows, 3 * cols]."""
+    """24-bit row-packed matrix (see include/glnn_b200.h): .data uint8 [rows, ldq]; a row holds dq
+    hi16 values then dq mid8 values (dq = cols rounded up to 8) and pad bytes up to ldq."""
 
     def __init__(self, data, cols):
         self.data, self.cols = data, cols
+
+    @staticmethod
+    def row_bytes(cols):
+        return (3 * ((cols + 7) // 8 * 8) + 31) // 32 * 32
+
+    @staticmethod
+    def empty(rows, cols, device, zero=False):
+        mk = torch.zeros if zero else torch.empty
+        return Q24(mk(rows, Q24.row_bytes(cols), dtype=torch.uint8, device=device), cols)
 
     @property
     def shape(self):
         return (self.data.shape[0], self.cols)
 
+    @property
+    def ldq(self):
+        return self.data.stride(0)
+
     def float(self):
-        n = self.cols
-        hi = self.data[:, :2 * n].contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
-        mid = self.data[:, 2 * n:].to(torch.int32)
-        return ((hi << 16) | (mid << 8)).view(torch.float32)
+        dq = (self.cols + 7) // 8 * 8
+        hi = self.data[:, :2 * dq].contiguous().view(torch.int16).to(torch.int32) & 0xFFFF
+        mid = self.data[:, 2 * dq:3 * dq].to(torch.int32)
+        return ((hi << 16) | (mid << 8)).view(torch.float32)[:, :self.cols]
+
+
+def quantize_q24(x, out=None):
+    """glnn_quantize_q24_f32: fp32 [rows, cols] -> Q24."""
+    lib = _lib.load()
+    require_cuda(x)
+    _f32(x)
+    rows, cols = x.shape
+    if out is None:
+        out = Q24.empty(rows, cols, x.device)
+    check(lib.glnn_quantize_q24_f32(ptr(x), _ld(x), rows, cols, ptr(out.data), out.ldq, stream()),
+          "glnn_quantize_q24_f32")
+    return out
 
 
 def gemm_planes_q24(a, b, trans_b=True, out=None, row_scale=None, bias=None, col_scale=None,
                     col_shift=None, relu=0):
-    """glnn_gemm_bf16x3_planes_q24: projection of Planes operands written as Q24."""
+    """glnn_gemm_bf16x3_planes_q24: projection of Planes operands written as Q24 (N % 8 == 0)."""
     lib = _lib.load()
     m, k = a.hi.shape[0], a.cols
     kb, n = (b.cols, b.hi.shape[0]) if trans_b else (b.hi.shape[0], b.cols)
     if k != kb:
         raise ValueError("gemm_planes_q24: inner dimensions differ")
     if out is None:
-        out = Q24(torch.empty(m, 3 * n, dtype=torch.uint8, device=a.hi.device), n)
+        out = Q24.empty(m, n, a.hi.device)
     check(lib.glnn_gemm_bf16x3_planes_q24(ptr(a.hi), ptr(a.lo), a.hi.stride(0), ptr(b.hi), ptr(b.lo),
-                                          b.hi.stride(0), int(trans_b), ptr(out.data), m, n, k,
+                                          b.hi.stride(0), int(trans_b), ptr(out.data), out.ldq, m, n, k,
                                           ptr(row_scale), ptr(bias), ptr(col_scale), ptr(col_shift),
                                           int(relu), stream()), "glnn_gemm_bf16x3_planes_q24")
     return out
 
 
-def spmm_csr_q24_planes(indptr, indices, xq, self_add=False, mean_plus_one=False, src_scale=None,
-                        dst_scale=None, out=None):
-    """glnn_spmm_csr_q24_planes: aggregation of a Q24 matrix into Planes."""
+def spmm(indptr, indices, x, d=None, out=None, out_planes=None, self_add=False, mean_plus_one=False,
+         src_scale=None, dst_scale=None, bias=None, col_scale=None, col_shift=None, relu=0,
+         log_softmax=0, hot_below=0):
+    """glnn_spmm_csr (general form).  x: fp32 tensor [n_src, >= d] or Q24; result in `out` (fp32
+    tensor) and/or `out_planes` (Planes); if neither is given an fp32 tensor is allocated.
+    log_softmax = c > 0 ends the epilogue with log_softmax over the first c columns (fp32 out
+    [n_dst, c]); hot_below = k marks source ids < k as L2-resident (a pure performance hint)."""
     lib = _lib.load()
-    n_dst, d = indptr.numel() - 1, xq.cols
+    require_cuda(indptr, indices, out, src_scale, dst_scale, bias, col_scale, col_shift)
+    _f32(out, src_scale, dst_scale, bias, col_scale, col_shift)
+    if indices.dtype != torch.int32:
+        raise ValueError("indices must be int32")
+    if indptr.dtype not in (torch.int32, torch.int64):
+        raise ValueError("indptr must be int32 or int64")
+    q = _lib.SpmmDesc()
+    q.indptr, q.indices, q.indptr64 = ptr(indptr), ptr(indices), int(indptr.dtype == torch.int64)
+    n_dst = indptr.numel() - 1
+    q.n_dst = n_dst
+    if isinstance(x, Q24):
+        require_cuda(x.data)
+        q.X_q24, q.ldq, q.n_src = ptr(x.data), x.ldq, x.data.shape[0]
+        d = x.cols if d is None else d
+        dev, dout = x.data.device, (d + 7) // 8 * 8
+    else:
+        require_cuda(x)
+        _f32(x)
+        q.X, q.ldx, q.n_src = ptr(x), _ld(x), x.shape[0]
+        d = x.shape[1] if d is None else d
+        dev, dout = x.device, d
+    q.d = d
+    if out is None and out_planes is None:
+        out = torch.empty(n_dst, log_softmax if log_softmax else dout, dtype=torch.float32, device=dev)
+    if out is not None:
+        q.Y, q.ldy = ptr(out), _ld(out)
+    if out_planes is not None:
+        q.Y_hi, q.Y_lo, q.ldyp = ptr(out_planes.hi), ptr(out_planes.lo), out_planes.hi.stride(0)
+    q.self_add, q.mean_plus_one = int(self_add), int(mean_plus_one)
+    q.src_scale, q.dst_scale, q.bias = ptr(src_scale), ptr(dst_scale), ptr(bias)
+    q.col_scale, q.col_shift, q.relu = ptr(col_scale), ptr(col_shift), int(relu)
+    q.log_softmax, q.hot_below = int(log_softmax), int(hot_below)
+    import ctypes
+    check(lib.glnn_spmm_csr(ctypes.byref(q), stream()), "glnn_spmm_csr")
+    return out if out is not None else out_planes
+
+
+def new_planes(rows, cols, device):
+    ldp = (cols + 7) // 8 * 8
+    return Planes(torch.zeros(rows, ldp, dtype=torch.int16, device=device),
+                  torch.zeros(rows, ldp, dtype=torch.int16, device=device), cols)
+
+
+def spmm_csr_q24_planes(indptr, indices, xq, self_add=False, mean_plus_one=False, src_scale=None,
+                        dst_scale=None, out=None, hot_below=0):
+    """Aggregation of a Q24 matrix into Planes (glnn_spmm_csr with X_q24 in, planes out)."""
     if out is None:
-        ldp = (d + 7) // 8 * 8
-        out = Planes(torch.zeros(n_dst, ldp, dtype=torch.int16, device=xq.data.device),
-                     torch.zeros(n_dst, ldp, dtype=torch.int16, device=xq.data.device), d)
-    check(lib.glnn_spmm_csr_q24_planes(ptr(indptr), int(indptr.dtype == torch.int64), ptr(indices),
-                                       ptr(xq.data), ptr(out.hi), ptr(out.lo), out.hi.stride(0), n_dst,
-                                       xq.data.shape[0], d, int(self_add), int(mean_plus_one),
-                                       ptr(src_scale), ptr(dst_scale), stream()),
-          "glnn_spmm_csr_q24_planes")
-    return out
+        out = new_planes(indptr.numel() - 1, xq.cols, xq.data.device)
+    return spmm(indptr, indices, xq, out_planes=out, self_add=self_add, mean_plus_one=mean_plus_one,
+                src_scale=src_scale, dst_scale=dst_scale, hot_below=hot_below)

@@ -119,22 +119,71 @@ GLNN_API int glnn_gemm_bf16x3_planes(const uint16_t* A_hi, const uint16_t* A_lo,
                             const float* bias, const float* col_scale, const float* col_shift,
                             int relu, glnn_stream_t stream);
 
-/* 24-bit row-packed embeddings ("q24"): a hidden-layer output that is only read by the NEXT layer's
- * neighbour gather is stored per row as N hi16 values followed by N mid8 values (the top 24 bits of
- * each fp32, rounded to nearest: 2^-17 relative), 3N bytes per row, N % 16 == 0, N <= 512.  The
- * gather is DRAM-bound on bytes per neighbour row, so this is 25 % less traffic on that kernel.
- * glnn_gemm_bf16x3_planes_q24 = glnn_gemm_bf16x3_planes (transA = 0) with the q24 output only;
- * glnn_spmm_csr_q24_planes = the aggregation reading q24 and writing bf16 hi/lo planes. */
+/* 24-bit row-packed matrices ("q24"): a matrix that is only read by a neighbour GATHER is stored per
+ * row as dq hi16 values followed by dq mid8 values (dq = d rounded up to 8; the top 24 bits of each
+ * fp32, rounded to nearest: 2^-17 relative; pad columns zero), rows ldq bytes apart with
+ * ldq >= 3 dq and ldq % 16 == 0 -- glnn_q24_row_bytes(d) rounds 3 dq up to whole 32-byte DRAM
+ * sectors.  The gather is DRAM-bound on bytes per neighbour row, so this is 25 % less traffic on
+ * the dominant kernel of the teacher forward.
+ * glnn_quantize_q24_f32 converts an fp32 matrix (the caller's features);
+ * glnn_gemm_bf16x3_planes_q24 = glnn_gemm_bf16x3_planes (transA = 0) with the q24 output only
+ * (N % 8 == 0); glnn_spmm_csr (below) reads q24 through desc->X_q24. */
+GLNN_API int64_t glnn_q24_row_bytes(int d);
+
+GLNN_API int glnn_quantize_q24_f32(const float* X, int64_t ldx, int64_t rows, int d, uint8_t* X_q24,
+                          int64_t ldq, glnn_stream_t stream);
+
 GLNN_API int glnn_gemm_bf16x3_planes_q24(const uint16_t* A_hi, const uint16_t* A_lo, int64_t lda,
                                 const uint16_t* B_hi, const uint16_t* B_lo, int64_t ldb, int transB,
-                                uint8_t* C_q24, int64_t M, int64_t N, int64_t K,
+                                uint8_t* C_q24, int64_t ldq, int64_t M, int64_t N, int64_t K,
                                 const float* row_scale, const float* bias, const float* col_scale,
                                 const float* col_shift, int relu, glnn_stream_t stream);
 
+/* Legacy form: q24 rows of exactly 3 d bytes (d % 16 == 0), planes output. */
 GLNN_API int glnn_spmm_csr_q24_planes(const void* indptr, int indptr64, const int32_t* indices,
                              const uint8_t* X_q24, uint16_t* Y_hi, uint16_t* Y_lo, int64_t ldyp,
                              int64_t n_dst, int64_t n_src, int d, int self_add, int mean_plus_one,
                              const float* src_scale, const float* dst_scale, glnn_stream_t stream);
+
+/* General form of the aggregation (same math as glnn_spmm_csr_f32): input fp32 (X, ldx) or q24
+ * (X_q24, ldq); output fp32 (Y, ldy) and/or bf16 planes (Y_hi, Y_lo, ldyp); with a q24 input the
+ * output rows are written in whole 8-column chunks (ldy / ldyp >= d rounded up to 8, pad = 0).
+ *   log_softmax = c > 0: the epilogue ends with log_softmax over the first c columns and writes only
+ *     those (Y fp32, any ldy >= c): evaluate()'s log_softmax (train_and_eval.py:98) fused into the
+ *     last layer's aggregation.  d <= 512.
+ *   hot_below = k > 0: L2 residency hint.  Gathered rows of source ids < k are loaded with the
+ *     evict_last policy, every other access of the kernel (cold rows, indices, output) evict_first,
+ *     so that the most-referenced rows of a degree-ordered graph stay in the 126 MB L2.  Purely a
+ *     performance hint: results do not depend on it.
+ */
+typedef struct glnn_spmm_desc {
+  const void* indptr;     /* int32 or int64 [n_dst + 1] */
+  const int32_t* indices; /* [nnz] */
+  int32_t indptr64;
+  int32_t d;
+  int64_t n_dst, n_src;
+  const float* X;
+  int64_t ldx;
+  const uint8_t* X_q24;
+  int64_t ldq;
+  float* Y;
+  int64_t ldy;
+  uint16_t* Y_hi;
+  uint16_t* Y_lo;
+  int64_t ldyp;
+  int32_t self_add, mean_plus_one;
+  const float* src_scale;
+  const float* dst_scale;
+  const float* bias;
+  const float* col_scale;
+  const float* col_shift;
+  int32_t relu;
+  int32_t log_softmax;
+  int32_t hot_below;
+  int32_t reserved;
+} glnn_spmm_desc;
+
+GLNN_API int glnn_spmm_csr(const glnn_spmm_desc* desc, glnn_stream_t stream);
 
 /* K5 (eval): folds BatchNorm1d running statistics into a per-column affine for the epilogues
  * above: scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (models.py:139-141). */

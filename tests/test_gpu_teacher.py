@@ -126,12 +126,86 @@ def test_q24_projection_then_gather(dev, d):
     h = (a.double() @ w.double().t() + bias.double()).clamp(min=0)
     q = ops.gemm_planes_q24(ops.split_planes(a.to(dev)), ops.split_planes(w.to(dev)), bias=bias.to(dev),
                             relu=1)
-    assert q.data.shape == (n, 3 * d)
+    assert q.data.shape == (n, ops.Q24.row_bytes(d)) and q.ldq % 32 == 0
     assert relerr(q.float().cpu(), h) < 3e-5                      # bf16x3 GEMM + 2^-17 rounding
     want = (O.spmm_sum(indptr, indices, h) + h) / (torch.from_numpy(np.diff(indptr)).double().unsqueeze(1) + 1)
     ip, ix = torch.from_numpy(indptr).int().to(dev), torch.from_numpy(indices).int().to(dev)
     got = ops.spmm_csr_q24_planes(ip, ix, q, self_add=True, mean_plus_one=True)
     assert relerr(got.float().cpu(), want) < 5e-5
+
+
+@pytest.mark.parametrize("d", [7, 48, 100, 104, 250])
+def test_q24_quantise_ragged_widths_then_gather(dev, d):
+    """q24 rows for widths that are not a multiple of 8/16 (ogbn-products features are 100 wide, the
+    projected logits 48): pad columns are zero, rows are whole 32-byte sectors, and the gather over
+    q24 equals the gather over the de-quantised matrix exactly (same fp32 adds)."""
+    from glnn_b200 import ops
+    n = 2500
+    indptr, indices = _rand_graph(n, n, 30000, seed=d, hubs=2, empty=3)
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(d)) * 3.0
+    q = ops.quantize_q24(x.to(dev))
+    assert q.ldq == ops.Q24.row_bytes(d) and q.ldq % 32 == 0 and q.ldq >= 3 * ((d + 7) // 8 * 8)
+    xq = q.float().cpu()
+    assert xq.shape == (n, d)
+    assert float(((xq - x).abs() / x.abs().clamp(min=1e-30)).max()) <= 2.0 ** -16   # 24-bit rounding
+    deg1 = torch.from_numpy(np.diff(indptr)).double().unsqueeze(1) + 1
+    want = (O.spmm_sum(indptr, indices, xq.double()) + xq.double()) / deg1
+    ip, ix = torch.from_numpy(indptr).int().to(dev), torch.from_numpy(indices).int().to(dev)
+    pl = ops.spmm(ip, ix, q, out_planes=ops.new_planes(n, d, dev), self_add=True, mean_plus_one=True)
+    assert relerr(pl.float().cpu(), want) < 2e-5          # planes keep 2^-18
+    dq = (d + 7) // 8 * 8
+    y = torch.full((n, dq), 7.0, device=dev)
+    ops.spmm(ip, ix, q, out=y, self_add=True, mean_plus_one=True)
+    assert relerr(y[:, :d].cpu(), want) < 1e-5
+    assert float(y[:, d:].abs().sum()) == 0               # pad columns are written as zeros
+    assert relerr(want, (O.spmm_sum(indptr, indices, x.double()) + x.double()) / deg1) < 2e-5
+
+
+@pytest.mark.parametrize("c,q24", [(47, True), (47, False), (7, True), (40, False), (10, False)])
+def test_spmm_fused_log_softmax_epilogue(dev, c, q24):
+    """Last-layer gather with bias + log_softmax fused (evaluate(), train_and_eval.py:98): the padded
+    class column must not enter the softmax and the output has exactly c columns."""
+    from glnn_b200 import ops
+    n = 3000
+    dpad = (c + 3) // 4 * 4
+    if q24 and dpad % 8:
+        dpad = (c + 7) // 8 * 8
+    indptr, indices = _rand_graph(n, n, 40000, seed=c, hubs=3, empty=4)
+    g = torch.Generator().manual_seed(c)
+    z = torch.randn(n, dpad, generator=g) * 2.0
+    z[:, c:] = 50.0  # garbage in the pad columns must be ignored by the softmax
+    bias = torch.zeros(dpad)
+    bias[:c] = torch.randn(c, generator=g)
+    ip, ix = torch.from_numpy(indptr).int().to(dev), torch.from_numpy(indices).int().to(dev)
+    src = ops.quantize_q24(z.to(dev)) if q24 else z.to(dev)
+    zz = (src.float().cpu() if q24 else z).double()
+    deg1 = torch.from_numpy(np.diff(indptr)).double().unsqueeze(1) + 1
+    logits = (O.spmm_sum(indptr, indices, zz) + zz) / deg1 + bias.double()
+    want = torch.log_softmax(logits[:, :c], dim=1)
+    out = torch.full((n, c), 9.0, device=dev)
+    ops.spmm(ip, ix, src, out=out, self_add=True, mean_plus_one=True, bias=bias.to(dev), log_softmax=c)
+    assert relerr(out.cpu(), want) < 1e-5
+    with pytest.raises(ValueError):
+        ops.spmm(ip, ix, src, out=out, log_softmax=dpad + 1)
+
+
+def test_spmm_l2_hints_do_not_change_results(dev):
+    """hot_below only selects L2 eviction policies; the sums are bit-identical."""
+    from glnn_b200 import ops
+    n, d = 4000, 256
+    indptr, indices = _rand_graph(n, n, 60000, seed=11, hubs=4, empty=2)
+    x = torch.randn(n, d, generator=torch.Generator().manual_seed(1)).to(dev)
+    ip, ix = torch.from_numpy(indptr).int().to(dev), torch.from_numpy(indices).int().to(dev)
+    q = ops.quantize_q24(x)
+    a = ops.spmm(ip, ix, q, self_add=True, mean_plus_one=True)
+    b = ops.spmm(ip, ix, q, self_add=True, mean_plus_one=True, hot_below=500)
+    # hub rows are combined with atomics (order-dependent rounding): compare the others exactly
+    small = torch.from_numpy(np.diff(indptr) <= 1024).to(dev)
+    assert torch.equal(a[small], b[small])
+    assert relerr(a, b) < 1e-6
+    c = ops.spmm(ip, ix, x, self_add=True, mean_plus_one=True, hot_below=n)
+    e = ops.spmm_csr(ip, ix, x, self_add=True, mean_plus_one=True)
+    assert torch.equal(c[small], e[small])
 
 
 def test_spmm_strided_views_and_bipartite(dev):
@@ -218,6 +292,38 @@ def test_gemm_planes_vs_fp64(dev, m, n, k, ta, tb):
     if not ta:                                        # plane output feeds a following GEMM
         gp = ops.gemm_planes(pa, pb, trans_a=ta, trans_b=tb, out_planes=True, relu=1)
         assert relerr(gp.float().cpu(), want.clamp(min=0)) < 3e-5
+
+
+@pytest.mark.parametrize("m,n,k", [(60001, 256, 256), (60000, 256, 100), (45003, 48, 256), (70000, 128, 72),
+                                   (19000, 40, 128), (33333, 200, 264)])
+def test_gemm_tall_persistent_vs_fp64(dev, m, n, k):
+    """Tall operands (>= one 128-row tile per SM, N <= 256) take the persistent TMA-fed kernel
+    (gemm_tall.cu): several tiles per CTA through the double-buffered TMEM accumulators, ragged last
+    tile, ragged K (zero-filled by TMA), N below the tile width; fp32, planes and q24 outputs with
+    the full epilogue."""
+    from glnn_b200 import ops
+    g = torch.Generator().manual_seed(m + n + k)
+    a = torch.randn(m, k, generator=g)
+    w = torch.randn(n, k, generator=g)
+    bias, scale, shift = (torch.randn(n, generator=g) for _ in range(3))
+    rs = torch.rand(m, generator=g) + 0.5
+    lin = (a.double() @ w.double().t()) * rs.double().unsqueeze(1) + bias.double()
+    want = (lin * scale.double() + shift.double()).clamp(min=0)
+    pa, pw = ops.split_planes(a.to(dev)), ops.split_planes(w.to(dev))
+    kw = dict(row_scale=rs.to(dev), bias=bias.to(dev), col_scale=scale.to(dev), col_shift=shift.to(dev),
+              relu=1)
+    got = ops.gemm_planes(pa, pw, trans_b=True, **kw)
+    assert relerr(got.cpu(), want) < 3e-5
+    plain = ops.gemm_planes(pa, pw, trans_b=True)
+    assert relerr(plain.cpu(), a.double() @ w.double().t()) < 3e-5
+    # row-exact spot check against the one-tile-per-CTA kernel's domain: every row block is right
+    blk = (got.cpu().double() - want).abs().view(-1)[: (m // 128) * 128 * n].view(m // 128, -1).amax(1)
+    assert float(blk.max() / want.abs().max()) < 3e-5
+    gp = ops.gemm_planes(pa, pw, trans_b=True, out_planes=True, **kw)
+    assert relerr(gp.float().cpu(), want) < 3e-5
+    if n % 8 == 0:
+        gq = ops.gemm_planes_q24(pa, pw, **kw)
+        assert relerr(gq.float().cpu(), want) < 4e-5
 
 
 def test_gemm_tcgen05_declines_unaligned_operands(dev):
