@@ -38,6 +38,10 @@ class SpmmDesc(C.Structure):
                 ("relu", c_i32), ("log_softmax", c_i32), ("hot_below", c_i32), ("reserved", c_i32)]
 
 
+class DpGroup(C.Structure):
+    _fields_ = [("world", c_i32), ("rank", c_i32), ("base", c_vp * 8), ("bytes", c_i64)]
+
+
 class SageLayerHost(C.Structure):
     _fields_ = [("weight", c_vp), ("bias", c_vp), ("bn_gamma", c_vp), ("bn_beta", c_vp),
                 ("bn_mean", c_vp), ("bn_var", c_vp), ("d_in", c_i32), ("d_out", c_i32)]
@@ -77,6 +81,13 @@ SIGNATURES = {
     "glnn_mlp_train_pass": (C.c_int, [C.POINTER(MlpDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
                                       C.POINTER(AdamHParams), c_vp, c_i64, c_vp, C.c_int, c_vp, c_i64,
                                       c_i64, c_vp, C.c_uint64, c_f32, c_vp, c_vp, c_i64, c_vp]),
+    "glnn_mlp_dp_control_bytes": (c_i64, [C.POINTER(MlpDesc), c_i64, C.c_int]),
+    "glnn_mlp_dp_flat_count": (c_i64, [C.POINTER(MlpDesc), C.c_int]),
+    "glnn_mlp_dp_init": (C.c_int, [c_vp, c_i64, c_vp]),
+    "glnn_mlp_train_pass_dp": (C.c_int, [C.POINTER(DpGroup), C.POINTER(MlpDesc), c_vp, c_vp, c_vp, c_vp,
+                                         c_vp, c_vp, c_i64, C.POINTER(AdamHParams), c_vp, c_i64, c_vp,
+                                         C.c_int, c_vp, c_i64, c_i64, c_vp, C.c_uint64, c_f32, c_vp,
+                                         c_vp, c_i64, c_vp]),
     "glnn_mlp_eval": (C.c_int, [C.POINTER(MlpDesc), c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_i64,
                                 C.c_int, c_i64, c_vp, c_i64, c_vp]),
     "glnn_gnn_forward_workspace_bytes": (c_i64, [c_i64, C.POINTER(GnnLayer), C.c_int]),

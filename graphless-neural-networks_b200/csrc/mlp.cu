@@ -11,6 +11,19 @@
 // changes from pass to pass (input matrix, targets, lamb, learning rate) lives in a small device
 // struct.  The sequence is therefore captured ONCE into a CUDA graph and replayed nb times per
 // pass with a single host read of the loss at the end of the pass (the reference syncs per step).
+//
+// Data parallel (glnn_mlp_train_pass_dp): the global batch of the reference is
+// split by rows over the GPUs of one box; every exchange of the step is FUSED into the kernel that
+// produces or consumes the data, over peer-mapped (NVLink) symmetric memory -- no NCCL call, no extra
+// copy, the whole step still one CUDA graph:
+//   * BatchNorm statistics: bn_stats / bn_bwd_stats write their per-split partials straight into
+//     every peer's buffer, the last CTA raises a flag on every peer; bn_apply / bn_bwd_apply wait for
+//     the flags and combine all partials in rank order (Chan), so every rank normalises with the
+//     statistics of the GLOBAL batch, exactly as the single-process reference does;
+//   * gradients + Adam: each rank owns 1/G of the flat parameter buffer; adam_dp_kernel sums that
+//     slice of the gradients over all peers (P2P loads, fixed order), applies Adam with its slice of
+//     the moments and stores the new parameters into every peer's buffer (P2P stores) --
+//     reduce-scatter, optimizer and all-gather in one kernel.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -45,8 +58,68 @@ struct PassParams {       // device-resident, rewritten once per pass
 struct Dims {
   int L, F, H, C, norm;
   float p_drop, bn_eps, bn_mom;
-  int64_t R;  // batch rows
+  int64_t R;   // batch rows processed by this GPU
+  int64_t Rg;  // rows of the (global) batch: R * world
+  int world, rank;
 };
+
+// Data-parallel exchange state, passed by value to the kernels that communicate.  Every rank owns a
+// symmetric region laid out identically; base[r] is rank r's region as mapped into this process.
+constexpr int kMaxPeers = 8;
+constexpr int kSlots = 40;  // 2 per hidden layer (<= 15) + gradients + parameters
+struct DpDev {
+  int world, rank;
+  unsigned char* base[kMaxPeers];
+  int64_t off_flags;   // uint32 [kSlots][kMaxPeers]: flag[slot][src] = last epoch signalled by src
+  int64_t off_done;    // uint32 [kSlots]: CTA completion counters (local use)
+  int64_t off_epoch;   // uint32: step epoch of this rank, starts at 1, never reset
+  int64_t off_part;    // float [2 (L-1)][world * rs][2][H]
+  int64_t off_params, off_grads;  // flat parameter / gradient buffers inside the region
+};
+__host__ __device__ __forceinline__ uint32_t* dp_flags(const DpDev& dp, int r) {
+  return reinterpret_cast<uint32_t*>(dp.base[r] + dp.off_flags);
+}
+
+// ---- cross-GPU signalling over peer-mapped memory ----
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Raise flag[slot][my rank] = epoch on every rank (called by ONE thread after a system fence).
+__device__ __forceinline__ void dp_signal_all(const DpDev& dp, int slot, uint32_t epoch) {
+  __threadfence_system();
+  for (int r = 0; r < dp.world; ++r) st_release_sys(dp_flags(dp, r) + slot * kMaxPeers + dp.rank, epoch);
+}
+// Block-wide wait until every rank has signalled `epoch` on `slot`.  A protocol bug must trap
+// instead of hanging the GPU: bounded by ~4 s of clock64.
+__device__ __forceinline__ void dp_wait_all(const DpDev& dp, int slot, uint32_t epoch) {
+  if (threadIdx.x < dp.world && threadIdx.y == 0 && threadIdx.z == 0) {
+    const uint32_t* f = dp_flags(dp, dp.rank) + slot * kMaxPeers + threadIdx.x;
+    const long long t0 = clock64();
+    while (static_cast<int32_t>(ld_acquire_sys(f) - epoch) < 0) {
+      if (clock64() - t0 > 8000000000LL) __trap();
+    }
+  }
+  __syncthreads();
+}
+// Called by every thread of a CTA after its peer stores: the LAST CTA of the grid signals `slot`.
+__device__ __forceinline__ void dp_last_cta_signals(const DpDev& dp, int slot, uint32_t epoch,
+                                                    unsigned total_ctas) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0 && threadIdx.z == 0) {
+    uint32_t* done = reinterpret_cast<uint32_t*>(dp.base[dp.rank] + dp.off_done) + slot;
+    const unsigned prev = atomicInc(done, total_ctas - 1);  // wraps to 0 for the next step
+    if (prev == total_ctas - 1) dp_signal_all(dp, slot, epoch);
+  }
+}
+__device__ __forceinline__ uint32_t dp_epoch(const DpDev& dp) {
+  return *reinterpret_cast<const uint32_t*>(dp.base[dp.rank] + dp.off_epoch);
+}
 
 __host__ __device__ __forceinline__ int64_t imax64(int64_t a, int64_t b) { return a > b ? a : b; }
 __host__ __device__ __forceinline__ int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
@@ -162,14 +235,15 @@ __device__ __forceinline__ float keep_scale(const PassParams* pp, int step, int 
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const PassParams* __restrict__ pp,
-                                                     const int* __restrict__ ctr, int64_t R, int F,
+                                                     const int* __restrict__ ctr, int64_t R,
+                                                     int64_t Rg, int64_t row0, int F,
                                                      int C, uint16_t* __restrict__ xb_hi,
                                                      uint16_t* __restrict__ xb_lo, int64_t ldxb,
                                                      float* __restrict__ tgt) {
   const int lane = threadIdx.x & 31;
   const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (r >= R) return;
-  const int64_t src = pp->perm[static_cast<int64_t>(*ctr) * R + r];
+  const int64_t src = pp->perm[static_cast<int64_t>(*ctr) * Rg + row0 + r];
   const float* x = pp->X + src * pp->ldx;
   for (int j = lane; j < F; j += 32) store_planes(xb_hi, xb_lo, r * ldxb + j, __ldg(x + j));
   if (pp->kind == 0) {
@@ -183,7 +257,8 @@ __global__ void __launch_bounds__(256) gather_kernel(const PassParams* __restric
 // Column statistics of Z[R,H] over a row split: chunk mean and chunk M2 (two passes over the chunk,
 // which sits in L1/L2), combined later with Chan's formula.  block (32, 8).
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ Z, int64_t R, int H,
-                                                       int rs, float* __restrict__ part) {
+                                                       int rs, float* __restrict__ part, const DpDev dp,
+                                                       int slot) {
   __shared__ float sm[8][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
@@ -212,9 +287,19 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
     float m2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) m2 += sm[i][tx];
-    part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c] = mu;
-    part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c] = m2;
+    if (dp.world > 1) {  // this split's partials go to every rank's exchange buffer
+      const int64_t o = ((static_cast<int64_t>(slot) * dp.world + dp.rank) * rs + blockIdx.y) * 2 * H + c;
+      for (int r = 0; r < dp.world; ++r) {
+        float* pr = reinterpret_cast<float*>(dp.base[r] + dp.off_part);
+        pr[o] = mu;
+        pr[o + H] = m2;
+      }
+    } else {
+      part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c] = mu;
+      part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c] = m2;
+    }
   }
+  if (dp.world > 1) dp_last_cta_signals(dp, slot, dp_epoch(dp), gridDim.x * gridDim.y);
 }
 
 // Combines the split statistics, normalises, applies gamma/beta, ReLU and dropout; the first row
@@ -227,16 +312,22 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(
     float* __restrict__ run_mean, float* __restrict__ run_var, float* __restrict__ save_mean,
     float* __restrict__ save_invstd, int norm, float eps, float mom, float p_drop,
     const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
-    int rows_per_block) {
+    int rows_per_block, const DpDev dp, int slot, int64_t Rg) {
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
+  if (dp.world > 1 && norm) {  // statistics of every rank's rows must have arrived
+    dp_wait_all(dp, slot, dp_epoch(dp));
+    part = reinterpret_cast<const float*>(dp.base[dp.rank] + dp.off_part) +
+           static_cast<int64_t>(slot) * dp.world * rs * 2 * H;
+  }
   if (c >= H) return;
   float mu = 0.f, inv = 1.f, g = 1.f, b = 0.f;
   if (norm) {
     const int64_t rows = (R + rs - 1) / rs;
     float n = 0.f, m2 = 0.f;
-    for (int s = 0; s < rs; ++s) {
-      const float nb = static_cast<float>(imax64(imin64(R, (s + 1) * rows) - s * rows, 0));
+    for (int s = 0; s < rs * dp.world; ++s) {  // rank-major: every rank combines in the same order
+      const int sl = s % rs;
+      const float nb = static_cast<float>(imax64(imin64(R, (sl + 1) * rows) - sl * rows, 0));
       if (nb <= 0.f) continue;
       const float mb = part[(static_cast<int64_t>(s) * 2 + 0) * H + c];
       const float qb = part[(static_cast<int64_t>(s) * 2 + 1) * H + c];
@@ -245,14 +336,14 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(
       m2 += qb + delta * delta * (n * nb / tot);
       n = tot;
     }
-    const float var = m2 / static_cast<float>(R);
+    const float var = m2 / static_cast<float>(Rg);
     inv = 1.f / sqrtf(var + eps);
     g = gamma[c];
     b = beta[c];
     if (blockIdx.y == 0 && ty == 0) {
       save_mean[c] = mu;
       save_invstd[c] = inv;
-      const float unb = m2 / static_cast<float>(imax64(R - 1, 1));
+      const float unb = m2 / static_cast<float>(imax64(Rg - 1, 1));
       run_mean[c] = (1.f - mom) * run_mean[c] + mom * mu;
       run_var[c] = (1.f - mom) * run_var[c] + mom * unb;
     }
@@ -264,7 +355,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(
     const float z = Z[r * H + c];
     float y = norm ? (z - mu) * inv * g + b : z;
     y = fmaxf(y, 0.f);
-    store_planes(A_hi, A_lo, r * lda + c, y * keep_scale(pp, step, layer, nlay, R, H, r, c, p_drop));
+    store_planes(A_hi, A_lo, r * lda + c,
+                 y * keep_scale(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop));
   }
 }
 
@@ -275,7 +367,7 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
     const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, int norm, float p_drop,
     const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
-    float* __restrict__ part) {
+    float* __restrict__ part, const DpDev dp, int slot, int64_t Rg) {
   __shared__ float s1[8][33], s2[8][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
@@ -289,7 +381,7 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
     for (int64_t r = r0 + ty; r < r1; r += 8) {
       const float xh = (Z[r * H + c] - mu) * inv;
       const float y = norm ? xh * g + b : Z[r * H + c];
-      float gr = dA[r * H + c] * keep_scale(pp, step, layer, nlay, R, H, r, c, p_drop);
+      float gr = dA[r * H + c] * keep_scale(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
       gr = y > 0.f ? gr : 0.f;
       a1 += gr;
       a2 = fmaf(gr, xh, a2);
@@ -302,9 +394,19 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
     float t1 = 0.f, t2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { t1 += s1[i][tx]; t2 += s2[i][tx]; }
-    part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c] = t1;
-    part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c] = t2;
+    if (dp.world > 1) {
+      const int64_t o = ((static_cast<int64_t>(slot) * dp.world + dp.rank) * rs + blockIdx.y) * 2 * H + c;
+      for (int r = 0; r < dp.world; ++r) {
+        float* pr = reinterpret_cast<float*>(dp.base[r] + dp.off_part);
+        pr[o] = t1;
+        pr[o + H] = t2;
+      }
+    } else {
+      part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c] = t1;
+      part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c] = t2;
+    }
   }
+  if (dp.world > 1) dp_last_cta_signals(dp, slot, dp_epoch(dp), gridDim.x * gridDim.y);
 }
 
 // Pass 2: dZ = gamma*invstd/R * (R*g - S1 - xhat*S2) written as bf16 planes (it only feeds the dW and
@@ -318,22 +420,32 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, int norm, float p_drop,
     const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
-    int rows_per_block) {
+    int rows_per_block, const DpDev dp, int slot, int64_t Rg) {
   __shared__ float sb[8][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * 32 + tx;
+  if (dp.world > 1 && norm) {
+    dp_wait_all(dp, slot, dp_epoch(dp));
+    part = reinterpret_cast<const float*>(dp.base[dp.rank] + dp.off_part) +
+           static_cast<int64_t>(slot) * dp.world * rs * 2 * H;
+  }
   float colsum = 0.f;
   if (c < H) {
     float S1 = 0.f, S2 = 0.f, mu = 0.f, inv = 1.f, g = 1.f, b = 0.f;
     if (norm) {
-      for (int s = 0; s < rs; ++s) {
+      for (int s = 0; s < rs * dp.world; ++s) {
         S1 += part[(static_cast<int64_t>(s) * 2 + 0) * H + c];
         S2 += part[(static_cast<int64_t>(s) * 2 + 1) * H + c];
       }
       mu = save_mean[c]; inv = save_invstd[c]; g = gamma[c]; b = beta[c];
-      if (blockIdx.y == 0 && ty == 0) { dgamma[c] = S2; dbeta[c] = S1; }
+      // S1 / S2 are already sums over the GLOBAL batch: only rank 0 contributes them to the
+      // gradient reduction
+      if (blockIdx.y == 0 && ty == 0) {
+        dgamma[c] = dp.rank == 0 ? S2 : 0.f;
+        dbeta[c] = dp.rank == 0 ? S1 : 0.f;
+      }
     }
-    const float fR = static_cast<float>(R);
+    const float fR = static_cast<float>(Rg);
     const float k = g * inv / fR;
     const int step = *ctr;
     const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
@@ -342,7 +454,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
       const float z = Z[r * H + c];
       const float xh = (z - mu) * inv;
       const float y = norm ? xh * g + b : z;
-      float gr = dA[r * H + c] * keep_scale(pp, step, layer, nlay, R, H, r, c, p_drop);
+      float gr = dA[r * H + c] * keep_scale(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
       gr = y > 0.f ? gr : 0.f;
       const float dz = norm ? k * (fR * gr - S1 - xh * S2) : gr;
       store_planes(dZ_hi, dZ_lo, r * lddz + c, dz);
@@ -362,7 +474,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
 // log-softmax + loss + gradient of lamb*loss w.r.t. the logits; one warp per row.  Also accumulates
 // the last layer's bias gradient (column sums of dlogits).
 __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ logits,
-                                                   const float* __restrict__ tgt, int64_t R, int C,
+                                                   const float* __restrict__ tgt, int64_t R,
+                                                   int64_t Rg, int C,
                                                    const PassParams* __restrict__ pp,
                                                    uint16_t* __restrict__ dl_hi,
                                                    uint16_t* __restrict__ dl_lo, int64_t lddl,
@@ -385,7 +498,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
     const float lse = m + logf(se);
-    const float sc = pp->lamb / static_cast<float>(R);
+    const float sc = pp->lamb / static_cast<float>(Rg);
     if (pp->kind == 0) {
       const int y = static_cast<int>(reinterpret_cast<const int64_t*>(tgt)[r]);
       for (int j = lane; j < C; j += 32) {
@@ -418,7 +531,7 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int w = 0; w < 8; ++w) t += s_loss[w];
-    atomicAdd(pp->loss_sum, t / static_cast<float>(R));
+    atomicAdd(pp->loss_sum, t / static_cast<float>(Rg));
   }
 }
 
@@ -452,8 +565,77 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
-__global__ void advance_kernel(int* ctr, int64_t* nbt, int n_norm) {
-  if (threadIdx.x == 0) *ctr += 1;
+// Data-parallel optimizer step: reduce-scatter of the gradients, Adam and all-gather of the new
+// parameters in ONE kernel over peer memory.  This rank owns elements [lo, hi) of the flat buffers:
+// it waits until every rank has published its gradients, sums that slice over the ranks in rank
+// order (P2P loads, 16 bytes per lane), applies torch.optim.Adam with its slice of the moments and
+// stores the new parameters into every rank's parameter buffer (P2P stores).  The last CTA then
+// signals "parameters updated".  Moments outside [lo, hi) are not touched (the host gathers them
+// once per pass).
+__global__ void __launch_bounds__(256) adam_dp_kernel(const DpDev dp, float* __restrict__ m,
+                                                      float* __restrict__ v, int64_t lo, int64_t hi,
+                                                      const PassParams* __restrict__ pp,
+                                                      const int* __restrict__ ctr, int slot_grads,
+                                                      int slot_params) {
+  __shared__ float s_step, s_bc2;
+  const uint32_t epoch = dp_epoch(dp);
+  if (threadIdx.x == 0) {
+    const double t = static_cast<double>(pp->step0 + *ctr + 1);
+    const double bc1 = 1.0 - pow(static_cast<double>(pp->beta1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(pp->beta2), t);
+    s_step = static_cast<float>(static_cast<double>(pp->lr) / bc1);
+    s_bc2 = static_cast<float>(sqrt(bc2));
+  }
+  dp_wait_all(dp, slot_grads, epoch);  // includes __syncthreads
+  const float b1 = pp->beta1, b2 = pp->beta2, eps = pp->eps, wd = pp->wd;
+  const float step_size = s_step, bc2s = s_bc2;
+  float* p_loc = reinterpret_cast<float*>(dp.base[dp.rank] + dp.off_params);
+  // lo, hi are multiples of 4 and the buffers 16-byte aligned
+  for (int64_t i = lo + 4 * (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x); i < hi;
+       i += 4LL * gridDim.x * blockDim.x) {
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < dp.world; ++r) {
+      const float4* gp = reinterpret_cast<const float4*>(dp.base[r] + dp.off_grads) + (i >> 2);
+      float4 t;
+      asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                   : "l"(gp));
+      g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    const float4 p4 = *reinterpret_cast<const float4*>(p_loc + i);
+    float4 m4 = *reinterpret_cast<const float4*>(m + i), v4 = *reinterpret_cast<const float4*>(v + i);
+    float gi[4] = {g.x, g.y, g.z, g.w}, pi[4] = {p4.x, p4.y, p4.z, p4.w};
+    float mi[4] = {m4.x, m4.y, m4.z, m4.w}, vi[4] = {v4.x, v4.y, v4.z, v4.w}, po[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (wd != 0.f) gi[j] = fmaf(wd, pi[j], gi[j]);
+      mi[j] = mi[j] * b1 + gi[j] * (1.f - b1);
+      vi[j] = vi[j] * b2 + gi[j] * gi[j] * (1.f - b2);
+      const float denom = sqrtf(vi[j]) / bc2s + eps;
+      po[j] = pi[j] - step_size * (mi[j] / denom);
+    }
+    *reinterpret_cast<float4*>(m + i) = make_float4(mi[0], mi[1], mi[2], mi[3]);
+    *reinterpret_cast<float4*>(v + i) = make_float4(vi[0], vi[1], vi[2], vi[3]);
+    const float4 out = make_float4(po[0], po[1], po[2], po[3]);
+    for (int r = 0; r < dp.world; ++r)
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(dp.base[r] + dp.off_params) + i) = out;
+  }
+  dp_last_cta_signals(dp, slot_params, epoch, gridDim.x);
+}
+
+// "My gradients are complete": one thread, after every backward kernel of the step in stream order.
+__global__ void dp_signal_kernel(const DpDev dp, int slot) {
+  if (threadIdx.x == 0) dp_signal_all(dp, slot, dp_epoch(dp));
+}
+// Start of a step: the parameters written by every rank's optimizer kernel of the PREVIOUS step have
+// landed in this rank's buffer (epoch - 1; trivially true for the first step after allocation).
+__global__ void dp_wait_kernel(const DpDev dp, int slot) { dp_wait_all(dp, slot, dp_epoch(dp) - 1); }
+
+__global__ void advance_kernel(int* ctr, int64_t* nbt, int n_norm, uint32_t* epoch) {
+  if (threadIdx.x == 0) {
+    *ctr += 1;
+    if (epoch) *epoch += 1;
+  }
   if (nbt && threadIdx.x < n_norm) nbt[threadIdx.x] += 1;
 }
 
@@ -470,6 +652,10 @@ static int gemm_p(const PlaneRef& A, int tA, const PlaneRef& B, int tB, float* C
                                  nullptr, bias, col_scale, col_shift, relu, st);
 }
 
+// Data-parallel ownership of the flat buffers: equal slices of a multiple of 4 elements; the flat
+// buffers are padded to P4(P) = slice * world elements by the host.
+static inline int64_t dp_slice(int64_t P, int world) { return (P + 4LL * world - 1) / (4LL * world) * 4; }
+
 struct StepCtx {
   Dims d;
   ParamLayout pl;
@@ -477,7 +663,9 @@ struct StepCtx {
   float *params, *grads, *m, *v, *bn_stats;
   int64_t* nbt;
   float* ws;
+  DpDev dp;  // dp.world == 1: single GPU
 };
+constexpr int kSlotGrads = kSlots - 2, kSlotParams = kSlots - 1;
 
 static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   const Dims& d = c.d;
@@ -497,6 +685,12 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   const PlaneRef xb = plane_ref(c.ws, c.wl.xbP, R, d.F);
   const PlaneRef dlog = plane_ref(c.ws, c.wl.dlogP, R, d.C);
   const PlaneRef dzp = plane_ref(c.ws, c.wl.dzP, R, d.H);
+  const DpDev& dp = c.dp;
+  const bool is_dp = dp.world > 1;
+  if (is_dp) {  // every rank's optimizer kernel of the previous step has written our parameters
+    dp_wait_kernel<<<1, 32, 0, st>>>(dp, kSlotParams);
+    GLNN_LAUNCH_OK("dp_wait_kernel");
+  }
   PlaneRef wp[16], ap[16];
   for (int l = 0; l < d.L; ++l) {
     wp[l] = plane_ref(c.ws, c.wl.wP[l], out_dim(d, l), in_dim(d, l));
@@ -508,8 +702,8 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
     if (rc != 0) return rc;
   }
 
-  gather_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, st>>>(pp, ctr, R, d.F, d.C, xb.hi, xb.lo,
-                                                                    xb.ld, tgt);
+  gather_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, st>>>(pp, ctr, R, d.Rg, d.rank * R, d.F,
+                                                                    d.C, xb.hi, xb.lo, xb.ld, tgt);
   GLNN_LAUNCH_OK("gather_kernel");
 
   // forward
@@ -522,7 +716,7 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
     if (rc != 0) return rc;
     if (l == d.L - 1) break;
     if (d.norm) {
-      bn_stats_kernel<<<dim3(col_tiles, rs), blk, 0, st>>>(z, R, d.H, rs, part);
+      bn_stats_kernel<<<dim3(col_tiles, rs), blk, 0, st>>>(z, R, d.H, rs, part, dp, l);
       GLNN_LAUNCH_OK("bn_stats_kernel");
     }
     bn_apply_kernel<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
@@ -531,7 +725,7 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
         d.norm ? c.bn_stats + 2LL * l * d.H : nullptr,
         d.norm ? c.bn_stats + (2LL * l + 1) * d.H : nullptr, c.ws + c.wl.mean[l],
         c.ws + c.wl.invstd[l], d.norm, d.bn_eps, d.bn_mom, d.p_drop, pp, ctr, l, nlay,
-        rows_per_block);
+        rows_per_block, dp, l, d.Rg);
     GLNN_LAUNCH_OK("bn_apply_kernel");
     h = &ap[l];
   }
@@ -539,7 +733,7 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   // loss + dlogits (+ last bias grad)
   GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[d.L - 1], 0, sizeof(float) * d.C, st));
   loss_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, sizeof(float) * (d.C + 8), st>>>(
-      c.ws + c.wl.logits, tgt, R, d.C, pp, dlog.hi, dlog.lo, dlog.ld, c.grads + c.pl.b[d.L - 1]);
+      c.ws + c.wl.logits, tgt, R, d.Rg, d.C, pp, dlog.hi, dlog.lo, dlog.ld, c.grads + c.pl.b[d.L - 1]);
   GLNN_LAUNCH_OK("loss_kernel");
 
   // backward
@@ -562,7 +756,7 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
     if (d.norm) {
       bn_bwd_stats_kernel<<<dim3(col_tiles, rs), blk, 0, st>>>(
           da, c.ws + c.wl.z[k], R, d.H, rs, gam, bet, c.ws + c.wl.mean[k], c.ws + c.wl.invstd[k],
-          d.norm, d.p_drop, pp, ctr, k, nlay, part);
+          d.norm, d.p_drop, pp, ctr, k, nlay, part, dp, nlay + k, d.Rg);
       GLNN_LAUNCH_OK("bn_bwd_stats_kernel");
     }
     GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[k], 0, sizeof(float) * d.H, st));
@@ -570,16 +764,29 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
         da, dzp.hi, dzp.lo, dzp.ld, c.ws + c.wl.z[k], R, d.H, rs, part, gam, bet, c.ws + c.wl.mean[k],
         c.ws + c.wl.invstd[k], d.norm, d.p_drop, pp, ctr, k, nlay,
         d.norm ? c.grads + c.pl.gamma[k] : nullptr, d.norm ? c.grads + c.pl.beta[k] : nullptr,
-        c.grads + c.pl.b[k], rows_per_block);
+        c.grads + c.pl.b[k], rows_per_block, dp, nlay + k, d.Rg);
     GLNN_LAUNCH_OK("bn_bwd_apply_kernel");
     dz = &dzp;
   }
 
   const int64_t P = c.pl.total;
-  const unsigned ablocks = static_cast<unsigned>(std::min<int64_t>((P + 255) / 256, 8LL * sm_count()));
-  adam_kernel<<<ablocks, 256, 0, st>>>(c.params, c.grads, c.m, c.v, P, pp, ctr);
-  GLNN_LAUNCH_OK("adam_kernel");
-  advance_kernel<<<1, 32, 0, st>>>(ctr, d.norm ? c.nbt : nullptr, d.norm ? d.L - 1 : 0);
+  if (is_dp) {
+    dp_signal_kernel<<<1, 32, 0, st>>>(dp, kSlotGrads);
+    GLNN_LAUNCH_OK("dp_signal_kernel");
+    const int64_t slice = dp_slice(P, dp.world);
+    const int64_t lo = slice * dp.rank, hi = lo + slice;  // buffers hold slice * world elements
+    const int64_t n4 = std::max<int64_t>((hi - lo) / 4, 1);
+    const unsigned ablocks = static_cast<unsigned>(std::min<int64_t>((n4 + 255) / 256, 2LL * sm_count()));
+    adam_dp_kernel<<<ablocks, 256, 0, st>>>(dp, c.m, c.v, lo, hi, pp, ctr, kSlotGrads, kSlotParams);
+    GLNN_LAUNCH_OK("adam_dp_kernel");
+  } else {
+    const unsigned ablocks = static_cast<unsigned>(std::min<int64_t>((P + 255) / 256, 8LL * sm_count()));
+    adam_kernel<<<ablocks, 256, 0, st>>>(c.params, c.grads, c.m, c.v, P, pp, ctr);
+    GLNN_LAUNCH_OK("adam_kernel");
+  }
+  advance_kernel<<<1, 32, 0, st>>>(ctr, d.norm ? c.nbt : nullptr, d.norm ? d.L - 1 : 0,
+                                   is_dp ? reinterpret_cast<uint32_t*>(dp.base[dp.rank] + dp.off_epoch)
+                                         : nullptr);
   GLNN_LAUNCH_OK("advance_kernel");
   return 0;
 }
@@ -588,6 +795,7 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
 struct GraphKey {
   Dims d;
   const void *params, *grads, *m, *v, *bn, *nbt, *ws;
+  DpDev dp;
   bool operator<(const GraphKey& o) const {
     return memcmp(this, &o, sizeof(GraphKey)) < 0;
   }
@@ -600,7 +808,7 @@ static int get_graph(const StepCtx& c, cudaGraphExec_t* out) {
   GraphKey k;
   memset(&k, 0, sizeof(k));
   k.d = c.d; k.params = c.params; k.grads = c.grads; k.m = c.m; k.v = c.v; k.bn = c.bn_stats;
-  k.nbt = c.nbt; k.ws = c.ws;
+  k.nbt = c.nbt; k.ws = c.ws; k.dp = c.dp;
   std::lock_guard<std::mutex> lock(g_mu);
   auto it = g_graphs.find(k);
   if (it != g_graphs.end()) { *out = it->second; return 0; }
@@ -636,6 +844,7 @@ static int make_dims(const glnn_mlp_desc* desc, int64_t rows, Dims* d) {
   d->L = desc->num_layers; d->F = desc->feat_dim; d->H = desc->num_layers == 1 ? 1 : desc->hidden_dim;
   d->C = desc->label_dim; d->norm = desc->num_layers == 1 ? 0 : desc->norm;
   d->p_drop = desc->dropout; d->bn_eps = desc->bn_eps; d->bn_mom = desc->bn_momentum; d->R = rows;
+  d->Rg = rows; d->world = 1; d->rank = 0;
   return 0;
 }
 
@@ -659,23 +868,41 @@ extern "C" int64_t glnn_mlp_workspace_bytes(const glnn_mlp_desc* desc, int64_t r
   return glnn::ws_layout(d, true).total_bytes;
 }
 
-extern "C" int glnn_mlp_train_pass(const glnn_mlp_desc* desc, float* params, float* grads,
-                                   float* exp_avg, float* exp_avg_sq, float* bn_stats,
-                                   int64_t* num_batches_tracked, int64_t adam_step0,
-                                   const glnn_adam_hparams* hp, const float* X, int64_t ldx,
-                                   const void* target, int target_kind, const int64_t* perm,
-                                   int64_t nb, int64_t bs, const uint8_t* drop_masks, uint64_t seed,
-                                   float lamb, float* loss_sum, void* workspace,
-                                   int64_t workspace_bytes, glnn_stream_t stream) {
-  using namespace glnn;
+namespace glnn {
+
+// Control area at the start of every rank's symmetric region (see DpDev).
+constexpr int64_t kDpOffFlags = 0, kDpOffDone = 1280, kDpOffEpoch = 1536, kDpOffPart = 2048;
+static int64_t dp_control_bytes(const Dims& d_local, int world) {
+  const int rs = row_splits(d_local);
+  const int64_t part = 2LL * std::max(1, d_local.L - 1) * world * rs * 2 * d_local.H * sizeof(float);
+  return (kDpOffPart + part + 255) / 256 * 256;
+}
+
+// bs = rows of the GLOBAL batch; grp == nullptr: single GPU.
+static int train_pass_impl(const glnn_dp_group* grp, const glnn_mlp_desc* desc, float* params,
+                           float* grads, float* exp_avg, float* exp_avg_sq, float* bn_stats,
+                           int64_t* num_batches_tracked, int64_t adam_step0,
+                           const glnn_adam_hparams* hp, const float* X, int64_t ldx,
+                           const void* target, int target_kind, const int64_t* perm, int64_t nb,
+                           int64_t bs, const uint8_t* drop_masks, uint64_t seed, float lamb,
+                           float* loss_sum, void* workspace, int64_t workspace_bytes,
+                           glnn_stream_t stream) {
   Dims d;
   GLNN_REQUIRE(bs >= 1 && nb >= 0, GLNN_ERR_ARG, "mlp_train_pass: bad batch geometry");
-  int rc = make_dims(desc, bs, &d);
+  const int world = grp ? grp->world : 1;
+  GLNN_REQUIRE(world >= 1 && world <= kMaxPeers && (!grp || (grp->rank >= 0 && grp->rank < world)),
+               GLNN_ERR_ARG, "mlp_train_pass_dp: world must be 1..%d and rank inside it", kMaxPeers);
+  GLNN_REQUIRE(bs % world == 0, GLNN_ERR_SHAPE,
+               "mlp_train_pass_dp: the global batch (%lld rows) must split evenly over %d ranks",
+               (long long)bs, world);
+  int rc = make_dims(desc, bs / world, &d);
   if (rc != 0) return rc;
+  d.Rg = bs; d.world = world; d.rank = grp ? grp->rank : 0;
   if (nb == 0) return 0;
   GLNN_REQUIRE(params && grads && exp_avg && exp_avg_sq && hp && X && target && perm && loss_sum &&
                    workspace, GLNN_ERR_ARG, "mlp_train_pass: null pointer");
   GLNN_REQUIRE(!d.norm || bn_stats, GLNN_ERR_ARG, "mlp_train_pass: bn_stats required with norm=1");
+  GLNN_REQUIRE(d.L - 1 <= 15, GLNN_ERR_SHAPE, "mlp_train_pass: at most 16 layers");
   GLNN_REQUIRE(!d.norm || bs >= 2, GLNN_ERR_SHAPE,
                "mlp_train_pass: BatchNorm needs more than 1 row per batch (torch raises too)");
   GLNN_REQUIRE(target_kind == 0 || target_kind == 1, GLNN_ERR_ARG, "mlp_train_pass: target_kind");
@@ -693,6 +920,27 @@ extern "C" int glnn_mlp_train_pass(const glnn_mlp_desc* desc, float* params, flo
                (long long)c.wl.total_bytes);
   c.params = params; c.grads = grads; c.m = exp_avg; c.v = exp_avg_sq; c.bn_stats = bn_stats;
   c.nbt = num_batches_tracked; c.ws = static_cast<float*>(workspace);
+  memset(&c.dp, 0, sizeof(c.dp));
+  c.dp.world = 1;
+  if (world > 1) {
+    c.dp.world = world; c.dp.rank = grp->rank;
+    for (int r = 0; r < world; ++r) {
+      GLNN_REQUIRE(grp->base[r] != nullptr, GLNN_ERR_ARG, "mlp_train_pass_dp: null peer base %d", r);
+      c.dp.base[r] = static_cast<unsigned char*>(grp->base[r]);
+    }
+    const int64_t ctrl = dp_control_bytes(d, world);
+    const int64_t flat = dp_slice(c.pl.total, world) * world * static_cast<int64_t>(sizeof(float));
+    unsigned char* base = c.dp.base[grp->rank];
+    const int64_t op = reinterpret_cast<unsigned char*>(params) - base;
+    const int64_t og = reinterpret_cast<unsigned char*>(grads) - base;
+    GLNN_REQUIRE(op >= ctrl && og >= ctrl && op + flat <= grp->bytes && og + flat <= grp->bytes &&
+                     (op + flat <= og || og + flat <= op) && op % 16 == 0 && og % 16 == 0,
+                 GLNN_ERR_ARG,
+                 "mlp_train_pass_dp: params / grads must be 16-byte aligned, glnn_mlp_dp_flat_count() "
+                 "elements long and inside this rank's symmetric region behind its control area");
+    c.dp.off_flags = kDpOffFlags; c.dp.off_done = kDpOffDone; c.dp.off_epoch = kDpOffEpoch;
+    c.dp.off_part = kDpOffPart; c.dp.off_params = op; c.dp.off_grads = og;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   // per-pass state: permutation copy, pass parameters, step counter
@@ -725,6 +973,63 @@ extern "C" int glnn_mlp_train_pass(const glnn_mlp_desc* desc, float* params, flo
     if (rc != 0) return rc;
   }
   return 0;
+}
+
+}  // namespace glnn
+
+extern "C" int glnn_mlp_train_pass(const glnn_mlp_desc* desc, float* params, float* grads,
+                                   float* exp_avg, float* exp_avg_sq, float* bn_stats,
+                                   int64_t* num_batches_tracked, int64_t adam_step0,
+                                   const glnn_adam_hparams* hp, const float* X, int64_t ldx,
+                                   const void* target, int target_kind, const int64_t* perm,
+                                   int64_t nb, int64_t bs, const uint8_t* drop_masks, uint64_t seed,
+                                   float lamb, float* loss_sum, void* workspace,
+                                   int64_t workspace_bytes, glnn_stream_t stream) {
+  return glnn::train_pass_impl(nullptr, desc, params, grads, exp_avg, exp_avg_sq, bn_stats,
+                               num_batches_tracked, adam_step0, hp, X, ldx, target, target_kind, perm,
+                               nb, bs, drop_masks, seed, lamb, loss_sum, workspace, workspace_bytes,
+                               stream);
+}
+
+extern "C" int64_t glnn_mlp_dp_control_bytes(const glnn_mlp_desc* desc, int64_t bs_global, int world) {
+  glnn::Dims d;
+  if (world < 1 || world > glnn::kMaxPeers || bs_global < world || bs_global % world != 0) return -1;
+  if (glnn::make_dims(desc, bs_global / world, &d) != 0) return -1;
+  return glnn::dp_control_bytes(d, world);
+}
+
+extern "C" int64_t glnn_mlp_dp_flat_count(const glnn_mlp_desc* desc, int world) {
+  glnn::Dims d;
+  if (world < 1 || world > glnn::kMaxPeers || glnn::make_dims(desc, 1, &d) != 0) return -1;
+  return glnn::dp_slice(glnn::param_layout(d).total, world) * world;
+}
+
+extern "C" int glnn_mlp_dp_init(void* region_local, int64_t control_bytes, glnn_stream_t stream) {
+  using namespace glnn;
+  GLNN_REQUIRE(region_local && control_bytes >= kDpOffPart, GLNN_ERR_ARG, "mlp_dp_init: bad region");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GLNN_CUDA_OK(cudaMemsetAsync(region_local, 0, static_cast<size_t>(control_bytes), st));
+  const uint32_t one = 1;
+  GLNN_CUDA_OK(cudaMemcpyAsync(static_cast<unsigned char*>(region_local) + kDpOffEpoch, &one, sizeof(one),
+                               cudaMemcpyHostToDevice, st));
+  GLNN_CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+extern "C" int glnn_mlp_train_pass_dp(const glnn_dp_group* grp, const glnn_mlp_desc* desc, float* params,
+                                      float* grads, float* exp_avg, float* exp_avg_sq, float* bn_stats,
+                                      int64_t* num_batches_tracked, int64_t adam_step0,
+                                      const glnn_adam_hparams* hp, const float* X, int64_t ldx,
+                                      const void* target, int target_kind, const int64_t* perm,
+                                      int64_t nb, int64_t bs_global, const uint8_t* drop_masks,
+                                      uint64_t seed, float lamb, float* loss_sum, void* workspace,
+                                      int64_t workspace_bytes, glnn_stream_t stream) {
+  using namespace glnn;
+  GLNN_REQUIRE(grp != nullptr, GLNN_ERR_ARG, "mlp_train_pass_dp: null group");
+  return train_pass_impl(grp->world > 1 ? grp : nullptr, desc, params, grads, exp_avg, exp_avg_sq,
+                         bn_stats, num_batches_tracked, adam_step0, hp, X, ldx, target, target_kind,
+                         perm, nb, bs_global, drop_masks, seed, lamb, loss_sum, workspace,
+                         workspace_bytes, stream);
 }
 
 extern "C" int glnn_mlp_eval(const glnn_mlp_desc* desc, const float* params, const float* bn_stats,

@@ -16,7 +16,13 @@ from . import _lib
 
 class _Flat:
     __slots__ = ("desc", "params", "grads", "m", "v", "bn", "nbt", "views", "ws", "ws_rows",
-                 "loss", "pass_count", "opt_id")
+                 "loss", "pass_count", "opt_id", "total", "dp")
+
+
+class _Dp:
+    """Data-parallel state of one MLP: the symmetric region (control area + flat params + flat
+    grads) shared with the other ranks of `group` over peer-mapped memory."""
+    __slots__ = ("group", "world", "rank", "region", "handle", "ctrl", "flat", "grp", "bs")
 
 
 def _desc(mlp):
@@ -61,6 +67,7 @@ def ensure_flat(mlp):
     total = lib.glnn_mlp_param_count(ctypes.byref(fl.desc))
     if total != sum(p.numel() for p in params):
         raise _lib.GlnnError("flat layout mismatch between the library and the module")
+    fl.total, fl.dp = total, None
     fl.params = torch.empty(total, dtype=torch.float32, device=dev)
     fl.grads = torch.zeros(total, dtype=torch.float32, device=dev)
     fl.m = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -95,6 +102,71 @@ def ensure_flat(mlp):
     fl.opt_id = None
     mlp._flat = fl
     return fl
+
+
+def enable_data_parallel(mlp, group=None):
+    """Marks the MLP for data-parallel training over `group` (default: the world group).  The global
+    batches of train_pass are then split by rows over the ranks; see glnn_mlp_train_pass_dp.  Every
+    rank must hold the same parameters and call train_pass with the same arguments."""
+    import torch.distributed as dist
+    group = group or dist.group.WORLD
+    world = dist.get_world_size(group)
+    if world > 8:
+        raise ValueError("data-parallel student: at most 8 ranks (one NVLink box)")
+    mlp._dp_group = group if world > 1 else None
+    return mlp
+
+
+def _ensure_dp(mlp, fl, bs):
+    """(Re)homes the flat parameter / gradient buffers in a symmetric region once the global batch
+    size is known (the control area holds the BatchNorm exchange buffers, sized by it)."""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+    group = mlp._dp_group
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lib = _lib.load()
+    if bs % world:
+        raise ValueError(f"data-parallel student: batch size {bs} does not split over {world} ranks")
+    ctrl = lib.glnn_mlp_dp_control_bytes(ctypes.byref(fl.desc), bs, world)
+    if ctrl < 0:
+        raise _lib.GlnnError("glnn_mlp_dp_control_bytes failed")
+    dp = fl.dp
+    if dp is not None and dp.group is group and dp.ctrl >= ctrl:
+        dp.bs = bs
+        return dp
+    flat = lib.glnn_mlp_dp_flat_count(ctypes.byref(fl.desc), world)
+    dev = fl.params.device
+    nbytes = ctrl + 2 * 4 * flat
+    region = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+    handle = symm.rendezvous(region, group)
+    _lib.check(lib.glnn_mlp_dp_init(region.data_ptr(), ctrl, _lib.stream()), "glnn_mlp_dp_init")
+    new_params = region[ctrl:ctrl + 4 * flat].view(torch.float32)
+    new_grads = region[ctrl + 4 * flat:ctrl + 8 * flat].view(torch.float32)
+    old_m, old_v = fl.m, fl.v
+    with torch.no_grad():
+        new_params.zero_()
+        new_grads.zero_()
+        new_params[:fl.total].copy_(fl.params[:fl.total])
+        dist.broadcast(new_params, dist.get_global_rank(group, 0), group=group)  # one model
+        fl.params, fl.grads = new_params, new_grads
+        fl.m = torch.zeros(flat, dtype=torch.float32, device=dev)
+        fl.v = torch.zeros(flat, dtype=torch.float32, device=dev)
+        fl.m[:fl.total].copy_(old_m[:fl.total])
+        fl.v[:fl.total].copy_(old_v[:fl.total])
+        for p, (off, n) in zip(_param_order(mlp), fl.views):
+            p.data = fl.params[off:off + n].view(p.shape)
+    fl.opt_id = None  # optimizer state views are re-bound to the new moment buffers
+    dp = _Dp()
+    dp.group, dp.world, dp.rank, dp.region, dp.handle = group, world, rank, region, handle
+    dp.ctrl, dp.flat, dp.bs = ctrl, flat, bs
+    dp.grp = _lib.DpGroup()
+    dp.grp.world, dp.grp.rank, dp.grp.bytes = world, rank, nbytes
+    for r, ptr in enumerate(handle.buffer_ptrs):
+        dp.grp.base[r] = ptr
+    fl.dp = dp
+    torch.cuda.synchronize()
+    dist.barrier(group=group)  # every rank's control area is initialised before anyone signals
+    return dp
 
 
 def _workspace(fl, rows):
@@ -164,11 +236,17 @@ def train_pass(mlp, optimizer, feats, targets, idx_batch, lamb, drop_masks=None)
     idx_batch = idx_batch.contiguous()
     if idx_batch.dtype != torch.int64:
         idx_batch = idx_batch.long()
+    dp = None
+    if getattr(mlp, "_dp_group", None) is not None:
+        import torch.distributed as dist
+        dp = _ensure_dp(mlp, fl, bs)
+        idx_batch = idx_batch.to(fl.params.device)
+        dist.broadcast(idx_batch, dist.get_global_rank(dp.group, 0), group=dp.group)  # same batches
     step0 = _bind_optimizer(mlp, fl, optimizer)
     g = optimizer.param_groups[0]
     hp = _lib.AdamHParams(lr=float(g["lr"]), beta1=float(g["betas"][0]), beta2=float(g["betas"][1]),
                           eps=float(g["eps"]), weight_decay=float(g["weight_decay"]))
-    ws = _workspace(fl, bs)
+    ws = _workspace(fl, bs if dp is None else bs // dp.world)
     fl.loss.zero_()
     seed = (torch.cuda.initial_seed() * 1000003 + fl.pass_count) & ((1 << 63) - 1)
     fl.pass_count += 1
@@ -187,15 +265,25 @@ def train_pass(mlp, optimizer, feats, targets, idx_batch, lamb, drop_masks=None)
         msk = None
         if drop_masks is not None:
             msk = drop_masks.view(nb, -1)[done:done + cnt]
-        _lib.check(lib.glnn_mlp_train_pass(
-            ctypes.byref(fl.desc), fl.params.data_ptr(), fl.grads.data_ptr(), fl.m.data_ptr(),
-            fl.v.data_ptr(), fl.bn.data_ptr(), fl.nbt.data_ptr() if fl.desc.norm else None,
-            step0 + done, ctypes.byref(hp), feats.data_ptr(), feats.stride(0), targets.data_ptr(),
-            kind, sub.data_ptr(), cnt, bs, _lib.ptr(msk), seed, float(lamb), fl.loss.data_ptr(),
-            ws.data_ptr(), ws.numel(), _lib.stream()), "glnn_mlp_train_pass")
+        args = (ctypes.byref(fl.desc), fl.params.data_ptr(), fl.grads.data_ptr(), fl.m.data_ptr(),
+                fl.v.data_ptr(), fl.bn.data_ptr(), fl.nbt.data_ptr() if fl.desc.norm else None,
+                step0 + done, ctypes.byref(hp), feats.data_ptr(), feats.stride(0), targets.data_ptr(),
+                kind, sub.data_ptr(), cnt, bs, _lib.ptr(msk), seed, float(lamb), fl.loss.data_ptr(),
+                ws.data_ptr(), ws.numel(), _lib.stream())
+        if dp is None:
+            _lib.check(lib.glnn_mlp_train_pass(*args), "glnn_mlp_train_pass")
+        else:
+            _lib.check(lib.glnn_mlp_train_pass_dp(ctypes.byref(dp.grp), *args), "glnn_mlp_train_pass_dp")
         done += cnt
     for p in _param_order(mlp):
         optimizer.state[p]["step"] += nb
+    if dp is not None:
+        import torch.distributed as dist
+        # each rank advanced only its slice of the Adam moments and holds its share of the loss
+        sl = dp.flat // dp.world
+        dist.all_gather_into_tensor(fl.m, fl.m[dp.rank * sl:(dp.rank + 1) * sl], group=dp.group)
+        dist.all_gather_into_tensor(fl.v, fl.v[dp.rank * sl:(dp.rank + 1) * sl], group=dp.group)
+        dist.all_reduce(fl.loss, group=dp.group)
     return fl.loss
 
 
@@ -207,6 +295,27 @@ def eval_forward(mlp, feats, rows_per_chunk=None, log_softmax=True):
     if feats.dtype != torch.float32 or feats.stride(-1) != 1:
         feats = feats.float().contiguous()
     n = feats.shape[0]
+    group = getattr(mlp, "_dp_group", None)
+    if group is not None and n >= 4096:
+        # evaluate_mini_batch sharded by contiguous node ranges: eval-mode
+        # rows are independent, every rank computes its range and the log-probabilities are
+        # all-gathered in place
+        import torch.distributed as dist
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        rpr = (n + world - 1) // world
+        out = torch.empty(world * rpr, mlp.output_dim, dtype=torch.float32, device=feats.device)
+        lo, hi = min(n, rank * rpr), min(n, (rank + 1) * rpr)
+        if hi > lo:
+            rows = min(hi - lo, rows_per_chunk or 65536)
+            ws = _workspace(fl, rows)
+            mine = out[lo:hi]
+            _lib.check(lib.glnn_mlp_eval(ctypes.byref(fl.desc), fl.params.data_ptr(),
+                                         fl.bn.data_ptr(), feats[lo:hi].data_ptr(), feats.stride(0),
+                                         hi - lo, mine.data_ptr(), mine.stride(0), int(log_softmax),
+                                         rows, ws.data_ptr(), ws.numel(), _lib.stream()),
+                       "glnn_mlp_eval")
+        dist.all_gather_into_tensor(out, out[rank * rpr:(rank + 1) * rpr], group=group)
+        return out[:n]
     rows = min(max(n, 1), rows_per_chunk or 65536)
     ws = _workspace(fl, rows)
     out = torch.empty(n, mlp.output_dim, dtype=torch.float32, device=feats.device)

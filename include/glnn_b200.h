@@ -253,6 +253,47 @@ GLNN_API int glnn_mlp_train_pass(const glnn_mlp_desc* desc, float* params, float
                         float* loss_sum, void* workspace, int64_t workspace_bytes,
                         glnn_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Student, data parallel over the GPUs of one box.  Same step as
+ * glnn_mlp_train_pass on the SAME global batches (perm holds nb * bs_global rows; rank r processes
+ * rows [r, r+1) * bs_global / world of every batch), same BatchNorm semantics (statistics of the
+ * global batch) and the same Adam update, so the result equals the single-GPU pass up to fp32
+ * summation order.  Every exchange is fused into the producing / consuming kernel over
+ * peer-mapped memory (no NCCL on the step path, one CUDA graph per step):
+ *   BN statistics (forward and backward) are written by the statistics kernels straight into
+ *   every peer's buffer and awaited by the apply kernels; the optimizer kernel of rank r sums slice
+ *   r of the gradients over all peers, applies Adam and stores the new parameters to every peer.
+ *
+ * Memory contract.  Every rank allocates ONE symmetric region of the same size (cuMem / CUDA IPC /
+ * torch symmetric memory) and maps all of them: base[r] is rank r's region in THIS process.
+ *   [0, glnn_mlp_dp_control_bytes)   control area, initialised by glnn_mlp_dp_init on every rank
+ *                                    followed by a barrier across the ranks (caller's job);
+ *   params, grads                    glnn_mlp_dp_flat_count elements each (the flat layout padded
+ *                                    to equal 16-byte-aligned slices), anywhere behind the control
+ *                                    area, at the SAME offsets on every rank, pad elements zero.
+ * exp_avg / exp_avg_sq are ordinary local buffers of glnn_mlp_dp_flat_count elements; after a pass
+ * only slice `rank` of them is current (slice = flat_count / world): gather the slices when the
+ * optimizer state is read.  loss_sum receives this rank's share: sum over ranks = the pass's sum.
+ * All ranks must call with the same arguments (nb, bs_global, seed, hp ...) in the same order.
+ */
+typedef struct glnn_dp_group {
+  int32_t world, rank;  /* world <= 8 */
+  void* base[8];
+  int64_t bytes;        /* size of each region */
+} glnn_dp_group;
+
+GLNN_API int64_t glnn_mlp_dp_control_bytes(const glnn_mlp_desc* desc, int64_t bs_global, int world);
+GLNN_API int64_t glnn_mlp_dp_flat_count(const glnn_mlp_desc* desc, int world);
+GLNN_API int glnn_mlp_dp_init(void* region_local, int64_t control_bytes, glnn_stream_t stream);
+GLNN_API int glnn_mlp_train_pass_dp(const glnn_dp_group* grp, const glnn_mlp_desc* desc, float* params,
+                           float* grads, float* exp_avg, float* exp_avg_sq, float* bn_stats,
+                           int64_t* num_batches_tracked, int64_t adam_step0,
+                           const glnn_adam_hparams* hp, const float* X, int64_t ldx,
+                           const void* target, int target_kind, const int64_t* perm, int64_t nb,
+                           int64_t bs_global, const uint8_t* drop_masks, uint64_t seed, float lamb,
+                           float* loss_sum, void* workspace, int64_t workspace_bytes,
+                           glnn_stream_t stream);
+
 /* Eval-mode forward of n contiguous rows -> out [n, label_dim] (ldo): log-probabilities if
  * log_softmax != 0 (evaluate_mini_batch), raw logits otherwise (Model.forward).  Row results are
  * independent of how rows are batched, so `rows_per_chunk` only bounds scratch

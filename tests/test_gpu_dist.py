@@ -1,5 +1,7 @@
 """Multi-GPU (needs >= 2 visible GPUs; skipped otherwise): the dst-row sharded SAGE forward with one
-NCCL all-gather per layer equals the single-GPU forward on the same inputs."""
+NCCL all-gather per layer equals the single-GPU forward on the same inputs, and the data-parallel
+student pass (BatchNorm statistics, gradient reduction, Adam and parameter exchange fused into the
+step's kernels over peer memory) equals the single-GPU pass on the same global batches."""
 import os
 import sys
 
@@ -58,3 +60,142 @@ def test_sharded_forward_matches_single_gpu(world):
         assert p.exitcode == 0
     for rank, err in res:
         assert err < 1e-5, (rank, err)
+
+
+def noise_driven(k, L, norm):
+    """Same rule as tests/test_oracle_golden.py::noise_driven: a Linear bias in front of BatchNorm has
+    a mathematically-zero gradient (rounding noise that Adam turns into O(lr) moves); it cancels in
+    train mode but leaks into running_mean."""
+    if norm != "batch":
+        return False
+    if k.startswith("layers.") and k.endswith(".bias") and int(k.split(".")[1]) != L - 1:
+        return True
+    return k.endswith("running_mean")
+
+
+def _student_worker(rank, world, port, q, cfg):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import relerr_q
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
+                            world_size=world, device_id=dev)
+    from glnn_b200 import mlp_engine
+    from glnn_b200.models import Model
+    f, h, c, bs, nb, L, norm, p_drop, kind = cfg
+    n = bs * nb + 37
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(n, f, generator=gen).to(dev)
+    if kind == "kl":
+        t = torch.log_softmax(torch.randn(n, c, generator=gen), 1).to(dev)
+    else:
+        t = torch.randint(0, c, (n,), generator=gen).to(dev)
+    idx = torch.randperm(n, generator=gen)[: nb * bs].view(nb, bs)
+    masks = None
+    if p_drop > 0:
+        masks = (torch.rand(nb, L - 1, bs, h, generator=gen) >= p_drop).to(torch.uint8).to(dev)
+
+    def make():
+        torch.manual_seed(0)
+        m = Model(dict(model_name="MLP", num_layers=L, feat_dim=f, hidden_dim=h, label_dim=c,
+                       dropout_ratio=p_drop, norm_type=norm, device=dev)).train()
+        return m, torch.optim.Adam(m.parameters(), lr=0.01, weight_decay=5e-4)
+
+    # (1) ONE step: the rank-summed gradient of the data-parallel step equals the single-GPU
+    # gradient (no trajectory involved; BatchNorm statistics are those of the global batch)
+    g1, o1 = make()
+    mlp_engine.train_pass(g1.encoder, o1, x, t, idx[:1], 0.7, drop_masks=None if masks is None else masks[:1])
+    gref = mlp_engine.ensure_flat(g1.encoder).grads.clone()
+    g2, o2 = make()
+    mlp_engine.enable_data_parallel(g2.encoder)
+    mlp_engine.train_pass(g2.encoder, o2, x, t, idx[:1], 0.7, drop_masks=None if masks is None else masks[:1])
+    fl2 = mlp_engine.ensure_flat(g2.encoder)
+    gsum = fl2.grads.clone()
+    dist.all_reduce(gsum)
+    grad_q = relerr_q(gsum[:gref.numel()].cpu(), gref.cpu(), 0.999)
+    grad_max = float((gsum[:gref.numel()] - gref).abs().max() / gref.abs().max())
+    # reference: the single-GPU pass on this rank, two passes (moments and step count carry over)
+    ref, ropt = make()
+    l_ref = [float(mlp_engine.train_pass(ref.encoder, ropt, x, t, idx, 0.7, drop_masks=masks)) for _ in range(2)]
+    # data parallel over both ranks
+    dpm, dopt = make()
+    mlp_engine.enable_data_parallel(dpm.encoder)
+    l_dp = [float(mlp_engine.train_pass(dpm.encoder, dopt, x, t, idx, 0.7, drop_masks=masks)) for _ in range(2)]
+    torch.cuda.synchronize()
+    rsd, dsd = ref.state_dict(), dpm.state_dict()
+    errs = {}
+    for k in rsd:
+        a, b = rsd[k].float().cpu(), dsd[k].float().cpu()
+        errs[k] = (relerr_q(b, a, 0.99), float((a - b).abs().max() / a.abs().max().clamp(min=1e-12)))
+    mom = {}
+    for (name, pr), pd in zip(ref.named_parameters(), dpm.parameters()):
+        if noise_driven(name[len("encoder."):], L, norm):
+            continue  # a Linear bias in front of BatchNorm: its gradient is rounding noise
+        for key in ("exp_avg", "exp_avg_sq"):
+            mom[name + "." + key] = relerr_q(dopt.state[pd][key].cpu(), ropt.state[pr][key].cpu(), 0.9)
+    steps = {int(dopt.state[pd]["step"]) for pd in dpm.parameters()}
+    # every rank must hold the same parameters bit for bit (only the owner of a slice computes it)
+    flat = mlp_engine.ensure_flat(dpm.encoder).params.clone()
+    other = [torch.empty_like(flat) for _ in range(world)]
+    dist.all_gather(other, flat)
+    same = all(bool(torch.equal(o, flat)) for o in other)
+    # sharded eval equals the replicated eval
+    ev_ref = mlp_engine.eval_forward(ref.encoder, x)
+    dpm.eval(); ref.eval()
+    ev_dp = mlp_engine.eval_forward(dpm.encoder, x)
+    ev_same = bool(torch.equal(ev_dp, mlp_engine.eval_forward(dpm.encoder, x[:4000])[:4000].clone())
+                   if False else True)
+    # sharded eval (rows split over the ranks) == the plain eval of the SAME parameters
+    dpm.encoder._dp_group, grp = None, dpm.encoder._dp_group
+    ev_plain = mlp_engine.eval_forward(dpm.encoder, x)
+    dpm.encoder._dp_group = grp
+    ev_err = float((ev_dp - ev_plain).abs().max())
+    q.put((rank, l_ref, l_dp, errs, mom, steps, same, tuple(ev_dp.shape), ev_err, grad_q, grad_max))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cfg", [
+    (100, 256, 47, 512, 6, 3, "batch", 0.0, "kl"),     # BN statistics + gradients across ranks
+    (64, 128, 10, 256, 5, 2, "none", 0.0, "nll"),      # no norm: only the fused optimizer exchange
+    (100, 256, 40, 512, 4, 3, "batch", 0.3, "nll"),    # host-injected dropout masks, global rows
+])
+def test_student_data_parallel_matches_single_gpu(cfg):
+    world = 2
+    if not torch.cuda.is_available() or torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_student_worker, args=(r, world, port, q, cfg)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    nb = cfg[4]
+    for rank, l_ref, l_dp, errs, mom, steps, same, shape, ev_err, grad_q, grad_max in res:
+        # one step: gradients agree to rounding, except the few entries behind a ReLU whose
+        # pre-activation flips sign with the BatchNorm summation order (DESIGN.md 4.3)
+        assert grad_q < 1e-4, (rank, grad_q)
+        assert grad_max < 2e-2, (rank, grad_max)
+        for a, b in zip(l_ref, l_dp):                       # per-pass loss sums
+            assert abs(a - b) <= 1e-4 * abs(a), (rank, l_ref, l_dp)
+        assert steps == {2 * nb}
+        assert same, "ranks diverged"
+        # same tolerances as the single-GPU student parity tests: statistics tight, weights loose
+        # (ReLU-mask flips make lower-layer trajectories chaotic at the 1e-3 level, DESIGN.md 4.3)
+        for k, (eq, emax) in errs.items():
+            if "num_batches_tracked" in k:
+                assert emax == 0
+            elif "running_var" in k:       # follows the (slightly chaotic) weight trajectory
+                assert emax < 1e-2, (k, emax)
+            elif "running_mean" in k:      # lags the noise-driven Linear bias in front of BatchNorm
+                assert emax < 0.3, (k, emax)
+            elif not noise_driven(k[len("encoder."):], cfg[5], cfg[6]):
+                assert eq < 5e-2 and emax < 0.3, (k, eq, emax)
+        # moments follow the last few gradients, i.e. the chaotic part of the trajectory: sanity bound
+        assert max(mom.values()) < 0.15, {k: round(v, 4) for k, v in mom.items() if v > 0.05}
+        assert shape[0] == cfg[3] * cfg[4] + 37 and ev_err == 0.0
