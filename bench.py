@@ -307,9 +307,10 @@ def teacher_kernel_breakdown(g, feats, model, iters, torch):
     return rows
 
 
-def student_step_rate(dev, torch, steps=20, warmup=3):
+def student_step_rate(dev, torch, steps=20, warmup=3, world=1):
     """Distillation steps of the products student MLP3w8 (100 -> 2048 -> 2048 -> 47, bs 4096, BN,
-    dropout 0.2, Adam) on synthetic teacher log-probabilities: KL pass of `steps` steps."""
+    dropout 0.2, Adam) on synthetic teacher log-probabilities: KL pass of `steps` steps.  With
+    world > 1 the same global batches are split over the ranks (glnn_mlp_train_pass_dp)."""
     from glnn_b200 import mlp_engine
     from glnn_b200.models import Model
     torch.manual_seed(0)
@@ -317,6 +318,8 @@ def student_step_rate(dev, torch, steps=20, warmup=3):
     n = bs * 64
     model = Model(dict(model_name="MLP3w8", num_layers=3, feat_dim=f, hidden_dim=h, label_dim=c,
                        dropout_ratio=0.2, norm_type="batch", device=dev)).train()
+    if world > 1:
+        mlp_engine.enable_data_parallel(model.encoder)
     opt = torch.optim.Adam(model.parameters(), lr=0.01)
     x = torch.randn(n, f, device=dev)
     t = torch.log_softmax(torch.randn(n, c, device=dev), 1)
@@ -328,10 +331,18 @@ def student_step_rate(dev, torch, steps=20, warmup=3):
     P = sum(p.numel() for p in model.parameters())
     sw, w1 = f * h + h * h + h * c, f * h
     flops = 2.0 * bs * (3 * sw - w1)
-    return {"config": "MLP3w8 100-2048-2048-47 bs4096 KL+Adam step (ogbn-products student)",
+    if world > 1:
+        import torch.distributed as dist
+        t_ms = torch.tensor([per_step], device=dev)
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        per_step = float(t_ms)
+    return {"config": "MLP3w8 100-2048-2048-47 bs4096 KL+Adam step (ogbn-products student)"
+                      + (f", data parallel x{world}: BN statistics, gradient reduce-scatter + Adam + "
+                         "parameter all-gather fused into the step's kernels over peer memory"
+                         if world > 1 else ""),
             "value": bs / (per_step * 1e-3), "unit": "nodes/s", "ms_per_step": per_step,
             "tflops": flops / (per_step * 1e-3) / 1e12, "params": P,
-            "launches_per_step": 23}
+            "launches_per_step": 23 if world == 1 else 25}
 
 
 def run_b200(args):
@@ -370,7 +381,9 @@ def run_b200(args):
                 return model.encoder.inference(loader, feats, log_softmax=True)
         # 3 aggregations x (main + hub drain + hub finish) + 3 projections + 3 weight splits +
         # log_softmax + 2 bn_fold
-        launches_per_step = 9 + 3 + 3 + 1 + 2
+        # quantise + 3 aggregations x (main + hub drain + hub finish) + 3 projections + 3 weight
+        # splits + 2 bn_fold (log_softmax is fused into the last aggregation)
+        launches_per_step = 1 + 9 + 3 + 3 + 2
     else:
         sg = DT.ShardedGraph(g, rank, world)
         feats_pad = sg.to_padded(feats)
@@ -384,7 +397,9 @@ def run_b200(args):
         def step():
             with torch.no_grad():
                 return DT.sage_forward_sharded(sg, feats_pad, layers, norms, gather_output=False)
-        launches_per_step = 9 + 3 + 3 + 1
+        # per chunk: 3 layers x (aggregation main + hub drain + hub finish) + 3 projections;
+        # + quantise + 3 weight splits
+        launches_per_step = sg.chunks * (9 + 3) + 1 + 3
 
     def barrier():
         if world > 1:
@@ -451,7 +466,8 @@ def run_b200(args):
         d_ptr, d_idx, d_feats = torch.empty_like(sg.indptr), torch.empty_like(sg.indices), \
             torch.empty_like(feats_pad)
         h_out = torch.empty(sg.rows, dims[3]).pin_memory()
-        lo = rank * sg.rows_max
+        d_out_rows = torch.empty(sg.rows, dims[3], device=dev)
+        my_rows = sg.pad_ids[sg.r0:sg.r0 + sg.rows]
 
         def e2e_step():
             d_ptr.copy_(h_ptr, non_blocking=True)
@@ -462,7 +478,8 @@ def run_b200(args):
             with torch.no_grad():
                 o = DT.sage_forward_sharded(sg, d_feats, layers, norms, gather_output=False)
             sg.indptr, sg.indices = keep
-            h_out.copy_(o[lo: lo + sg.rows], non_blocking=True)
+            torch.index_select(o, 0, my_rows, out=d_out_rows)   # this rank's rows, local order
+            h_out.copy_(d_out_rows, non_blocking=True)
 
         def e2e_drain():
             pass
@@ -482,6 +499,12 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t)
     clk = clocks.stop() if rank == 0 else {}
+    student = None
+    if world > 1:
+        try:
+            student = student_step_rate(dev, torch, world=world)
+        except Exception as ex:
+            student = {"error": repr(ex)}
 
     if rank != 0:
         if world > 1:
@@ -509,6 +532,7 @@ def run_b200(args):
     }
     if world > 1:
         line["shards"] = gathered
+        line["student"] = student
 
     if world == 1:
         rows = teacher_kernel_breakdown(g, feats, model, max(3, min(args.steps, 10)), torch)

@@ -1,16 +1,21 @@
 """Destination-row sharded SAGE teacher forward over the GPUs of one box.
 
 The reference is single-process; this is how the same forward spreads over NVLink-connected B200s:
-  * rows (destination nodes) are cut into G contiguous ranges balanced by NNZ (power-law degrees
-    make node-count balance wrong); rank g owns CSR rows [cut[g], cut[g+1]);
-  * every rank keeps a full replica of the current layer's embeddings in a PADDED layout
-    [G * rows_max, d]: rank g's rows live at [g * rows_max, g * rows_max + rows_g).  Column ids of
-    the local CSR slice are relabelled into that layout once, so the gather kernel indexes the
-    replica directly and the exchange is one equal-sized all-gather per layer;
-  * per layer: local aggregation + projection for the owned rows (same kernels as 1 GPU) and ONE
-    all-gather of a [rows_max, d] slab (NCCL over NVLink 5 / NVSwitch) -- of the layer input for
-    an aggregate-first layer, of the narrow projection for a project-first layer.  The final
-    log-probabilities are gathered the same way.
+  * rows (destination nodes) are cut into G contiguous ranges balanced by nnz + row cost (power-law
+    degrees make node-count balance wrong); rank g owns CSR rows [cut[g], cut[g+1]);
+  * every rank keeps a full replica of the matrix the next gather reads, in a PADDED, CHUNKED layout
+    [C chunks][G ranks][rc rows]: local row r of rank g lives at (r // rc) * G * rc + g * rc + r % rc.
+    Column ids of the local CSR slice are relabelled into that layout once, so the gather kernel
+    indexes the replica directly, and chunk c of every rank forms one contiguous block that a single
+    in-place all-gather fills;
+  * per layer: local aggregation + projection of the owned rows (same kernels as 1 GPU: q24 gathers,
+    tcgen05 projections) and ONE exchange of the matrix the next gather needs -- the layer output
+    for an aggregate-first successor, the narrow projection for a project-first layer (ogbn-products'
+    last layer moves 48 instead of 256 columns).  The exchange is pipelined: the rows are processed
+    in C chunks and the NCCL all-gather of chunk c (side stream, NVLink 5 / NVSwitch) overlaps the
+    aggregation + projection of chunk c + 1;
+  * what is exchanged is the 24-bit row-packed format the gather reads anyway (768 instead of 1024
+    bytes per 256-wide row).
 """
 import torch
 import torch.distributed as dist
@@ -39,21 +44,26 @@ def nnz_balanced_cuts(indptr, world, row_cost=ROW_COST):
 
 
 class ShardedGraph:
-    """Rank-local slice of a CSRGraph in the padded global layout."""
+    """Rank-local slice of a CSRGraph in the padded, chunked global layout."""
 
-    def __init__(self, g, rank, world):
+    def __init__(self, g, rank, world, chunks=None):
         self.rank, self.world, self.n = rank, world, g.num_nodes()
         self.cuts = nnz_balanced_cuts(g.indptr, world)
-        self.rows_max = max(self.cuts[i + 1] - self.cuts[i] for i in range(world))
+        rows_max = max(max(self.cuts[i + 1] - self.cuts[i] for i in range(world)), 1)
+        if chunks is None:  # pipeline the exchange only when a chunk is still a big kernel
+            chunks = 4 if (world > 1 and rows_max >= 4 * 32768) else 1
+        self.chunks = chunks
+        self.rc = (rows_max + chunks - 1) // chunks          # rows per chunk and rank
+        self.rows_max = self.rc * chunks                      # padded rows per rank
+        self.total_rows = world * self.rows_max
         r0, r1 = self.cuts[rank], self.cuts[rank + 1]
         self.r0, self.rows = r0, r1 - r0
         p = g.indptr.to(torch.int64)
         e0, e1 = int(p[r0]), int(p[r1])
         dev = g.indices.device
         cuts_t = torch.tensor(self.cuts, dtype=torch.int64, device=dev)
-        cols = g.indices[e0:e1].to(torch.int64)
-        owner = torch.searchsorted(cuts_t, cols, right=True) - 1
-        cols = owner * self.rows_max + (cols - cuts_t[owner])
+        self._cuts_t = cuts_t
+        cols = self._pad_ids(g.indices[e0:e1].to(torch.int64))
         local_ptr = p[r0:r1 + 1] - e0
         deg = local_ptr[1:] - local_ptr[:-1]
         # the SAGE "gcn" self term becomes an explicit edge to the row's own slot in the replica
@@ -64,24 +74,42 @@ class ShardedGraph:
         merged = torch.empty(nnz, dtype=torch.int64, device=dev)
         is_self = torch.zeros(nnz, dtype=torch.bool, device=dev)
         is_self[self_pos] = True
-        merged[is_self] = rank * self.rows_max + rows
+        merged[is_self] = self._pad_ids(rows + r0)
         merged[~is_self] = cols
         self.indices = merged.to(torch.int32)
         new_ptr = local_ptr + torch.arange(self.rows + 1, device=dev, dtype=torch.int64)
         self.indptr = new_ptr.to(torch.int32) if nnz < 2 ** 31 else new_ptr
         self.inv_deg1 = (1.0 / (deg.to(torch.float32) + 1.0)).contiguous()
+        self.pad_ids = self._pad_ids(torch.arange(self.n, device=dev, dtype=torch.int64))
+
+    def _pad_ids(self, nodes):
+        """Original node ids -> row in the padded, chunked replica layout."""
+        owner = torch.searchsorted(self._cuts_t, nodes, right=True) - 1
+        owner.clamp_(0, self.world - 1)
+        local = nodes - self._cuts_t[owner]
+        return (local // self.rc) * (self.world * self.rc) + owner * self.rc + local % self.rc
+
+    def chunk_rows(self, c):
+        """Local row range [a, b) of chunk c (may be empty for the last chunks of a short shard)."""
+        a = min(self.rows, c * self.rc)
+        return a, min(self.rows, a + self.rc)
+
+    def slab_start(self, c, rank=None):
+        """First replica row of chunk c of `rank` (default: this rank)."""
+        return c * self.world * self.rc + (self.rank if rank is None else rank) * self.rc
 
     def to_padded(self, x):
-        """[n, d] in original node order -> [world * rows_max, d] padded layout (zeros in pads)."""
-        out = torch.zeros(self.world * self.rows_max, x.shape[1], dtype=x.dtype, device=x.device)
-        for g in range(self.world):
-            a, b = self.cuts[g], self.cuts[g + 1]
-            out[g * self.rows_max: g * self.rows_max + (b - a)] = x[a:b]
+        """[n, d] in original node order -> [total_rows, d] padded replica (zeros in the pads)."""
+        out = torch.zeros(self.total_rows, x.shape[1], dtype=x.dtype, device=x.device)
+        out[self.pad_ids.to(x.device)] = x
         return out
 
     def from_padded(self, xp):
-        return torch.cat([xp[g * self.rows_max: g * self.rows_max + (self.cuts[g + 1] - self.cuts[g])]
-                          for g in range(self.world)])
+        return xp[self.pad_ids.to(xp.device)]
+
+    def local_rows_of(self, xp):
+        """This rank's rows [rows, d] (local order) out of a padded replica."""
+        return xp[self.pad_ids[self.r0:self.r0 + self.rows].to(xp.device)]
 
 
 def _pad_rows(w, b, dpad):
@@ -96,35 +124,70 @@ def _pad_rows(w, b, dpad):
     return wp, bp
 
 
-def _buffer(sg, key, rows, cols, like):
-    """Per-shard cache of activation buffers: a forward reuses the same HBM every call (no
-    allocator traffic, no memsets of multi-GB tensors inside the timed region).  Pad rows are never
-    read by the gathers (no column id points at them), so their content is irrelevant."""
+def _cached(sg, key, make):
+    """Per-shard cache of activation buffers: a forward reuses the same HBM every call (no allocator
+    traffic, no memsets of multi-GB tensors inside the timed region).  Pad rows are never read by
+    the gathers (no column id points at them), so their content is irrelevant."""
     cache = sg.__dict__.setdefault("_bufs", {})
     t = cache.get(key)
-    if t is None or t.shape != (rows, cols) or t.device != like.device or t.dtype != like.dtype:
-        t = torch.zeros(rows, cols, dtype=like.dtype, device=like.device)
+    if t is None:
+        t = make()
         cache[key] = t
     return t
+
+
+class _Exchange:
+    """Chunk-wise in-place all-gather of a replica buffer on a side stream, so that the exchange of
+    chunk c overlaps the computation of chunk c + 1 (CUDA); synchronous on CPU / gloo."""
+
+    def __init__(self, sg, group, cuda, mark):
+        self.sg, self.group, self.cuda, self.mark = sg, group, cuda, mark
+        self.stream = None
+        if cuda and sg.world > 1:
+            self.stream = _cached(sg, ("comm_stream",), torch.cuda.Stream)
+
+    def chunk(self, buf2d, c):
+        sg = self.sg
+        if sg.world == 1:
+            return
+        lo = c * sg.world * sg.rc
+        whole = buf2d[lo: lo + sg.world * sg.rc]
+        mine = buf2d[sg.slab_start(c): sg.slab_start(c) + sg.rc]
+        if self.stream is None:
+            dist.all_gather_into_tensor(whole, mine, group=self.group)
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            dist.all_gather_into_tensor(whole, mine, group=self.group)
+
+    def wait(self, what):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        self.mark(what)
 
 
 def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None, log_softmax=True,
                          timings=None, gather_output=True):
     """layers: [(W [out,in], b)], norms: [(scale, shift)] folded eval-BN per hidden layer (or []).
-    feats_pad: padded replica of the input features (valid on every rank).  Returns the padded
-    replica [world * rows_max, label_dim] of the output (log-probabilities when log_softmax); the
-    returned tensor is a cached buffer that the next call overwrites.  With gather_output=False
-    the result stays sharded: only this rank's slab [rank*rows_max, +rows) of it is valid (what a
-    sharded consumer -- loss/accuracy reduction, a sharded student -- needs).
+    feats_pad: padded replica (sg.to_padded) of the input features, valid on every rank.  Returns
+    the padded replica [total_rows, label_dim] of the output (log-probabilities when log_softmax);
+    the returned tensor is a cached buffer that the next call overwrites.  With gather_output=False
+    the result stays sharded: only this rank's rows of it are valid (sg.local_rows_of) -- what a
+    sharded consumer (loss / accuracy reduction, a sharded student) needs.
 
     Exchange plan: an aggregate-first layer needs the full replica of its input (all-gather of the
     previous output, d_in wide); a project-first layer (4-padded d_out < d_in) projects only the
-    owned rows and all-gathers the narrow projection instead -- for ogbn-products the last layer
-    moves 48 instead of 256 columns.  `kernels` (default: the CUDA ops) is injectable so the host
-    logic can be exercised with gloo on CPU by the tests."""
+    owned rows and all-gathers the narrow projection instead.  `kernels` (default: the CUDA ops) is
+    injectable so that the host logic -- cuts, relabelling, chunked layout, exchange plan -- can be
+    exercised with gloo on CPU by the tests (fp32 torch double: same control flow, fp32 replicas)."""
     k = kernels or ops
-    world, rm = sg.world, sg.rows_max
-    lo, hi = sg.rank * rm, sg.rank * rm + sg.rows
+    cuda = hasattr(k, "Q24")           # the real kernels: q24 replicas, planes operands
+    world = sg.world
+    dev = feats_pad.device
+    L = len(layers)
+    C = sg.chunks
 
     def mark(name):
         if timings is not None and feats_pad.is_cuda:
@@ -132,21 +195,76 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
             ev.record()
             timings.append((name, ev))
 
-    def gather(buf):
-        if world > 1:  # in place: this rank's slab already sits at its offset in the output
-            dist.all_gather_into_tensor(buf, buf[lo: lo + rm], group=group)
-        mark(f"all_gather {tuple(buf.shape)} {buf.dtype}".replace("torch.", ""))
-
+    xch = _Exchange(sg, group, feats_pad.is_cuda, mark)
     mark("start")
-
-    h, h_full = feats_pad, True   # h: fp32 replica, or ops.Q24 replica after a q24 hand-off
-    L = len(layers)
-    planes_ok = hasattr(k, "spmm_csr_planes")
 
     def proj_first(i):
         d_o, d_i = layers[i][0].shape
         sc = norms[i][0] if (norms and i != L - 1) else None
         return ((d_o + 3) // 4 * 4) < d_i and (sc is None or d_o % 4 == 0)
+
+    # ---- format helpers: a "replica" is what a gather reads, an "operand" what a projection reads
+    def new_replica(key, d):
+        if cuda:
+            return _cached(sg, key, lambda: k.Q24.empty(sg.total_rows, d, dev, zero=True))
+        return _cached(sg, key, lambda: torch.zeros(sg.total_rows, d, dtype=torch.float32, device=dev))
+
+    def replica_2d(rep):
+        return rep.data if cuda else rep
+
+    def new_operand(key, d):
+        if cuda:
+            return _cached(sg, key, lambda: k.new_planes(max(sg.rows, 1), d, dev))
+        return _cached(sg, key, lambda: torch.zeros(max(sg.rows, 1), d, dtype=torch.float32, device=dev))
+
+    def rows_of(op, a, b):
+        if cuda:
+            return k.Planes(op.hi[a:b], op.lo[a:b], op.cols)
+        return op[a:b]
+
+    def aggregate(rep, d, a, b, out_op):
+        """mean over (neighbours + self) of replica rows for local rows [a, b) -> operand rows."""
+        if cuda:
+            k.spmm(sg.indptr[a:b + 1], sg.indices, rep, d=d, out_planes=rows_of(out_op, a, b),
+                   dst_scale=sg.inv_deg1[a:b])
+        else:
+            k.spmm_csr(sg.indptr[a:b + 1], sg.indices, rep, d=d, out=out_op[a:b],
+                       dst_scale=sg.inv_deg1[a:b])
+
+    def project(op_rows, w, wpl, b, scale, shift, relu, dest, a, b_row, c):
+        """dest: ("replica", rep) -> rows of chunk c in the gather format; ("operand", op) -> local
+        rows [a, b_row); ("final", out2d) -> fp32 rows of the padded output."""
+        kind, buf = dest
+        kw = dict(bias=b, col_scale=scale, col_shift=shift, relu=relu)
+        if kind == "replica":
+            s0 = sg.slab_start(c)
+            if cuda:
+                k.gemm_planes_q24(op_rows, wpl, out=k.Q24(buf.data[s0:s0 + (b_row - a)], buf.cols), **kw)
+            else:
+                k.gemm(op_rows, w, trans_b=True, out=buf[s0:s0 + (b_row - a)], **kw)
+        elif kind == "operand":
+            if cuda:
+                k.gemm_planes(op_rows, wpl, trans_b=True, out_planes=rows_of(buf, a, b_row), **kw)
+            else:
+                k.gemm(op_rows, w, trans_b=True, out=buf[a:b_row], **kw)
+        else:
+            s0 = sg.slab_start(c)
+            if cuda:
+                k.gemm_planes(op_rows, wpl, trans_b=True, out=buf[s0:s0 + (b_row - a)], **kw)
+            else:
+                k.gemm(op_rows, w, trans_b=True, out=buf[s0:s0 + (b_row - a)], **kw)
+
+    # ---- layer loop
+    h_rep, h_op = None, None   # replica (gather input) / operand (projection input) of the current h
+    if not proj_first(0):
+        if cuda:
+            h_rep = new_replica(("xq",), layers[0][0].shape[1])
+            k.quantize_q24(feats_pad, out=h_rep)
+            mark("features fp32 -> q24")
+        else:
+            h_rep = feats_pad
+    c_out = layers[-1][0].shape[0]
+    out = _cached(sg, ("out",), lambda: torch.zeros(sg.total_rows, c_out, dtype=torch.float32, device=dev))
 
     for l, (w, b) in enumerate(layers):
         last = l == L - 1
@@ -156,67 +274,98 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
         dpad = (d_out + 3) // 4 * 4
         if proj_first(l):
             wp, bp = _pad_rows(w, b, dpad)
-            z = _buffer(sg, ("z", l), world * rm, dpad, feats_pad)
-            k.gemm(h[lo:hi, :d_in], wp, trans_b=True, out=z[lo:hi])
+            wpl = k.split_planes(wp) if cuda else None
+            z_rep = new_replica(("z", l), dpad)
+            if h_op is None:  # first layer: the owned rows of the input features
+                h_op = new_operand(("x_op",), d_in)
+                mine = sg.local_rows_of(feats_pad)[:, :d_in].contiguous()
+                if cuda:
+                    h_op = k.split_planes(mine)
+                else:
+                    h_op[: sg.rows] = mine
+            for c in range(C):
+                a, e = sg.chunk_rows(c)
+                if e > a:
+                    project(rows_of(h_op, a, e), wp, wpl, None, None, None, 0, ("replica", z_rep), a, e, c)
+                xch.chunk(replica_2d(z_rep), c)
             mark(f"L{l} gemm {d_in}->{dpad}")
-            gather(z)
-            y = _buffer(sg, ("y", l), world * rm, dpad, feats_pad)
-            k.spmm_csr(sg.indptr, sg.indices, z, d=dpad, out=y[lo:hi], dst_scale=sg.inv_deg1,
-                       bias=bp, col_scale=scale, col_shift=shift, relu=relu)
-            mark(f"L{l} spmm d={dpad}")
-        else:
-            is_q24 = planes_ok and isinstance(h, k.Q24)
-            if not h_full:
-                gather(h.data if is_q24 else h)
-            # the output feeds another gather and nothing else -> exchange it as 24-bit rows
-            out_q24 = planes_ok and not last and not proj_first(l + 1) and d_out % 8 == 0 \
-                and d_out <= 512
-            if planes_ok:
-                # gather straight into bf16 hi/lo planes, the tensor-core projection's operand format
-                ldp = (d_in + 7) // 8 * 8
-                pl = sg.__dict__.setdefault("_planes", {}).get(l)
-                if pl is None or pl.hi.shape != (max(sg.rows, 1), ldp):
-                    mk = lambda: torch.zeros(max(sg.rows, 1), ldp, dtype=torch.int16,
-                                             device=feats_pad.device)
-                    pl = k.Planes(mk(), mk(), d_in)
-                    sg._planes[l] = pl
-                if is_q24:
-                    k.spmm_csr_q24_planes(sg.indptr, sg.indices, h, dst_scale=sg.inv_deg1, out=pl)
-                else:
-                    k.spmm_csr_planes(sg.indptr, sg.indices, h, d=d_in, dst_scale=sg.inv_deg1, out=pl)
-                mark(f"L{l} spmm d={d_in}")
-                wpl = k.split_planes(w)
-                if out_q24:
-                    cache = sg.__dict__.setdefault("_bufs", {})
-                    yq = cache.get(("yq", l))
-                    ldq = k.Q24.row_bytes(d_out)
-                    if yq is None or yq.shape != (world * rm, ldq):
-                        yq = torch.zeros(world * rm, ldq, dtype=torch.uint8, device=feats_pad.device)
-                        cache[("yq", l)] = yq
-                    k.gemm_planes_q24(pl, wpl, out=k.Q24(yq[lo:hi], d_out), bias=b, col_scale=scale,
-                                      col_shift=shift, relu=relu)
-                    y = k.Q24(yq, d_out)
-                else:
-                    y = _buffer(sg, ("y", l), world * rm, dpad, feats_pad)
-                    k.gemm_planes(pl, wpl, trans_b=True, out=y[lo:hi, :d_out], bias=b, col_scale=scale,
-                                  col_shift=shift, relu=relu)
+            xch.wait(f"L{l} exchange z ({dpad} wide)")
+            nxt_pf = (not last) and proj_first(l + 1)
+            if last:
+                # bias (+ log_softmax) fused into the gather epilogue, straight into the padded output
+                for c in range(C):
+                    a, e = sg.chunk_rows(c)
+                    if e <= a:
+                        continue
+                    s0 = sg.slab_start(c)
+                    if cuda and log_softmax:
+                        k.spmm(sg.indptr[a:e + 1], sg.indices, z_rep, d=dpad, out=out[s0:s0 + (e - a)],
+                               dst_scale=sg.inv_deg1[a:e], bias=bp, log_softmax=d_out)
+                    elif cuda:
+                        y = k.spmm(sg.indptr[a:e + 1], sg.indices, z_rep, d=dpad,
+                                   dst_scale=sg.inv_deg1[a:e], bias=bp)
+                        out[s0:s0 + (e - a)] = y[:, :d_out]
+                    else:
+                        y = k.spmm_csr(sg.indptr[a:e + 1], sg.indices, z_rep, d=dpad,
+                                       dst_scale=sg.inv_deg1[a:e], bias=bp)[:, :d_out]
+                        out[s0:s0 + (e - a)] = torch.log_softmax(y, 1) if log_softmax else y
+                mark(f"L{l} spmm d={dpad}" + (" +log_softmax" if log_softmax else ""))
+                h_rep = h_op = None
             else:
-                y = _buffer(sg, ("y", l), world * rm, dpad, h)
-                agg = _buffer(sg, ("agg", l), max(sg.rows, 1), (d_in + 3) // 4 * 4, h)
-                k.spmm_csr(sg.indptr, sg.indices, h, d=d_in, out=agg[: sg.rows, :d_in],
-                           dst_scale=sg.inv_deg1)
-                mark(f"L{l} spmm d={d_in}")
-                k.gemm(agg[: sg.rows, :d_in], w, trans_b=True, out=y[lo:hi, :d_out], bias=b,
-                       col_scale=scale, col_shift=shift, relu=relu)
-            mark(f"L{l} gemm {d_in}->{d_out}")
-        h, h_full = y, False
-    c = layers[-1][0].shape[0]
-    out = _buffer(sg, ("out",), world * rm, c, h)
-    if log_softmax:
-        k.log_softmax(h[lo:hi, :c], out=out[lo:hi])
-    else:
-        out[lo:hi] = h[lo:hi, :c]
-    mark("log_softmax")
-    if gather_output:  # otherwise every rank keeps only its own slab valid (rows lo:hi)
-        gather(out)
+                y_op = new_operand(("y_op", l), dpad)
+                if cuda:
+                    k.spmm(sg.indptr, sg.indices, z_rep, d=dpad, out_planes=rows_of(y_op, 0, sg.rows),
+                           dst_scale=sg.inv_deg1, bias=bp, col_scale=scale, col_shift=shift, relu=relu)
+                else:
+                    k.spmm_csr(sg.indptr, sg.indices, z_rep, d=dpad, out=y_op[: sg.rows],
+                               dst_scale=sg.inv_deg1, bias=bp, col_scale=scale, col_shift=shift, relu=relu)
+                mark(f"L{l} spmm d={dpad}")
+                h_op, h_rep = (k.Planes(y_op.hi, y_op.lo, d_out) if cuda else y_op[:, :d_out]), None
+                if not nxt_pf:  # an aggregate-first successor needs the replica of this output
+                    h_rep = new_replica(("yrep", l), d_out)
+                    for c in range(C):
+                        a, e = sg.chunk_rows(c)
+                        s0 = sg.slab_start(c)
+                        if e > a:
+                            if cuda:
+                                k.quantize_q24(rows_of(h_op, a, e).float(), out=k.Q24(h_rep.data[s0:s0 + e - a], d_out))
+                            else:
+                                h_rep[s0:s0 + e - a] = h_op[a:e]
+                        xch.chunk(replica_2d(h_rep), c)
+                    xch.wait(f"L{l} exchange output ({d_out} wide)")
+        else:
+            wpl = k.split_planes(w) if cuda else None
+            agg = new_operand(("agg", l), d_in)
+            nxt_pf = (not last) and proj_first(l + 1)
+            if last:
+                dest = ("final", out)
+            elif nxt_pf:
+                dest = ("operand", new_operand(("y_op", l), d_out))
+            else:
+                dest = ("replica", new_replica(("yrep", l), d_out))
+            for c in range(C):
+                a, e = sg.chunk_rows(c)
+                if e > a:
+                    aggregate(h_rep, d_in, a, e, agg)
+                    project(rows_of(agg, a, e), w, wpl, b, scale, shift, relu, dest, a, e, c)
+                if dest[0] == "replica":
+                    xch.chunk(replica_2d(dest[1]), c)
+            mark(f"L{l} spmm d={d_in} + gemm {d_in}->{d_out}")
+            if dest[0] == "replica":
+                xch.wait(f"L{l} exchange output ({d_out} wide)")
+                h_rep, h_op = dest[1], None
+            elif dest[0] == "operand":
+                h_rep, h_op = None, dest[1]
+            else:
+                if log_softmax:
+                    for c in range(C):
+                        a, e = sg.chunk_rows(c)
+                        s0 = sg.slab_start(c)
+                        if e > a:
+                            k.log_softmax(out[s0:s0 + e - a], out=out[s0:s0 + e - a])
+                    mark("log_softmax")
+    if gather_output:  # otherwise every rank keeps only its own rows valid
+        for c in range(C):
+            xch.chunk(out, c)
+        xch.wait("exchange output")
     return out

@@ -97,6 +97,9 @@ class TorchKernels:
                  src_scale=None, dst_scale=None, bias=None, col_scale=None, col_shift=None, relu=0):
         import glnn_oracle as O
         d = x.shape[1] if d is None else d
+        if int(indptr[0]) != 0:  # a row range of a larger CSR (absolute offsets, as the kernel takes it)
+            indices = indices[int(indptr[0]): int(indptr[-1])]
+            indptr = indptr - indptr[0]
         xs = x[:, :d].contiguous()
         if src_scale is not None:
             xs = xs * src_scale.unsqueeze(1)
@@ -126,3 +129,122 @@ class TorchKernels:
             out.copy_(y)
             return out
         return y
+
+
+def dp_student_pass(dist, rank, world, p, state, feats, targets, kind, idx_batch, lamb, num_layers,
+                    norm, lr, weight_decay, eps=1e-5, momentum=0.1):
+    """Test double of glnn_mlp_train_pass_dp (csrc/mlp.cu) in plain torch over any process group:
+    the SAME decomposition the kernels use, so that the protocol can be checked on CPU (gloo):
+      * rank r takes rows [r, r+1) * B / world of every global batch;
+      * BatchNorm: per-rank (mean, M2) -> all_gather -> Chan combination in rank order -> every rank
+        normalises with the statistics of the GLOBAL batch and updates its running stats with them;
+      * backward: per-rank S1 = sum g, S2 = sum g * xhat -> all_gather -> sums; dgamma / dbeta are
+        already global, so only rank 0 contributes them to the gradient reduction;
+      * d(lamb * loss)/dlogits is scaled by 1 / B_global;
+      * optimizer: rank r sums slice r of the flat gradient over the ranks (rank order), applies Adam
+        to that slice with its slice of the moments, the new parameter slices are all-gathered.
+    p / state: the oracle's dicts (glnn_oracle.mlp_forward), updated in place.  Returns the pass's
+    mean unscaled loss (sum of the ranks' shares)."""
+    import math
+    import torch
+    keys = [k for k in p if not (k.endswith("running_mean") or k.endswith("running_var")
+                                 or k.endswith("num_batches_tracked"))]
+    nb, B = idx_batch.shape
+    R = B // world
+
+    def gather_cat(t):
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t.contiguous())
+        return outs
+
+    total = 0.0
+    for i in range(nb):
+        rows = idx_batch[i, rank * R:(rank + 1) * R]
+        h = feats[rows]
+        cache = []
+        for l in range(num_layers):
+            w, b = p[f"layers.{l}.weight"], p[f"layers.{l}.bias"]
+            z = h @ w.t() + b
+            if l == num_layers - 1:
+                cache.append((h, None, None, None))
+                h = z
+                break
+            if norm == "batch":
+                mu_l = z.mean(0)
+                m2_l = ((z - mu_l) ** 2).sum(0)
+                parts = gather_cat(torch.stack([mu_l, m2_l]))
+                n, mu, m2 = 0.0, torch.zeros_like(mu_l), torch.zeros_like(mu_l)
+                for part in parts:                      # Chan, rank order
+                    delta, tot = part[0] - mu, n + R
+                    mu = mu + delta * (R / tot)
+                    m2 = m2 + part[1] + delta * delta * (n * R / tot)
+                    n = tot
+                var = m2 / B
+                p[f"norms.{l}.running_mean"].mul_(1 - momentum).add_(momentum * mu)
+                p[f"norms.{l}.running_var"].mul_(1 - momentum).add_(momentum * m2 / max(B - 1, 1))
+                p[f"norms.{l}.num_batches_tracked"] += 1
+                invstd = 1.0 / torch.sqrt(var + eps)
+                xhat = (z - mu) * invstd
+                y = xhat * p[f"norms.{l}.weight"] + p[f"norms.{l}.bias"]
+            else:
+                xhat, invstd, y = None, None, z
+            cache.append((h, xhat, invstd, y))
+            h = torch.relu(y)
+        logits = h
+        s = torch.log_softmax(logits, dim=1)
+        tg = targets[rows]
+        if kind == "nll":
+            loss_share = -s[torch.arange(R), tg].sum() / B
+            d = s.exp()
+            d[torch.arange(R), tg] -= 1.0
+        else:
+            et = tg.exp()
+            loss_share = (et * (tg - s)).sum() / B
+            d = s.exp() * et.sum(1, keepdim=True) - et
+        d = d * (lamb / B)
+        total += float(loss_share)
+        grads = {}
+        for l in reversed(range(num_layers)):
+            h_in, xhat, invstd, y = cache[l]
+            if l != num_layers - 1:
+                d = d * (y > 0).to(d.dtype)
+                if norm == "batch":
+                    parts = gather_cat(torch.stack([d.sum(0), (d * xhat).sum(0)]))
+                    S1, S2 = sum(q[0] for q in parts), sum(q[1] for q in parts)
+                    grads[f"norms.{l}.bias"] = S1 if rank == 0 else torch.zeros_like(S1)
+                    grads[f"norms.{l}.weight"] = S2 if rank == 0 else torch.zeros_like(S2)
+                    d = (p[f"norms.{l}.weight"] * invstd / B) * (B * d - S1 - xhat * S2)
+            grads[f"layers.{l}.weight"] = d.t() @ h_in
+            grads[f"layers.{l}.bias"] = d.sum(0)
+            if l > 0:
+                d = d @ p[f"layers.{l}.weight"]
+        # fused optimizer: flat buffers, equal slices of a multiple of 4 elements
+        flat_g = torch.cat([grads[k].reshape(-1) for k in keys])
+        P = flat_g.numel()
+        sl = (P + 4 * world - 1) // (4 * world) * 4
+        pad = lambda t: torch.cat([t, t.new_zeros(sl * world - P)])
+        flat_g = pad(flat_g)
+        flat_p = pad(torch.cat([p[k].reshape(-1) for k in keys]))
+        flat_m = pad(torch.cat([state[k]["exp_avg"].reshape(-1) for k in keys]))
+        flat_v = pad(torch.cat([state[k]["exp_avg_sq"].reshape(-1) for k in keys]))
+        lo, hi = rank * sl, (rank + 1) * sl
+        g = sum(q[lo:hi] for q in gather_cat(flat_g))      # P2P loads of slice `rank`, rank order
+        t = state[keys[0]]["step"] + 1
+        if weight_decay != 0:
+            g = g + weight_decay * flat_p[lo:hi]
+        m = flat_m[lo:hi] * 0.9 + 0.1 * g
+        v = flat_v[lo:hi] * 0.999 + 0.001 * g * g
+        denom = v.sqrt() / math.sqrt(1 - 0.999 ** t) + 1e-8
+        new_p = flat_p[lo:hi] - (lr / (1 - 0.9 ** t)) * m / denom
+        all_p, all_m, all_v = (torch.cat(gather_cat(x)) for x in (new_p, m, v))
+        off = 0
+        for k in keys:
+            n = p[k].numel()
+            p[k].copy_(all_p[off:off + n].view_as(p[k]))
+            state[k]["exp_avg"].copy_(all_m[off:off + n].view_as(p[k]))
+            state[k]["exp_avg_sq"].copy_(all_v[off:off + n].view_as(p[k]))
+            state[k]["step"] = t
+            off += n
+    tot = torch.tensor([total], dtype=torch.float64)
+    dist.all_reduce(tot)
+    return float(tot) / nb

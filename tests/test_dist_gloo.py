@@ -27,7 +27,7 @@ def _problem():
     return n, src, dst, layers, norms, x
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, chunks=1):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     import warnings
@@ -38,15 +38,16 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     n, src, dst, layers, norms, x = _problem()
     g = graph((src, dst), num_nodes=n)
-    sg = DT.ShardedGraph(g, rank, world)
+    sg = DT.ShardedGraph(g, rank, world, chunks=chunks)
     out = DT.sage_forward_sharded(sg, sg.to_padded(x), layers, norms, kernels=TorchKernels)
+    assert sg.total_rows == world * sg.rc * chunks and sg.rows_max == sg.rc * chunks
     q.put((rank, sg.from_padded(out).numpy(), sg.cuts))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_forward_equals_single_process(world):
+@pytest.mark.parametrize("world,chunks", [(2, 1), (3, 1), (2, 3), (3, 4)])
+def test_sharded_forward_equals_single_process(world, chunks):
     import glnn_oracle as O
     n, src, dst, layers, norms, x = _problem()
     indptr, indices = O.csr_from_edges(src, dst, n)
@@ -54,8 +55,8 @@ def test_sharded_forward_equals_single_process(world):
     want = torch.log_softmax(O.sage_inference(indptr, indices, x, layers, bn), 1).numpy()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + world + (os.getpid() % 500)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29500 + world + 7 * chunks + (os.getpid() % 400)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, chunks)) for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]
@@ -78,3 +79,70 @@ def test_nnz_balanced_cuts():
     even = nnz_balanced_cuts(indptr, 4, row_cost=16)
     sizes = [even[i + 1] - even[i] for i in range(4)]
     assert max(sizes) - min(sizes) < 80   # row-weighted cuts keep the slabs (and the padding) even
+
+
+def _student_problem(norm):
+    gen = torch.Generator().manual_seed(3)
+    f, h, c, L, n, bs, nb = 12, 16, 5, 3, 200, 24, 4
+    p = {}
+    dims = [f, h, h, c]
+    for l in range(L):
+        p[f"layers.{l}.weight"] = torch.randn(dims[l + 1], dims[l], generator=gen, dtype=torch.float64) * 0.3
+        p[f"layers.{l}.bias"] = torch.randn(dims[l + 1], generator=gen, dtype=torch.float64) * 0.1
+    if norm == "batch":
+        for l in range(L - 1):
+            p[f"norms.{l}.weight"] = torch.rand(h, generator=gen, dtype=torch.float64) + 0.5
+            p[f"norms.{l}.bias"] = torch.randn(h, generator=gen, dtype=torch.float64) * 0.1
+            p[f"norms.{l}.running_mean"] = torch.zeros(h, dtype=torch.float64)
+            p[f"norms.{l}.running_var"] = torch.ones(h, dtype=torch.float64)
+            p[f"norms.{l}.num_batches_tracked"] = torch.zeros((), dtype=torch.int64)
+    x = torch.randn(n, f, generator=gen, dtype=torch.float64)
+    soft = torch.log_softmax(torch.randn(n, c, generator=gen, dtype=torch.float64), 1)
+    hard = torch.randint(0, c, (n,), generator=gen)
+    idx = torch.randperm(n, generator=gen)[: nb * bs].view(nb, bs)
+    return p, x, soft, hard, idx, L
+
+
+def _student_worker(rank, world, port, q, norm):
+    for pth in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+        sys.path.insert(0, pth)
+    import glnn_oracle as O
+    from helpers import dp_student_pass
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    p, x, soft, hard, idx, L = _student_problem(norm)
+    st = O.init_adam_state(p)
+    l1 = dp_student_pass(dist, rank, world, p, st, x, hard, "nll", idx, 0.3, L, norm, 0.01, 5e-4)
+    l2 = dp_student_pass(dist, rank, world, p, st, x, soft, "kl", idx, 0.7, L, norm, 0.01, 5e-4)
+    q.put((rank, l1, l2, {k: v.numpy().copy() for k, v in p.items()},
+           {k: v["exp_avg_sq"].numpy().copy() for k, v in st.items()}))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,norm", [(2, "batch"), (3, "batch"), (2, "none")])
+def test_student_data_parallel_protocol_equals_single_process(world, norm):
+    """The decomposition that glnn_mlp_train_pass_dp fuses into its kernels (global-batch BatchNorm
+    from per-rank partials, dgamma/dbeta contributed once, 1/B_global loss scaling, slice-owned Adam
+    with parameter all-gather), restated in fp64 torch and run over gloo, reproduces the oracle's
+    single-process train_mini_batch (train_and_eval.py:59-86) to fp64 rounding."""
+    import glnn_oracle as O
+    p, x, soft, hard, idx, L = _student_problem(norm)
+    st = O.init_adam_state(p)
+    w1 = O.train_mini_batch(p, st, x, hard, "nll", idx.shape[1], idx, 0.3, L, norm, 0.0, 0.01, 5e-4)
+    w2 = O.train_mini_batch(p, st, x, soft, "kl", idx.shape[1], idx, 0.7, L, norm, 0.0, 0.01, 5e-4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29300 + world + (os.getpid() % 150)
+    procs = [ctx.Process(target=_student_worker, args=(r, world, port, q, norm)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    for rank, l1, l2, got, got_v in results:
+        assert abs(l1 - w1) < 1e-12 and abs(l2 - w2) < 1e-12, (rank, l1, w1, l2, w2)
+        for k, v in p.items():
+            assert np.allclose(got[k].astype(np.float64), v.double().numpy(), rtol=1e-9, atol=1e-12), (rank, k)
+        for k, v in st.items():
+            assert np.allclose(got_v[k], v["exp_avg_sq"].numpy(), rtol=1e-9, atol=1e-30), (rank, k)

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, chunks):
     sys.path.insert(0, ROOT)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
@@ -31,7 +31,7 @@ def _worker(rank, world, port, q):
                                      label_dim=47, dropout_ratio=0.5, norm_type="batch",
                                      device=dev))).eval()
     feats = torch.randn(n, 100, generator=torch.Generator().manual_seed(1)).to(dev)
-    sg = DT.ShardedGraph(g, rank, world)
+    sg = DT.ShardedGraph(g, rank, world, chunks=chunks)
     enc = model.encoder
     layers = [(c.fc_neigh.weight.detach(), c.fc_neigh.bias.detach()) for c in enc.layers]
     norms = [ops.bn_fold(b.weight, b.bias, b.running_mean, b.running_var, b.eps) for b in enc.norms]
@@ -39,19 +39,24 @@ def _worker(rank, world, port, q):
         out = sg.from_padded(DT.sage_forward_sharded(sg, sg.to_padded(feats), layers, norms))
         ref = enc.inference(G.FullNeighborLoader(g), feats, log_softmax=True)
     err = float((out - ref).abs().max() / ref.abs().max())
-    q.put((rank, err))
+    # sharded output: only the owned rows, no final exchange
+    with torch.no_grad():
+        o2 = DT.sage_forward_sharded(sg, sg.to_padded(feats), layers, norms, gather_output=False)
+    mine = sg.local_rows_of(o2)
+    err2 = float((mine - ref[sg.r0:sg.r0 + sg.rows]).abs().max() / ref.abs().max())
+    q.put((rank, max(err, err2)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2])
-def test_sharded_forward_matches_single_gpu(world):
+@pytest.mark.parametrize("world,chunks", [(2, 1), (2, 3)])
+def test_sharded_forward_matches_single_gpu(world, chunks):
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + (os.getpid() % 200)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = 29700 + 3 * chunks + (os.getpid() % 150)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, chunks)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
