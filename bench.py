@@ -345,6 +345,121 @@ def student_step_rate(dev, torch, steps=20, warmup=3, world=1):
             "launches_per_step": 23 if world == 1 else 25}
 
 
+def other_configs(dev, torch, hbm_peak):
+    """The remaining BASELINE.json configs, measured in the same run (each a few hundred ms):
+    configs[0] cora GCN teacher (train step + evaluate), configs[1] arxiv SAGE forward, configs[2]
+    arxiv student distillation steps.  CPU side: the oracle port on the host cores where it exists."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    from glnn_b200 import graph as G, mlp_engine, train_and_eval as TE
+    from glnn_b200.models import Model
+    from glnn_b200.utils import get_evaluator
+    from glnn_b200.workloads import SHAPES, dataset_graph, randomise_bn_, sage_bytes_per_forward
+    out = {}
+    # ---- configs[1]: SAGE teacher forward, ogbn-arxiv shape
+    s = SHAPES["ogbn-arxiv"]
+    g = dataset_graph("ogbn-arxiv", device=dev, seed=0)
+    n, dims = s["n"], DIMS["ogbn-arxiv"]
+    torch.manual_seed(0)
+    model = randomise_bn_(Model(dict(model_name="SAGE", num_layers=3, feat_dim=dims[0], hidden_dim=dims[1],
+                                     label_dim=dims[3], dropout_ratio=0.2, norm_type="batch",
+                                     device=dev))).eval()
+    feats = torch.randn(n, dims[0], device=dev)
+    loader = G.FullNeighborLoader(g)
+
+    def fwd():
+        with torch.no_grad():
+            return model.encoder.inference(loader, feats, log_softmax=True)
+    for _ in range(3):
+        fwd()
+    ms = _event_ms(fwd, 20, torch)
+    alg = sage_bytes_per_forward(n, g.num_edges(), dims)
+    entry = {"workload": "SAGE teacher full-graph forward + log_softmax, ogbn-arxiv shape",
+             "nodes": n, "edges": g.num_edges(), "ms": round(ms, 4), "nodes_per_s": n / (ms * 1e-3),
+             "algorithmic_GBps": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / hbm_peak,
+             "note": "the whole working set (features 87 MB, CSR 10 MB, activations 173 MB) is close to "
+                     "the 126 MB L2; back-to-back forwards, no flush"}
+    try:
+        indptr = g.indptr.cpu().numpy().astype("int64")
+        indices = g.indices.cpu().numpy().astype("int64")
+        rate, dt, nrows = cpu_teacher_rate(indptr, indices, n, dims, 2, 2, 1)
+        entry["cpu_port_nodes_per_s"] = rate
+        entry["cpu_sample"] = f"every 2nd destination row ({nrows} rows x 3 layers), {dt:.2f} s/step"
+    except Exception as ex:
+        entry["cpu_port_error"] = repr(ex)
+    out["ogbn-arxiv SAGE forward"] = entry
+    # ---- configs[2]: arxiv students, bs 512, one soft-label (KL) pass of 100 steps
+    x = feats
+    t = torch.log_softmax(torch.randn(n, dims[3], device=dev), 1)
+    for name, hidden, p_drop in (("MLP", 256, 0.2), ("MLP3w4", 1024, 0.5)):
+        torch.manual_seed(0)
+        st = Model(dict(model_name=name, num_layers=3, feat_dim=dims[0], hidden_dim=hidden,
+                        label_dim=dims[3], dropout_ratio=p_drop, norm_type="batch", device=dev)).train()
+        opt = torch.optim.Adam(st.parameters(), lr=0.01)
+        steps, bs = 100, 512
+        idx = torch.randperm(n)[: steps * bs].view(steps, bs).to(dev)
+        mlp_engine.train_pass(st.encoder, opt, x, t, idx[:4], 1.0)
+        ms = _event_ms(lambda: mlp_engine.train_pass(st.encoder, opt, x, t, idx, 1.0), 2, torch) / steps
+        sw, w1 = dims[0] * hidden + hidden * hidden + hidden * dims[3], dims[0] * hidden
+        st.eval()
+        ev_ms = _event_ms(lambda: mlp_engine.eval_forward(st.encoder, x), 3, torch)
+        out[f"ogbn-arxiv student {name} (3x{hidden}, bs 512, KL + Adam)"] = {
+            "ms_per_step": round(ms, 5), "nodes_per_s": bs / (ms * 1e-3),
+            "TFLOPs_fp32_equivalent": 2.0 * bs * (3 * sw - w1) / (ms * 1e-3) / 1e12,
+            "eval_all_nodes_ms": round(ev_ms, 4), "eval_nodes_per_s": n / (ev_ms * 1e-3),
+            "note": "one CUDA graph of 23 launches per step; at bs 512 the step is launch/latency-bound"}
+    del g, feats, x, t
+    # ---- configs[0]: GCN teacher on a cora-shaped graph (full-batch train step + evaluate)
+    s = SHAPES["cora"]
+    g = dataset_graph("cora", device=dev, seed=0)
+    n = s["n"]
+    torch.manual_seed(0)
+    model = Model(dict(model_name="GCN", num_layers=2, feat_dim=s["feat"], hidden_dim=s["hidden"],
+                       label_dim=s["classes"], dropout_ratio=0.8, norm_type="none", device=dev))
+    feats = (torch.rand(n, s["feat"], device=dev) < 0.0127).float()
+    labels = torch.randint(0, s["classes"], (n,), device=dev)
+    idx_train = torch.randperm(n)[:140].to(dev)
+    crit, evaluator = torch.nn.NLLLoss(), get_evaluator("cora")
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=1e-3)
+    for _ in range(3):
+        TE.train(model, g, feats, labels, crit, opt, idx_train)
+        TE.evaluate(model, g, feats, labels, crit, evaluator, idx_train)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        TE.train(model, g, feats, labels, crit, opt, idx_train)
+    torch.cuda.synchronize()
+    t_train = (time.perf_counter() - t0) / 20
+    t0 = time.perf_counter()
+    for _ in range(20):
+        TE.evaluate(model, g, feats, labels, crit, evaluator, idx_train)
+    torch.cuda.synchronize()
+    t_eval = (time.perf_counter() - t0) / 20
+    entry = {"workload": "GCN teacher 1433-64-7 on a cora-shaped graph (2485 nodes, CPF-style binary "
+                         "features), full-batch train step and evaluate, wall clock incl. the "
+                         "reference's per-step host sync",
+             "train_step_ms": round(t_train * 1e3, 4), "evaluate_ms": round(t_eval * 1e3, 4),
+             "train_nodes_per_s": n / t_train, "eval_nodes_per_s": n / t_eval,
+             "note": "launch-latency-bound at this size (SURVEY 8a3); training runs autograd over the "
+                     "aggregation / projection kernels"}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import glnn_oracle as O
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        layers = [(sd[f"encoder.layers.{l}.weight"], sd[f"encoder.layers.{l}.bias"]) for l in range(2)]
+        ip, ix = g.indptr.cpu().numpy().astype("int64"), g.indices.cpu().numpy().astype("int64")
+        fc = feats.cpu()
+        O.gcn_forward(ip, ix, fc, layers)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            O.gcn_forward(ip, ix, fc, layers)
+        entry["cpu_port_evaluate_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 3)
+    except Exception as ex:
+        entry["cpu_port_error"] = repr(ex)
+    out["cora GCN teacher"] = entry
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -576,6 +691,12 @@ def run_b200(args):
                           f"{stride}th destination row = {nrows} rows x 3 layers, {dt:.2f} s/step"}
         except Exception as ex:
             line["cpu_baseline"] = {"error": repr(ex)}
+        del g, feats, loader
+        torch.cuda.empty_cache()
+        try:
+            line["other_configs"] = other_configs(dev, torch, hbm_peak)
+        except Exception as ex:
+            line["other_configs"] = {"error": repr(ex)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

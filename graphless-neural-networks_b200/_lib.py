@@ -5,7 +5,7 @@ import os
 import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libglnn_b200.so")
+LIB_PATH = os.environ.get("GLNN_B200_LIB") or os.path.join(HERE, "lib", "libglnn_b200.so")
 
 _lock = threading.Lock()
 _lib = None

@@ -27,6 +27,13 @@
 
 #include "common.cuh"
 
+// Resident CTAs per SM of the narrow (<= 8 values per lane) kernels: 3 (85 registers, no spills, 24
+// warps) measured 3-5 % faster than 4 (64 registers, ~200 B of spills in the gather loop) and 8 %
+// faster than 2 on the q24 rows of the products forward.
+#ifndef GLNN_SPMM_MINB
+#define GLNN_SPMM_MINB 3
+#endif
+
 namespace glnn {
 
 struct HubTask {
@@ -161,6 +168,7 @@ __device__ __forceinline__ void load_chunk(const SpmmArgs& a, int64_t r, int col
   }
 }
 
+template <bool PLANES = true>
 __device__ __forceinline__ void store4(const SpmmArgs& a, int64_t row, int col, const float* v,
                                        uint64_t pol) {
   if (a.Y)
@@ -168,7 +176,7 @@ __device__ __forceinline__ void store4(const SpmmArgs& a, int64_t row, int col, 
          make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]),
                     __float_as_uint(v[3])),
          pol);
-  if (a.Yh) {
+  if (PLANES && a.Yh) {
     const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
     const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
     const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[0] - f01.x, v[1] - f01.y);
@@ -185,8 +193,25 @@ template <int W>
 __device__ __forceinline__ void store_chunk(const SpmmArgs& a, int64_t row, int col,
                                             const float (&v)[W], uint64_t pol) {
   if constexpr (W == 8) {
-    store4(a, row, col, v, pol);
-    store4(a, row, col + 4, v + 4, pol);
+    // one 16-byte store per plane (two 8-byte halves of a sector issued by different instructions
+    // reached DRAM as partial writes: ncu showed 4.5 GB written for 2.5 GB of planes)
+    if (a.Y) {
+      store4<false>(a, row, col, v, pol);
+      store4<false>(a, row, col + 4, v + 4, pol);
+    }
+    if (a.Yh) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 hh = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const float2 f = __bfloat1622float2(hh);
+        const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[i] = *reinterpret_cast<const uint32_t*>(&ll);
+      }
+      st16(a.Yh + row * a.ldyp + col, make_uint4(h[0], h[1], h[2], h[3]), pol);
+      st16(a.Yl + row * a.ldyp + col, make_uint4(l[0], l[1], l[2], l[3]), pol);
+    }
   } else if constexpr (W == 4) {
     store4(a, row, col, v, pol);
   } else {
@@ -208,13 +233,14 @@ __device__ __forceinline__ void gather_range(const SpmmArgs& a, int64_t beg, int
   // neighbours in flight per group iteration: q24 rows are 25 % smaller and their decode costs
   // registers, so keep 8 of them in flight as RAW words (6 registers each) and decode afterwards
   constexpr int U = (W == 8) ? (G >= 8 ? 8 : G) : ((G >= 4) ? 4 : G);
+  // (requesting the ids of the next batch ahead of the current rows was measured and does not help:
+  // 14.8 / 8.4 / 4.4 ms with vs 14.9 / 8.3 / 4.4 ms without at d = 256 / 100 / 48 -- the kernel is
+  // DRAM-bound, not latency-bound)
   for (int64_t base = beg; base < end; base += G) {
-    const int64_t e = base + gl;
-    int my = -1;
+    const int my = (base + gl < end) ? static_cast<int>(ld4(a.indices + base + gl, pol.cold)) : -1;
     float mys = 1.f;
-    if (e < end) {
-      my = static_cast<int>(ld4(a.indices + e, pol.cold));
-      if constexpr (HAS_SS) mys = __ldg(a.src_scale + my);
+    if constexpr (HAS_SS) {
+      if (my >= 0) mys = __ldg(a.src_scale + my);
     }
     const int cnt = static_cast<int>(min(static_cast<int64_t>(G), end - base));
     for (int j = 0; j < cnt; j += U) {
@@ -405,7 +431,7 @@ __device__ __forceinline__ void cta_gather(const SpmmArgs& a, int64_t beg, int64
 }
 
 template <int G, int VPL, int W, bool HAS_SS>
-__global__ void __launch_bounds__(kWarps * 32, (VPL * W <= 8 ? 4 : 1)) spmm_csr_kernel(const SpmmArgs a) {
+__global__ void __launch_bounds__(kWarps * 32, (VPL * W <= 8 ? GLNN_SPMM_MINB : 1)) spmm_csr_kernel(const SpmmArgs a) {
   constexpr int RPW = 32 / G;          // rows per warp
   constexpr int NG = kWarps * RPW;     // groups (= rows) per CTA
   __shared__ float s_part[NG][G * VPL * W];
@@ -650,7 +676,7 @@ int spmm_run(const glnn_spmm_desc& d0, cudaStream_t st) {
   if (rc != 0) return rc;
   const bool vec = q24 || ((d % 4 == 0) && (q.ldx % 4 == 0) && aligned16(q.X));
   GLNN_REQUIRE(!q24 || ((!q.Y || q.log_softmax || (q.ldy % 4 == 0 && aligned16(q.Y))) &&
-                        (!q.Y_hi || q.ldyp % 8 == 0)),
+                        (!q.Y_hi || (q.ldyp % 8 == 0 && aligned16(q.Y_hi) && aligned16(q.Y_lo)))),
                GLNN_ERR_ALIGN, "spmm: q24 input needs 16-byte aligned output rows");
   const bool vec_out = (!q.Y || q.log_softmax || (q.ldy % 4 == 0 && aligned16(q.Y)));
   const int chunk = (vec && vec_out) ? 512 : 128;
