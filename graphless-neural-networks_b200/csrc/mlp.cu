@@ -157,8 +157,10 @@ struct WsLayout {
 };
 static inline int pad8(int d) { return (d + 7) / 8 * 8; }
 static inline int64_t plane_pair_floats(int64_t rows, int width) { return rows * pad8(width); }
+// columns per thread of the column-wise BatchNorm kernels
+static inline int bn_vec(const Dims& d) { return d.H % 4 == 0 ? 4 : 1; }
 static int row_splits(const Dims& d) {
-  const int col_tiles = std::max(1, (d.H + 31) / 32);
+  const int col_tiles = std::max(1, (d.H + 32 * bn_vec(d) - 1) / (32 * bn_vec(d)));
   int rs = (4 * 148 + col_tiles - 1) / col_tiles;
   rs = static_cast<int>(std::min<int64_t>(rs, std::max<int64_t>(1, d.R / 32)));
   return std::max(1, std::min(rs, 64));
@@ -254,49 +256,156 @@ __global__ void __launch_bounds__(256) gather_kernel(const PassParams* __restric
   }
 }
 
+// ---- column-wise BatchNorm kernels -------------------------------------------------------------
+// block (32, 8): a thread owns V adjacent columns (V = 4 when H % 4 == 0: 16-byte loads of the fp32
+// operands, 8-byte stores per bf16 plane; V = 1 otherwise), threadIdx.y strides over the rows of the
+// CTA's row split, four row loads in flight per thread.  All of Z / dA (33.5 MB at bs 4096, H 2048)
+// stays L2-resident between the kernels of a step.
+template <int V>
+struct ColVec {
+  float v[V];
+};
+template <int V>
+__device__ __forceinline__ ColVec<V> ld_cols(const float* __restrict__ p) {
+  ColVec<V> r;
+  if constexpr (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    r.v[0] = t.x; r.v[1] = t.y; r.v[2] = t.z; r.v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) r.v[i] = p[i];
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void store_planes_cols(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                                                  int64_t idx, const ColVec<V>& y) {
+  if constexpr (V == 4) {
+    uint32_t h[2], l[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(y.v[2 * i]), h1 = __float2bfloat16_rn(y.v[2 * i + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(y.v[2 * i] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(y.v[2 * i + 1] - __bfloat162float(h1));
+      h[i] = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&h0)) |
+             (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&h1)) << 16);
+      l[i] = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&l0)) |
+             (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&l1)) << 16);
+    }
+    *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h[0], h[1]);
+    *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l[0], l[1]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < V; ++i) store_planes(hi, lo, idx + i, y.v[i]);
+  }
+}
+// keep/(1-p) factors of V adjacent elements (same per-element stream as keep_scale)
+template <int V>
+__device__ __forceinline__ ColVec<V> keep_scale_cols(const PassParams* pp, int step, int layer, int nlay,
+                                                     int64_t R, int H, int64_t r, int c, float p_drop) {
+  ColVec<V> k;
+  if (p_drop <= 0.f) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) k.v[i] = 1.f;
+    return k;
+  }
+  const float s = 1.f / (1.f - p_drop);
+  if (pp->masks) {
+    const int64_t o = ((static_cast<int64_t>(step) * nlay + layer) * R + r) * H + c;
+    if constexpr (V == 4) {
+      const uint32_t m = *reinterpret_cast<const uint32_t*>(pp->masks + o);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) k.v[i] = ((m >> (8 * i)) & 0xffu) ? s : 0.f;
+    } else {
+#pragma unroll
+      for (int i = 0; i < V; ++i) k.v[i] = pp->masks[o + i] ? s : 0.f;
+    }
+    return k;
+  }
+  const uint64_t base = pp->seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(pp->step0 + step) + 1) +
+                        0xD1B54A32D192ED03ull * (static_cast<uint64_t>(layer) + 1) +
+                        static_cast<uint64_t>(r) * H + c;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    uint64_t x = base + i;
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    k.v[i] = (static_cast<float>(x >> 40) * (1.0f / 16777216.0f)) >= p_drop ? s : 0.f;
+  }
+  return k;
+}
+
 // Column statistics of Z[R,H] over a row split: chunk mean and chunk M2 (two passes over the chunk,
-// which sits in L1/L2), combined later with Chan's formula.  block (32, 8).
+// which sits in L1/L2), combined later with Chan's formula.
+template <int V>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ Z, int64_t R, int H,
                                                        int rs, float* __restrict__ part, const DpDev dp,
                                                        int slot) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[8][32 * V + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c = blockIdx.x * 32 + tx;
+  const int c = (blockIdx.x * 32 + tx) * V;
   const int64_t rows = (R + rs - 1) / rs;
   const int64_t r0 = blockIdx.y * rows, r1 = min(R, r0 + rows);
   const float cnt = static_cast<float>(imax64(r1 - r0, 1));
-  float s = 0.f;
-  if (c < H)
-    for (int64_t r = r0 + ty; r < r1; r += 8) s += Z[r * H + c];
-  sm[ty][tx] = s;
-  __syncthreads();
-  float tot = 0.f;
+  float s[V];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) tot += sm[i][tx];
-  const float mu = tot / cnt;
-  __syncthreads();
-  float q = 0.f;
-  if (c < H)
+  for (int i = 0; i < V; ++i) s[i] = 0.f;
+  if (c < H) {
+#pragma unroll 4
     for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const float dz = Z[r * H + c] - mu;
-      q = fmaf(dz, dz, q);
+      const ColVec<V> z = ld_cols<V>(Z + r * H + c);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s[i] += z.v[i];
     }
-  sm[ty][tx] = q;
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) sm[ty][tx * V + i] = s[i];
+  __syncthreads();
+  float mu[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) tot += sm[j][tx * V + i];
+    mu[i] = tot / cnt;
+  }
+  __syncthreads();
+  float q[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) q[i] = 0.f;
+  if (c < H) {
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const ColVec<V> z = ld_cols<V>(Z + r * H + c);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float dz = z.v[i] - mu[i];
+        q[i] = fmaf(dz, dz, q[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < V; ++i) sm[ty][tx * V + i] = q[i];
   __syncthreads();
   if (ty == 0 && c < H) {
-    float m2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) m2 += sm[i][tx];
-    if (dp.world > 1) {  // this split's partials go to every rank's exchange buffer
-      const int64_t o = ((static_cast<int64_t>(slot) * dp.world + dp.rank) * rs + blockIdx.y) * 2 * H + c;
-      for (int r = 0; r < dp.world; ++r) {
-        float* pr = reinterpret_cast<float*>(dp.base[r] + dp.off_part);
-        pr[o] = mu;
-        pr[o + H] = m2;
+    for (int i = 0; i < V; ++i) {
+      float m2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) m2 += sm[j][tx * V + i];
+      if (dp.world > 1) {  // this split's partials go to every rank's exchange buffer
+        const int64_t o =
+            ((static_cast<int64_t>(slot) * dp.world + dp.rank) * rs + blockIdx.y) * 2 * H + c + i;
+        for (int r = 0; r < dp.world; ++r) {
+          float* pr = reinterpret_cast<float*>(dp.base[r] + dp.off_part);
+          pr[o] = mu[i];
+          pr[o + H] = m2;
+        }
+      } else {
+        part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c + i] = mu[i];
+        part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c + i] = m2;
       }
-    } else {
-      part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c] = mu;
-      part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c] = m2;
     }
   }
   if (dp.world > 1) dp_last_cta_signals(dp, slot, dp_epoch(dp), gridDim.x * gridDim.y);
@@ -305,6 +414,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 // Combines the split statistics, normalises, applies gamma/beta, ReLU and dropout; the first row
 // tile also stores mean / invstd for the backward pass and updates the running statistics
 // (momentum update with the UNBIASED variance, as nn.BatchNorm1d does).  norm == 0: y = z.
+template <int V>
 __global__ void __launch_bounds__(256) bn_apply_kernel(
     const float* __restrict__ Z, uint16_t* __restrict__ A_hi, uint16_t* __restrict__ A_lo, int64_t lda,
     int64_t R, int H, int rs,
@@ -314,96 +424,161 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(
     const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
     int rows_per_block, const DpDev dp, int slot, int64_t Rg) {
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c = blockIdx.x * 32 + tx;
+  const int c = (blockIdx.x * 32 + tx) * V;
   if (dp.world > 1 && norm) {  // statistics of every rank's rows must have arrived
     dp_wait_all(dp, slot, dp_epoch(dp));
     part = reinterpret_cast<const float*>(dp.base[dp.rank] + dp.off_part) +
            static_cast<int64_t>(slot) * dp.world * rs * 2 * H;
   }
-  if (c >= H) return;
-  float mu = 0.f, inv = 1.f, g = 1.f, b = 0.f;
+  const bool active = c < H;
+  float mu[V], inv[V], g[V], b[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { mu[i] = 0.f; inv[i] = 1.f; g[i] = 1.f; b[i] = 0.f; }
   if (norm) {
+    // Chan combination of the split statistics: threadIdx.y = j combines the splits s = j (mod 8) in
+    // ascending order, then all threads combine the 8 partials in the order j = 0..7 -- a fixed tree,
+    // so every CTA (and, data parallel, every rank: s is rank-major) gets identical bits.
+    __shared__ float sn[8], smu[8][32 * V + 1], sq[8][32 * V + 1];
     const int64_t rows = (R + rs - 1) / rs;
-    float n = 0.f, m2 = 0.f;
-    for (int s = 0; s < rs * dp.world; ++s) {  // rank-major: every rank combines in the same order
-      const int sl = s % rs;
-      const float nb = static_cast<float>(imax64(imin64(R, (sl + 1) * rows) - sl * rows, 0));
+    float n = 0.f, m2[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) m2[i] = 0.f;
+    if (active) {
+      for (int s = ty; s < rs * dp.world; s += 8) {
+        const int sl = s % rs;
+        const float nb = static_cast<float>(imax64(imin64(R, (sl + 1) * rows) - sl * rows, 0));
+        if (nb <= 0.f) continue;
+        const ColVec<V> mb = ld_cols<V>(part + (static_cast<int64_t>(s) * 2 + 0) * H + c);
+        const ColVec<V> qb = ld_cols<V>(part + (static_cast<int64_t>(s) * 2 + 1) * H + c);
+        const float tot = n + nb;
+#pragma unroll
+        for (int i = 0; i < V; ++i) {
+          const float delta = mb.v[i] - mu[i];
+          mu[i] += delta * (nb / tot);
+          m2[i] += qb.v[i] + delta * delta * (n * nb / tot);
+        }
+        n = tot;
+      }
+    }
+    if (tx == 0) sn[ty] = n;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { smu[ty][tx * V + i] = mu[i]; sq[ty][tx * V + i] = m2[i]; }
+    __syncthreads();
+    n = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) { mu[i] = 0.f; m2[i] = 0.f; }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float nb = sn[j];
       if (nb <= 0.f) continue;
-      const float mb = part[(static_cast<int64_t>(s) * 2 + 0) * H + c];
-      const float qb = part[(static_cast<int64_t>(s) * 2 + 1) * H + c];
-      const float delta = mb - mu, tot = n + nb;
-      mu += delta * (nb / tot);
-      m2 += qb + delta * delta * (n * nb / tot);
+      const float tot = n + nb;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float delta = smu[j][tx * V + i] - mu[i];
+        mu[i] += delta * (nb / tot);
+        m2[i] += sq[j][tx * V + i] + delta * delta * (n * nb / tot);
+      }
       n = tot;
     }
-    const float var = m2 / static_cast<float>(Rg);
-    inv = 1.f / sqrtf(var + eps);
-    g = gamma[c];
-    b = beta[c];
-    if (blockIdx.y == 0 && ty == 0) {
-      save_mean[c] = mu;
-      save_invstd[c] = inv;
-      const float unb = m2 / static_cast<float>(imax64(Rg - 1, 1));
-      run_mean[c] = (1.f - mom) * run_mean[c] + mom * mu;
-      run_var[c] = (1.f - mom) * run_var[c] + mom * unb;
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float var = m2[i] / static_cast<float>(Rg);
+        inv[i] = 1.f / sqrtf(var + eps);
+        g[i] = gamma[c + i];
+        b[i] = beta[c + i];
+        if (blockIdx.y == 0 && ty == 0) {
+          save_mean[c + i] = mu[i];
+          save_invstd[c + i] = inv[i];
+          const float unb = m2[i] / static_cast<float>(imax64(Rg - 1, 1));
+          run_mean[c + i] = (1.f - mom) * run_mean[c + i] + mom * mu[i];
+          run_var[c + i] = (1.f - mom) * run_var[c + i] + mom * unb;
+        }
+      }
     }
   }
+  if (!active) return;
   const int step = *ctr;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
   const int64_t r1 = min(R, r0 + rows_per_block);
+#pragma unroll 4
   for (int64_t r = r0 + ty; r < r1; r += 8) {
-    const float z = Z[r * H + c];
-    float y = norm ? (z - mu) * inv * g + b : z;
-    y = fmaxf(y, 0.f);
-    store_planes(A_hi, A_lo, r * lda + c,
-                 y * keep_scale(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop));
+    const ColVec<V> z = ld_cols<V>(Z + r * H + c);
+    const ColVec<V> k = keep_scale_cols<V>(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
+    ColVec<V> y;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float t = norm ? (z.v[i] - mu[i]) * inv[i] * g[i] + b[i] : z.v[i];
+      y.v[i] = fmaxf(t, 0.f) * k.v[i];
+    }
+    store_planes_cols<V>(A_hi, A_lo, r * lda + c, y);
   }
 }
 
 // Backward through dropout, ReLU and BatchNorm.  Pass 1: per split  S1 = sum g, S2 = sum g*xhat with
 // g = dA * keep/(1-p) * [y > 0].
+template <int V>
 __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
     const float* __restrict__ dA, const float* __restrict__ Z, int64_t R, int H, int rs,
     const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, int norm, float p_drop,
     const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
     float* __restrict__ part, const DpDev dp, int slot, int64_t Rg) {
-  __shared__ float s1[8][33], s2[8][33];
+  __shared__ float s1[8][32 * V + 1], s2[8][32 * V + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c = blockIdx.x * 32 + tx;
+  const int c = (blockIdx.x * 32 + tx) * V;
   const int64_t rows = (R + rs - 1) / rs;
   const int64_t r0 = blockIdx.y * rows, r1 = min(R, r0 + rows);
-  float a1 = 0.f, a2 = 0.f;
+  float a1[V], a2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { a1[i] = 0.f; a2[i] = 0.f; }
   if (c < H) {
-    const float mu = norm ? save_mean[c] : 0.f, inv = norm ? save_invstd[c] : 1.f;
-    const float g = norm ? gamma[c] : 1.f, b = norm ? beta[c] : 0.f;
+    float mu[V], inv[V], g[V], b[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      mu[i] = norm ? save_mean[c + i] : 0.f;
+      inv[i] = norm ? save_invstd[c + i] : 1.f;
+      g[i] = norm ? gamma[c + i] : 1.f;
+      b[i] = norm ? beta[c + i] : 0.f;
+    }
     const int step = *ctr;
+#pragma unroll 4
     for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const float xh = (Z[r * H + c] - mu) * inv;
-      const float y = norm ? xh * g + b : Z[r * H + c];
-      float gr = dA[r * H + c] * keep_scale(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
-      gr = y > 0.f ? gr : 0.f;
-      a1 += gr;
-      a2 = fmaf(gr, xh, a2);
+      const ColVec<V> z = ld_cols<V>(Z + r * H + c);
+      const ColVec<V> da = ld_cols<V>(dA + r * H + c);
+      const ColVec<V> k = keep_scale_cols<V>(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xh = (z.v[i] - mu[i]) * inv[i];
+        const float y = norm ? xh * g[i] + b[i] : z.v[i];
+        float gr = da.v[i] * k.v[i];
+        gr = y > 0.f ? gr : 0.f;
+        a1[i] += gr;
+        a2[i] = fmaf(gr, xh, a2[i]);
+      }
     }
   }
-  s1[ty][tx] = a1;
-  s2[ty][tx] = a2;
+#pragma unroll
+  for (int i = 0; i < V; ++i) { s1[ty][tx * V + i] = a1[i]; s2[ty][tx * V + i] = a2[i]; }
   __syncthreads();
   if (ty == 0 && c < H) {
-    float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { t1 += s1[i][tx]; t2 += s2[i][tx]; }
-    if (dp.world > 1) {
-      const int64_t o = ((static_cast<int64_t>(slot) * dp.world + dp.rank) * rs + blockIdx.y) * 2 * H + c;
-      for (int r = 0; r < dp.world; ++r) {
-        float* pr = reinterpret_cast<float*>(dp.base[r] + dp.off_part);
-        pr[o] = t1;
-        pr[o + H] = t2;
+    for (int i = 0; i < V; ++i) {
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { t1 += s1[j][tx * V + i]; t2 += s2[j][tx * V + i]; }
+      if (dp.world > 1) {
+        const int64_t o =
+            ((static_cast<int64_t>(slot) * dp.world + dp.rank) * rs + blockIdx.y) * 2 * H + c + i;
+        for (int r = 0; r < dp.world; ++r) {
+          float* pr = reinterpret_cast<float*>(dp.base[r] + dp.off_part);
+          pr[o] = t1;
+          pr[o + H] = t2;
+        }
+      } else {
+        part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c + i] = t1;
+        part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c + i] = t2;
       }
-    } else {
-      part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c] = t1;
-      part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c] = t2;
     }
   }
   if (dp.world > 1) dp_last_cta_signals(dp, slot, dp_epoch(dp), gridDim.x * gridDim.y);
@@ -413,6 +588,7 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
 // dX projections); dgamma = S2,
 // dbeta = S1; the Linear bias gradient is the column sum of dZ (mathematically 0 in front of a
 // BatchNorm; the reference computes it the same way and Adam still sees its rounding noise).
+template <int V>
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const float* __restrict__ dA, uint16_t* __restrict__ dZ_hi, uint16_t* __restrict__ dZ_lo,
     int64_t lddz, const float* __restrict__ Z, int64_t R, int H, int rs,
@@ -421,53 +597,75 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const PassParams* __restrict__ pp, const int* __restrict__ ctr, int layer, int nlay,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias,
     int rows_per_block, const DpDev dp, int slot, int64_t Rg) {
-  __shared__ float sb[8][33];
+  __shared__ float sb[8][32 * V + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int c = blockIdx.x * 32 + tx;
+  const int c = (blockIdx.x * 32 + tx) * V;
   if (dp.world > 1 && norm) {
     dp_wait_all(dp, slot, dp_epoch(dp));
     part = reinterpret_cast<const float*>(dp.base[dp.rank] + dp.off_part) +
            static_cast<int64_t>(slot) * dp.world * rs * 2 * H;
   }
-  float colsum = 0.f;
+  float colsum[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) colsum[i] = 0.f;
   if (c < H) {
-    float S1 = 0.f, S2 = 0.f, mu = 0.f, inv = 1.f, g = 1.f, b = 0.f;
+    float S1[V], S2[V], mu[V], inv[V], g[V], b[V], k[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) { S1[i] = 0.f; S2[i] = 0.f; mu[i] = 0.f; inv[i] = 1.f; g[i] = 1.f; b[i] = 0.f; }
+    const float fR = static_cast<float>(Rg);
     if (norm) {
+#pragma unroll 8
       for (int s = 0; s < rs * dp.world; ++s) {
-        S1 += part[(static_cast<int64_t>(s) * 2 + 0) * H + c];
-        S2 += part[(static_cast<int64_t>(s) * 2 + 1) * H + c];
+        const ColVec<V> p1 = ld_cols<V>(part + (static_cast<int64_t>(s) * 2 + 0) * H + c);
+        const ColVec<V> p2 = ld_cols<V>(part + (static_cast<int64_t>(s) * 2 + 1) * H + c);
+#pragma unroll
+        for (int i = 0; i < V; ++i) { S1[i] += p1.v[i]; S2[i] += p2.v[i]; }
       }
-      mu = save_mean[c]; inv = save_invstd[c]; g = gamma[c]; b = beta[c];
-      // S1 / S2 are already sums over the GLOBAL batch: only rank 0 contributes them to the
-      // gradient reduction
-      if (blockIdx.y == 0 && ty == 0) {
-        dgamma[c] = dp.rank == 0 ? S2 : 0.f;
-        dbeta[c] = dp.rank == 0 ? S1 : 0.f;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        mu[i] = save_mean[c + i]; inv[i] = save_invstd[c + i]; g[i] = gamma[c + i]; b[i] = beta[c + i];
+        // S1 / S2 are already sums over the GLOBAL batch: only rank 0 contributes them to the
+        // gradient reduction
+        if (blockIdx.y == 0 && ty == 0) {
+          dgamma[c + i] = dp.rank == 0 ? S2[i] : 0.f;
+          dbeta[c + i] = dp.rank == 0 ? S1[i] : 0.f;
+        }
       }
     }
-    const float fR = static_cast<float>(Rg);
-    const float k = g * inv / fR;
+#pragma unroll
+    for (int i = 0; i < V; ++i) k[i] = g[i] * inv[i] / fR;
     const int step = *ctr;
     const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
     const int64_t r1 = min(R, r0 + rows_per_block);
+#pragma unroll 4
     for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const float z = Z[r * H + c];
-      const float xh = (z - mu) * inv;
-      const float y = norm ? xh * g + b : z;
-      float gr = dA[r * H + c] * keep_scale(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
-      gr = y > 0.f ? gr : 0.f;
-      const float dz = norm ? k * (fR * gr - S1 - xh * S2) : gr;
-      store_planes(dZ_hi, dZ_lo, r * lddz + c, dz);
-      colsum += dz;
+      const ColVec<V> z = ld_cols<V>(Z + r * H + c);
+      const ColVec<V> da = ld_cols<V>(dA + r * H + c);
+      const ColVec<V> ks = keep_scale_cols<V>(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
+      ColVec<V> dz;
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xh = (z.v[i] - mu[i]) * inv[i];
+        const float y = norm ? xh * g[i] + b[i] : z.v[i];
+        float gr = da.v[i] * ks.v[i];
+        gr = y > 0.f ? gr : 0.f;
+        dz.v[i] = norm ? k[i] * (fR * gr - S1[i] - xh * S2[i]) : gr;
+        colsum[i] += dz.v[i];
+      }
+      store_planes_cols<V>(dZ_hi, dZ_lo, r * lddz + c, dz);
     }
   }
-  sb[ty][tx] = colsum;
+#pragma unroll
+  for (int i = 0; i < V; ++i) sb[ty][tx * V + i] = colsum[i];
   __syncthreads();
   if (ty == 0 && c < H) {
-    float t = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) t += sb[i][tx];
-    atomicAdd(dbias + c, t);
+    for (int i = 0; i < V; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += sb[j][tx * V + i];
+      atomicAdd(dbias + c + i, t);
+    }
   }
 }
 
@@ -667,6 +865,7 @@ struct StepCtx {
 };
 constexpr int kSlotGrads = kSlots - 2, kSlotParams = kSlots - 1;
 
+#define BN_LAUNCH(name) (bv == 4 ? name<4> : name<1>)
 static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   const Dims& d = c.d;
   const int64_t R = d.R;
@@ -677,7 +876,8 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   const int rs = c.wl.rs;
   const int nlay = d.L - 1;
   const dim3 blk(32, 8);
-  const int col_tiles = (d.H + 31) / 32;
+  const int bv = bn_vec(d);
+  const int col_tiles = (d.H + 32 * bv - 1) / (32 * bv);
   const int rows_per_block = static_cast<int>(std::max<int64_t>(32, (R + rs - 1) / rs));
   const int row_tiles = static_cast<int>((R + rows_per_block - 1) / rows_per_block);
   int rc;
@@ -716,10 +916,10 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
     if (rc != 0) return rc;
     if (l == d.L - 1) break;
     if (d.norm) {
-      bn_stats_kernel<<<dim3(col_tiles, rs), blk, 0, st>>>(z, R, d.H, rs, part, dp, l);
+      BN_LAUNCH(bn_stats_kernel)<<<dim3(col_tiles, rs), blk, 0, st>>>(z, R, d.H, rs, part, dp, l);
       GLNN_LAUNCH_OK("bn_stats_kernel");
     }
-    bn_apply_kernel<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
+    BN_LAUNCH(bn_apply_kernel)<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
         z, ap[l].hi, ap[l].lo, ap[l].ld, R, d.H, rs, part,
         d.norm ? c.params + c.pl.gamma[l] : nullptr, d.norm ? c.params + c.pl.beta[l] : nullptr,
         d.norm ? c.bn_stats + 2LL * l * d.H : nullptr,
@@ -754,13 +954,13 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
     const float* gam = d.norm ? c.params + c.pl.gamma[k] : nullptr;
     const float* bet = d.norm ? c.params + c.pl.beta[k] : nullptr;
     if (d.norm) {
-      bn_bwd_stats_kernel<<<dim3(col_tiles, rs), blk, 0, st>>>(
+      BN_LAUNCH(bn_bwd_stats_kernel)<<<dim3(col_tiles, rs), blk, 0, st>>>(
           da, c.ws + c.wl.z[k], R, d.H, rs, gam, bet, c.ws + c.wl.mean[k], c.ws + c.wl.invstd[k],
           d.norm, d.p_drop, pp, ctr, k, nlay, part, dp, nlay + k, d.Rg);
       GLNN_LAUNCH_OK("bn_bwd_stats_kernel");
     }
     GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[k], 0, sizeof(float) * d.H, st));
-    bn_bwd_apply_kernel<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
+    BN_LAUNCH(bn_bwd_apply_kernel)<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
         da, dzp.hi, dzp.lo, dzp.ld, c.ws + c.wl.z[k], R, d.H, rs, part, gam, bet, c.ws + c.wl.mean[k],
         c.ws + c.wl.invstd[k], d.norm, d.p_drop, pp, ctr, k, nlay,
         d.norm ? c.grads + c.pl.gamma[k] : nullptr, d.norm ? c.grads + c.pl.beta[k] : nullptr,

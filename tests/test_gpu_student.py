@@ -207,7 +207,11 @@ def test_student_single_step_gradients(dev, shape, kind):
 @pytest.mark.parametrize("shape", REAL_SHAPES[:3])
 def test_student_real_shapes_vs_oracle(dev, shape, graph_mode):
     """6 NLL + 6 KL steps at arxiv / products layer shapes.  Per-pass losses must match the fp64
-    oracle to 1e-4.  Weights after 12 Adam steps cannot be held to 1e-4 by ANY implementation: the
+    oracle to 3e-4: from the second step on the loss inherits the trajectory noise described below
+    -- the ORACLE's own fp32 run deviates from its fp64 run by up to 1.1e-4 on single steps of these
+    passes (measured: MLP3w8/256 KL step 5), and split-K / bias-gradient atomics make the B200 run
+    differ from itself at that level between graph replay and direct launches; the first step of a
+    pass (identical state) is held to 1e-4 by test_student_single_step_gradients.  Weights after 12 Adam steps cannot be held to 1e-4 by ANY implementation: the
     dynamics (batch statistics, ReLU masks, Adam's g/sqrt(v)) amplify rounding noise ~1e4x -- the
     ORACLE's own fp32 run deviates from its fp64 run by ~0.6 % (99th percentile, printed below) --
     so the trajectory check is a loose sanity bound; exact parity lives in the single-step gradient
@@ -236,7 +240,7 @@ def test_student_real_shapes_vs_oracle(dev, shape, graph_mode):
             got[0] += mlp_engine.train_pass(model.encoder, opt, fd, ld, idx1[i:i + 1].to(dev), 0.3).item() / nb
         for i in range(nb):
             got[1] += mlp_engine.train_pass(model.encoder, opt, fd, td, idx2[i:i + 1].to(dev), 0.7).item() / nb
-    assert np.allclose(got, runs[torch.float64][1], rtol=TOL)
+    assert np.allclose(got, runs[torch.float64][1], rtol=3e-4)
     sd = {k[len("encoder."):]: v.detach().cpu() for k, v in model.state_dict().items()}
     for k in ("layers.0.weight", "layers.1.weight", "layers.2.weight", "layers.2.bias",
               "norms.0.weight", "norms.1.bias", "norms.0.running_var", "norms.1.running_var"):
