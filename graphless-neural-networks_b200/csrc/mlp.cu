@@ -161,7 +161,7 @@ static inline int64_t plane_pair_floats(int64_t rows, int width) { return rows *
 static inline int bn_vec(const Dims& d) { return d.H % 4 == 0 ? 4 : 1; }
 static int row_splits(const Dims& d) {
   const int col_tiles = std::max(1, (d.H + 32 * bn_vec(d) - 1) / (32 * bn_vec(d)));
-  int rs = (4 * 148 + col_tiles - 1) / col_tiles;
+  int rs = std::max(1, 2 * 148 / col_tiles);  // one wave of 2 resident CTAs per SM (B200: 148 SMs)
   rs = static_cast<int>(std::min<int64_t>(rs, std::max<int64_t>(1, d.R / 32)));
   return std::max(1, std::min(rs, 64));
 }
@@ -218,24 +218,6 @@ __device__ __forceinline__ void store_planes(uint16_t* __restrict__ hi, uint16_t
   lo[idx] = *reinterpret_cast<const uint16_t*>(&l);
 }
 
-__device__ __forceinline__ float keep_scale(const PassParams* pp, int step, int layer, int nlay,
-                                            int64_t R, int H, int64_t r, int c, float p_drop) {
-  if (p_drop <= 0.f) return 1.f;
-  bool keep;
-  if (pp->masks) {
-    keep = pp->masks[((static_cast<int64_t>(step) * nlay + layer) * R + r) * H + c] != 0;
-  } else {  // counter-based stream: splitmix64 of (seed, step, layer, element)
-    uint64_t x = pp->seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(pp->step0 + step) + 1) +
-                 0xD1B54A32D192ED03ull * (static_cast<uint64_t>(layer) + 1) +
-                 static_cast<uint64_t>(r) * H + c;
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27; x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    keep = (static_cast<float>(x >> 40) * (1.0f / 16777216.0f)) >= p_drop;
-  }
-  return keep ? 1.f / (1.f - p_drop) : 0.f;
-}
-
 __global__ void __launch_bounds__(256) gather_kernel(const PassParams* __restrict__ pp,
                                                      const int* __restrict__ ctr, int64_t R,
                                                      int64_t Rg, int64_t row0, int F,
@@ -284,13 +266,11 @@ __device__ __forceinline__ void store_planes_cols(uint16_t* __restrict__ hi, uin
     uint32_t h[2], l[2];
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(y.v[2 * i]), h1 = __float2bfloat16_rn(y.v[2 * i + 1]);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(y.v[2 * i] - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(y.v[2 * i + 1] - __bfloat162float(h1));
-      h[i] = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&h0)) |
-             (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&h1)) << 16);
-      l[i] = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&l0)) |
-             (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&l1)) << 16);
+      const __nv_bfloat162 hh = __floats2bfloat162_rn(y.v[2 * i], y.v[2 * i + 1]);
+      h[i] = *reinterpret_cast<const uint32_t*>(&hh);
+      const float f0 = __uint_as_float(h[i] << 16), f1 = __uint_as_float(h[i] & 0xffff0000u);
+      const __nv_bfloat162 ll = __floats2bfloat162_rn(y.v[2 * i] - f0, y.v[2 * i + 1] - f1);
+      l[i] = *reinterpret_cast<const uint32_t*>(&ll);
     }
     *reinterpret_cast<uint2*>(hi + idx) = make_uint2(h[0], h[1]);
     *reinterpret_cast<uint2*>(lo + idx) = make_uint2(l[0], l[1]);
@@ -299,111 +279,173 @@ __device__ __forceinline__ void store_planes_cols(uint16_t* __restrict__ hi, uin
     for (int i = 0; i < V; ++i) store_planes(hi, lo, idx + i, y.v[i]);
   }
 }
-// keep/(1-p) factors of V adjacent elements (same per-element stream as keep_scale)
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return x;
+}
+// Dropout of one (step, layer): everything that does not change along a thread's row loop is read
+// ONCE (the PassParams fields live in global memory; re-reading them per row put a dependent load
+// and a branch between the row loads and serialised them).
+struct DropCtx {
+  const uint8_t* masks;  // host-injected keep masks of this (step, layer), row 0; null -> device stream
+  uint64_t key;          // device stream: (seed, step, layer)
+  float p, scale;        // p <= 0: no dropout
+  uint32_t thr;          // device stream: drop when the element's 16 random bits are < thr
+};
+__device__ __forceinline__ DropCtx drop_ctx(const PassParams* __restrict__ pp, int step, int layer,
+                                            int nlay, int64_t Rg, int H, float p_drop) {
+  DropCtx d;
+  d.p = p_drop;
+  d.scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+  d.masks = nullptr;
+  d.key = 0;
+  d.thr = static_cast<uint32_t>(ceilf(fminf(fmaxf(p_drop, 0.f), 1.f) * 65536.f));
+  if (p_drop > 0.f) {
+    const uint8_t* m = pp->masks;
+    if (m) d.masks = m + (static_cast<int64_t>(step) * nlay + layer) * Rg * H;
+    d.key = pp->seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(pp->step0 + step) + 1) +
+            0xD1B54A32D192ED03ull * (static_cast<uint64_t>(layer) + 1);
+  }
+  return d;
+}
+// keep/(1-p) factors of V adjacent elements of global row r (the decision of an element does not
+// depend on V).  mword: the V mask bytes of the elements, preloaded by the caller in mask mode.
 template <int V>
-__device__ __forceinline__ ColVec<V> keep_scale_cols(const PassParams* pp, int step, int layer, int nlay,
-                                                     int64_t R, int H, int64_t r, int c, float p_drop) {
+__device__ __forceinline__ ColVec<V> keep_cols(const DropCtx& d, int H, int64_t r, int c, uint32_t mword) {
   ColVec<V> k;
-  if (p_drop <= 0.f) {
+  if (d.p <= 0.f) {
 #pragma unroll
     for (int i = 0; i < V; ++i) k.v[i] = 1.f;
     return k;
   }
-  const float s = 1.f / (1.f - p_drop);
-  if (pp->masks) {
-    const int64_t o = ((static_cast<int64_t>(step) * nlay + layer) * R + r) * H + c;
-    if constexpr (V == 4) {
-      const uint32_t m = *reinterpret_cast<const uint32_t*>(pp->masks + o);
+  if (d.masks) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) k.v[i] = ((m >> (8 * i)) & 0xffu) ? s : 0.f;
-    } else {
-#pragma unroll
-      for (int i = 0; i < V; ++i) k.v[i] = pp->masks[o + i] ? s : 0.f;
-    }
+    for (int i = 0; i < V; ++i) k.v[i] = ((mword >> (8 * i)) & 0xffu) ? d.scale : 0.f;
     return k;
   }
-  const uint64_t base = pp->seed + 0x9E3779B97F4A7C15ull * (static_cast<uint64_t>(pp->step0 + step) + 1) +
-                        0xD1B54A32D192ED03ull * (static_cast<uint64_t>(layer) + 1) +
-                        static_cast<uint64_t>(r) * H + c;
+  // counter-based stream: one splitmix64 per aligned GROUP OF FOUR adjacent elements, 16 bits each,
+  // compared as integers against thr = ceil(p * 2^16) (keep probability exact to 2^-16), keyed by
+  // (seed, step, layer, group index)
+  const uint64_t e0 = static_cast<uint64_t>(r) * H + c;
+  if constexpr (V == 4) {  // c and H multiples of 4: one whole group
+    const uint64_t x = splitmix64(d.key + (e0 >> 2));
+    const uint32_t lo = static_cast<uint32_t>(x), hi = static_cast<uint32_t>(x >> 32);
+    k.v[0] = (lo & 0xffffu) >= d.thr ? d.scale : 0.f;
+    k.v[1] = (lo >> 16) >= d.thr ? d.scale : 0.f;
+    k.v[2] = (hi & 0xffffu) >= d.thr ? d.scale : 0.f;
+    k.v[3] = (hi >> 16) >= d.thr ? d.scale : 0.f;
+  } else {
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    uint64_t x = base + i;
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-    x ^= x >> 27; x *= 0x94D049BB133111EBull;
-    x ^= x >> 31;
-    k.v[i] = (static_cast<float>(x >> 40) * (1.0f / 16777216.0f)) >= p_drop ? s : 0.f;
+    for (int i = 0; i < V; ++i) {
+      const uint64_t e = e0 + i;
+      const uint64_t x = splitmix64(d.key + (e >> 2));
+      const uint32_t u = static_cast<uint32_t>(x >> (16 * (e & 3))) & 0xffffu;
+      k.v[i] = u >= d.thr ? d.scale : 0.f;
+    }
   }
   return k;
 }
-
-// Column statistics of Z[R,H] over a row split: chunk mean and chunk M2 (two passes over the chunk,
-// which sits in L1/L2), combined later with Chan's formula.
 template <int V>
-__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ Z, int64_t R, int H,
+__device__ __forceinline__ uint32_t ld_mask(const DropCtx& d, int H, int64_t r, int c) {
+  if constexpr (V == 4) return *reinterpret_cast<const uint32_t*>(d.masks + r * H + c);
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < V; ++i) m |= static_cast<uint32_t>(d.masks[r * H + c + i]) << (8 * i);
+  return m;
+}
+
+// Row loop of the column-wise kernels: threadIdx.y strides over rows [r0, r1); UB rows are LOADED
+// first (A, optionally B, optionally the mask bytes: UB or 2 UB independent 16-byte loads in flight
+// per thread) and only then handed to f(local row, a, b, keep) -- written out explicitly because the
+// compiler does not move loads across the per-row dropout code.
+template <int V, int UB, bool HAS_B, bool DROP, class F>
+__device__ __forceinline__ void for_rows(const float* __restrict__ A, const float* __restrict__ B, int H,
+                                         int c, int64_t r0, int64_t r1, int ty, const DropCtx& dc,
+                                         int64_t grow0, F&& f) {
+  for (int64_t rb = r0 + ty; rb < r1; rb += 8 * UB) {
+    ColVec<V> a[UB], b[UB];
+    uint32_t m[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int64_t r = rb + 8 * u;
+      m[u] = 0;
+      if (r < r1) {
+        a[u] = ld_cols<V>(A + r * H + c);
+        if constexpr (HAS_B) b[u] = ld_cols<V>(B + r * H + c);
+        if constexpr (DROP) {
+          if (dc.masks) m[u] = ld_mask<V>(dc, H, grow0 + r, c);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int64_t r = rb + 8 * u;
+      if (r < r1) {
+        ColVec<V> k;
+        if constexpr (DROP) {
+          k = keep_cols<V>(dc, H, grow0 + r, c, m[u]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) k.v[i] = 1.f;
+        }
+        f(r, a[u], b[u], k);
+      }
+    }
+  }
+}
+
+// Column statistics of Z[R,H] over a row split: chunk mean and chunk M2 in ONE pass with the chunk's
+// first row as the shift K (sum (z-K), sum (z-K)^2: no cancellation, K is a sample of the column),
+// combined later with Chan's formula.
+template <int V>
+__global__ void __launch_bounds__(256, 2) bn_stats_kernel(const float* __restrict__ Z, int64_t R, int H,
                                                        int rs, float* __restrict__ part, const DpDev dp,
                                                        int slot) {
-  __shared__ float sm[8][32 * V + 1];
+  __shared__ float s1[8][32 * V + 1], s2[8][32 * V + 1];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = (blockIdx.x * 32 + tx) * V;
   const int64_t rows = (R + rs - 1) / rs;
   const int64_t r0 = blockIdx.y * rows, r1 = min(R, r0 + rows);
   const float cnt = static_cast<float>(imax64(r1 - r0, 1));
-  float s[V];
+  float s[V], q[V];
+  ColVec<V> K;
 #pragma unroll
-  for (int i = 0; i < V; ++i) s[i] = 0.f;
-  if (c < H) {
-#pragma unroll 4
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const ColVec<V> z = ld_cols<V>(Z + r * H + c);
+  for (int i = 0; i < V; ++i) { s[i] = 0.f; q[i] = 0.f; K.v[i] = 0.f; }
+  if (c < H && r0 < r1) {
+    K = ld_cols<V>(Z + r0 * H + c);
+    for_rows<V, 8, false, false>(Z, nullptr, H, c, r0, r1, ty, DropCtx{}, 0,
+                                 [&](int64_t, const ColVec<V>& z, const ColVec<V>&, const ColVec<V>&) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) s[i] += z.v[i];
-    }
+                                   for (int i = 0; i < V; ++i) {
+                                     const float dz = z.v[i] - K.v[i];
+                                     s[i] += dz;
+                                     q[i] = fmaf(dz, dz, q[i]);
+                                   }
+                                 });
   }
 #pragma unroll
-  for (int i = 0; i < V; ++i) sm[ty][tx * V + i] = s[i];
-  __syncthreads();
-  float mu[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) {
-    float tot = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) tot += sm[j][tx * V + i];
-    mu[i] = tot / cnt;
-  }
-  __syncthreads();
-  float q[V];
-#pragma unroll
-  for (int i = 0; i < V; ++i) q[i] = 0.f;
-  if (c < H) {
-#pragma unroll 4
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const ColVec<V> z = ld_cols<V>(Z + r * H + c);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float dz = z.v[i] - mu[i];
-        q[i] = fmaf(dz, dz, q[i]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < V; ++i) sm[ty][tx * V + i] = q[i];
+  for (int i = 0; i < V; ++i) { s1[ty][tx * V + i] = s[i]; s2[ty][tx * V + i] = q[i]; }
   __syncthreads();
   if (ty == 0 && c < H) {
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      float m2 = 0.f;
+      float S = 0.f, Q = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) m2 += sm[j][tx * V + i];
+      for (int j = 0; j < 8; ++j) { S += s1[j][tx * V + i]; Q += s2[j][tx * V + i]; }
+      const float mu = K.v[i] + S / cnt;
+      const float m2 = fmaxf(Q - S * (S / cnt), 0.f);
       if (dp.world > 1) {  // this split's partials go to every rank's exchange buffer
         const int64_t o =
             ((static_cast<int64_t>(slot) * dp.world + dp.rank) * rs + blockIdx.y) * 2 * H + c + i;
         for (int r = 0; r < dp.world; ++r) {
           float* pr = reinterpret_cast<float*>(dp.base[r] + dp.off_part);
-          pr[o] = mu[i];
+          pr[o] = mu;
           pr[o + H] = m2;
         }
       } else {
-        part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c + i] = mu[i];
+        part[(static_cast<int64_t>(blockIdx.y) * 2 + 0) * H + c + i] = mu;
         part[(static_cast<int64_t>(blockIdx.y) * 2 + 1) * H + c + i] = m2;
       }
     }
@@ -415,7 +457,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 // tile also stores mean / invstd for the backward pass and updates the running statistics
 // (momentum update with the UNBIASED variance, as nn.BatchNorm1d does).  norm == 0: y = z.
 template <int V>
-__global__ void __launch_bounds__(256) bn_apply_kernel(
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(
     const float* __restrict__ Z, uint16_t* __restrict__ A_hi, uint16_t* __restrict__ A_lo, int64_t lda,
     int64_t R, int H, int rs,
     const float* __restrict__ part, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -501,24 +543,23 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(
   const int step = *ctr;
   const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
   const int64_t r1 = min(R, r0 + rows_per_block);
-#pragma unroll 4
-  for (int64_t r = r0 + ty; r < r1; r += 8) {
-    const ColVec<V> z = ld_cols<V>(Z + r * H + c);
-    const ColVec<V> k = keep_scale_cols<V>(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
-    ColVec<V> y;
+  const DropCtx dc = drop_ctx(pp, step, layer, nlay, Rg, H, p_drop);
+  for_rows<V, 4, false, true>(Z, nullptr, H, c, r0, r1, ty, dc, dp.rank * R,
+                              [&](int64_t r, const ColVec<V>& z, const ColVec<V>&, const ColVec<V>& k) {
+                                ColVec<V> y;
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float t = norm ? (z.v[i] - mu[i]) * inv[i] * g[i] + b[i] : z.v[i];
-      y.v[i] = fmaxf(t, 0.f) * k.v[i];
-    }
-    store_planes_cols<V>(A_hi, A_lo, r * lda + c, y);
-  }
+                                for (int i = 0; i < V; ++i) {
+                                  const float t = norm ? (z.v[i] - mu[i]) * inv[i] * g[i] + b[i] : z.v[i];
+                                  y.v[i] = fmaxf(t, 0.f) * k.v[i];
+                                }
+                                store_planes_cols<V>(A_hi, A_lo, r * lda + c, y);
+                              });
 }
 
 // Backward through dropout, ReLU and BatchNorm.  Pass 1: per split  S1 = sum g, S2 = sum g*xhat with
 // g = dA * keep/(1-p) * [y > 0].
 template <int V>
-__global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
+__global__ void __launch_bounds__(256, 2) bn_bwd_stats_kernel(
     const float* __restrict__ dA, const float* __restrict__ Z, int64_t R, int H, int rs,
     const float* __restrict__ gamma, const float* __restrict__ beta,
     const float* __restrict__ save_mean, const float* __restrict__ save_invstd, int norm, float p_drop,
@@ -542,21 +583,19 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
       b[i] = norm ? beta[c + i] : 0.f;
     }
     const int step = *ctr;
-#pragma unroll 4
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const ColVec<V> z = ld_cols<V>(Z + r * H + c);
-      const ColVec<V> da = ld_cols<V>(dA + r * H + c);
-      const ColVec<V> k = keep_scale_cols<V>(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
+    const DropCtx dc = drop_ctx(pp, step, layer, nlay, Rg, H, p_drop);
+    for_rows<V, 4, true, true>(Z, dA, H, c, r0, r1, ty, dc, dp.rank * R,
+                               [&](int64_t, const ColVec<V>& z, const ColVec<V>& da, const ColVec<V>& k) {
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float xh = (z.v[i] - mu[i]) * inv[i];
-        const float y = norm ? xh * g[i] + b[i] : z.v[i];
-        float gr = da.v[i] * k.v[i];
-        gr = y > 0.f ? gr : 0.f;
-        a1[i] += gr;
-        a2[i] = fmaf(gr, xh, a2[i]);
-      }
-    }
+                                 for (int i = 0; i < V; ++i) {
+                                   const float xh = (z.v[i] - mu[i]) * inv[i];
+                                   const float y = norm ? xh * g[i] + b[i] : z.v[i];
+                                   float gr = da.v[i] * k.v[i];
+                                   gr = y > 0.f ? gr : 0.f;
+                                   a1[i] += gr;
+                                   a2[i] = fmaf(gr, xh, a2[i]);
+                                 }
+                               });
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) { s1[ty][tx * V + i] = a1[i]; s2[ty][tx * V + i] = a2[i]; }
@@ -589,7 +628,7 @@ __global__ void __launch_bounds__(256) bn_bwd_stats_kernel(
 // dbeta = S1; the Linear bias gradient is the column sum of dZ (mathematically 0 in front of a
 // BatchNorm; the reference computes it the same way and Adam still sees its rounding noise).
 template <int V>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(
     const float* __restrict__ dA, uint16_t* __restrict__ dZ_hi, uint16_t* __restrict__ dZ_lo,
     int64_t lddz, const float* __restrict__ Z, int64_t R, int H, int rs,
     const float* __restrict__ part, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -637,23 +676,21 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(
     const int step = *ctr;
     const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
     const int64_t r1 = min(R, r0 + rows_per_block);
-#pragma unroll 4
-    for (int64_t r = r0 + ty; r < r1; r += 8) {
-      const ColVec<V> z = ld_cols<V>(Z + r * H + c);
-      const ColVec<V> da = ld_cols<V>(dA + r * H + c);
-      const ColVec<V> ks = keep_scale_cols<V>(pp, step, layer, nlay, Rg, H, dp.rank * R + r, c, p_drop);
-      ColVec<V> dz;
+    const DropCtx dc = drop_ctx(pp, step, layer, nlay, Rg, H, p_drop);
+    for_rows<V, 4, true, true>(Z, dA, H, c, r0, r1, ty, dc, dp.rank * R,
+                               [&](int64_t r, const ColVec<V>& z, const ColVec<V>& da, const ColVec<V>& ks) {
+                                 ColVec<V> dz;
 #pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float xh = (z.v[i] - mu[i]) * inv[i];
-        const float y = norm ? xh * g[i] + b[i] : z.v[i];
-        float gr = da.v[i] * ks.v[i];
-        gr = y > 0.f ? gr : 0.f;
-        dz.v[i] = norm ? k[i] * (fR * gr - S1[i] - xh * S2[i]) : gr;
-        colsum[i] += dz.v[i];
-      }
-      store_planes_cols<V>(dZ_hi, dZ_lo, r * lddz + c, dz);
-    }
+                                 for (int i = 0; i < V; ++i) {
+                                   const float xh = (z.v[i] - mu[i]) * inv[i];
+                                   const float y = norm ? xh * g[i] + b[i] : z.v[i];
+                                   float gr = da.v[i] * ks.v[i];
+                                   gr = y > 0.f ? gr : 0.f;
+                                   dz.v[i] = norm ? k[i] * (fR * gr - S1[i] - xh * S2[i]) : gr;
+                                   colsum[i] += dz.v[i];
+                                 }
+                                 store_planes_cols<V>(dZ_hi, dZ_lo, r * lddz + c, dz);
+                               });
   }
 #pragma unroll
   for (int i = 0; i < V; ++i) sb[ty][tx * V + i] = colsum[i];
@@ -878,7 +915,10 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   const dim3 blk(32, 8);
   const int bv = bn_vec(d);
   const int col_tiles = (d.H + 32 * bv - 1) / (32 * bv);
-  const int rows_per_block = static_cast<int>(std::max<int64_t>(32, (R + rs - 1) / rs));
+  // the apply kernels run as ONE wave of 2 resident CTAs per SM (their register budget), each CTA
+  // looping over its rows: a second partial wave cost more than the longer loop
+  const int64_t want_tiles = std::max<int64_t>(1, std::min<int64_t>(2LL * 148 / col_tiles, R / 32));
+  const int rows_per_block = static_cast<int>((R + want_tiles - 1) / want_tiles);
   const int row_tiles = static_cast<int>((R + rows_per_block - 1) / rows_per_block);
   int rc;
 
