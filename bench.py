@@ -576,28 +576,20 @@ def run_b200(args):
             pipe.drain()
         h2d = h_indptr.numel() * h_indptr.element_size() + h_indices.numel() * 4 + h_feats.numel() * 4
     else:
+        # every rank uploads its CSR slice and its OWN feature rows (1/G of the features; the input
+        # replica is assembled over NVLink) and downloads its rows of the output
+        from glnn_b200.pipeline import HostShardedTeacherPipeline
         h_ptr, h_idx = sg.indptr.cpu().pin_memory(), sg.indices.cpu().pin_memory()
-        h_feats = feats_pad.cpu().pin_memory()
-        d_ptr, d_idx, d_feats = torch.empty_like(sg.indptr), torch.empty_like(sg.indices), \
-            torch.empty_like(feats_pad)
-        h_out = torch.empty(sg.rows, dims[3]).pin_memory()
-        d_out_rows = torch.empty(sg.rows, dims[3], device=dev)
-        my_rows = sg.pad_ids[sg.r0:sg.r0 + sg.rows]
+        h_feats = feats[sg.r0:sg.r0 + sg.rows].cpu().pin_memory()
+        h_outs = [torch.empty(sg.rows, dims[3]).pin_memory() for _ in range(2)]
+        h_out = h_outs[0]
+        pipe = HostShardedTeacherPipeline(sg, layers, norms, dims[0], dims[3], dev)
 
         def e2e_step():
-            d_ptr.copy_(h_ptr, non_blocking=True)
-            d_idx.copy_(h_idx, non_blocking=True)
-            d_feats.copy_(h_feats, non_blocking=True)
-            keep = (sg.indptr, sg.indices)
-            sg.indptr, sg.indices = d_ptr, d_idx
-            with torch.no_grad():
-                o = DT.sage_forward_sharded(sg, d_feats, layers, norms, gather_output=False)
-            sg.indptr, sg.indices = keep
-            torch.index_select(o, 0, my_rows, out=d_out_rows)   # this rank's rows, local order
-            h_out.copy_(d_out_rows, non_blocking=True)
+            pipe.submit(h_ptr, h_idx, h_feats, h_outs[pipe.step % 2])
 
         def e2e_drain():
-            pass
+            pipe.drain()
         h2d = h_ptr.numel() * h_ptr.element_size() + h_idx.numel() * 4 + h_feats.numel() * 4
     e2e_step()
     e2e_drain()
@@ -609,10 +601,14 @@ def run_b200(args):
     ev1.record()
     barrier()
     e2e_ms = ev0.elapsed_time(ev1) / args.steps
+    d2h = h_out.numel() * 4
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t)
+        io = torch.tensor([h2d, d2h], device=dev, dtype=torch.int64)   # whole job: sum over ranks
+        dist.all_reduce(io)
+        h2d, d2h = int(io[0]), int(io[1])
     clk = clocks.stop() if rank == 0 else {}
     student = None
     if world > 1:
@@ -639,9 +635,12 @@ def run_b200(args):
                    "l2": "inputs (features 0.98 GB, CSR 0.5 GB, activations 2.5 GB) far exceed the "
                          "126 MB L2; no flush needed"},
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "nodes/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(h_out.numel() * 4),
-                "overlap": ("copy streams: step i+1 upload / step i-1 download overlap step i compute "
-                            "(2 device input slots)") if world == 1 else "none (serial per step)"},
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "overlap": "copy streams: step i+1 upload / step i-1 download overlap step i compute "
+                           "(2 device input slots)" + ("" if world == 1 else
+                           "; every rank uploads its CSR slice + its own feature rows and downloads "
+                           "its rows of the output, the input replica is exchanged over NVLink; "
+                           "bytes are summed over ranks")},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk,
     }
@@ -662,9 +661,9 @@ def run_b200(args):
         line["roofline"] = {
             "bound": "hbm", "kernel": "spmm_csr_kernel / " + dom[0], "achieved": achieved,
             "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": _ncu_traffic("r1_spmm_d256.raw.csv"),
-            "traffic_source": "profiles/r1_spmm_d256.raw.csv (ncu --set full, same kernel, d=256, "
-                              "same graph generator)",
+            "traffic": _ncu_traffic("r1h_spmm_q24_d256.raw.csv"),
+            "traffic_source": "profiles/r1h_spmm_q24_d256.raw.csv (ncu --set full, same kernel and "
+                              "operand format: q24 768 B rows, d=256, same graph generator)",
             "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[2],
             "gather_bytes_per_launch": gather_bytes, "gather_GBps": gather_gbps,
             "gather_frac_of_peak": gather_gbps / hbm_peak,

@@ -169,9 +169,12 @@ class _Exchange:
 
 
 def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None, log_softmax=True,
-                         timings=None, gather_output=True):
+                         timings=None, gather_output=True, feats_local=None):
     """layers: [(W [out,in], b)], norms: [(scale, shift)] folded eval-BN per hidden layer (or []).
-    feats_pad: padded replica (sg.to_padded) of the input features, valid on every rank.  Returns
+    feats_pad: padded replica (sg.to_padded) of the input features, valid on every rank -- OR None
+    with feats_local = this rank's OWN feature rows [sg.rows, d_in] (local order): the replica of the
+    input is then assembled by the same chunked exchange as every other layer (each rank quantises
+    its rows, NVLink all-gather), so a host only ships 1/G of the features to each GPU.  Returns
     the padded replica [total_rows, label_dim] of the output (log-probabilities when log_softmax);
     the returned tensor is a cached buffer that the next call overwrites.  With gather_output=False
     the result stays sharded: only this rank's rows of it are valid (sg.local_rows_of) -- what a
@@ -185,17 +188,22 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
     k = kernels or ops
     cuda = hasattr(k, "Q24")           # the real kernels: q24 replicas, planes operands
     world = sg.world
-    dev = feats_pad.device
+    if (feats_pad is None) == (feats_local is None):
+        raise ValueError("sage_forward_sharded: give exactly one of feats_pad / feats_local")
+    feats_any = feats_pad if feats_pad is not None else feats_local
+    if feats_local is not None and feats_local.shape[0] != sg.rows:
+        raise ValueError(f"feats_local has {feats_local.shape[0]} rows, this shard owns {sg.rows}")
+    dev = feats_any.device
     L = len(layers)
     C = sg.chunks
 
     def mark(name):
-        if timings is not None and feats_pad.is_cuda:
+        if timings is not None and feats_any.is_cuda:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             timings.append((name, ev))
 
-    xch = _Exchange(sg, group, feats_pad.is_cuda, mark)
+    xch = _Exchange(sg, group, feats_any.is_cuda, mark)
     mark("start")
 
     def proj_first(i):
@@ -257,8 +265,22 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
     # ---- layer loop
     h_rep, h_op = None, None   # replica (gather input) / operand (projection input) of the current h
     if not proj_first(0):
-        if cuda:
-            h_rep = new_replica(("xq",), layers[0][0].shape[1])
+        d0 = layers[0][0].shape[1]
+        if feats_local is not None:  # own rows -> gather format, chunk-wise exchange of the replica
+            h_rep = new_replica(("xq",), d0)
+            for c in range(C):
+                a, e = sg.chunk_rows(c)
+                s0 = sg.slab_start(c)
+                if e > a:
+                    if cuda:
+                        k.quantize_q24(feats_local[a:e], out=k.Q24(h_rep.data[s0:s0 + e - a], d0))
+                    else:
+                        h_rep[s0:s0 + e - a] = feats_local[a:e, :d0]
+                xch.chunk(replica_2d(h_rep), c)
+            mark("features fp32 -> q24 (own rows)")
+            xch.wait(f"exchange features ({d0} wide)")
+        elif cuda:
+            h_rep = new_replica(("xq",), d0)
             k.quantize_q24(feats_pad, out=h_rep)
             mark("features fp32 -> q24")
         else:
@@ -278,7 +300,8 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
             z_rep = new_replica(("z", l), dpad)
             if h_op is None:  # first layer: the owned rows of the input features
                 h_op = new_operand(("x_op",), d_in)
-                mine = sg.local_rows_of(feats_pad)[:, :d_in].contiguous()
+                mine = (feats_local if feats_local is not None
+                        else sg.local_rows_of(feats_pad))[:, :d_in].contiguous()
                 if cuda:
                     h_op = k.split_planes(mine)
                 else:

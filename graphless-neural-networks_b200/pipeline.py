@@ -54,3 +54,64 @@ class HostTeacherPipeline:
         for s in self.slots:
             cur.wait_event(s["downloaded"])
             cur.wait_event(s["computed"])
+
+
+class HostShardedTeacherPipeline:
+    """The same host-facing path for the dst-row sharded forward (one instance per rank): every step
+    uploads THIS rank's CSR slice and THIS rank's feature rows (1/G of the features -- the input
+    replica is assembled over NVLink by sage_forward_sharded(feats_local=...)), runs the sharded
+    forward and downloads this rank's rows of the log-probabilities.  Uploads / downloads of
+    neighbouring steps overlap with compute exactly as in HostTeacherPipeline."""
+
+    def __init__(self, sg, layers, norms, feat_dim, label_dim, device, group=None, depth=2):
+        self.sg, self.layers, self.norms, self.group = sg, layers, norms, group
+        self.dev, self.depth, self.step = device, depth, 0
+        self.h2d, self.d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        self.slots = []
+        for _ in range(depth):
+            self.slots.append(dict(
+                indptr=torch.empty_like(sg.indptr), indices=torch.empty_like(sg.indices),
+                feats=torch.empty(sg.rows, feat_dim, dtype=torch.float32, device=device),
+                out=torch.empty(sg.rows, label_dim, dtype=torch.float32, device=device),
+                uploaded=torch.cuda.Event(), computed=torch.cuda.Event(), downloaded=torch.cuda.Event()))
+
+    def submit(self, h_indptr, h_indices, h_feats, h_out):
+        """h_*: pinned host tensors (this rank's relabelled CSR slice, its feature rows [rows, F]);
+        h_out: pinned [rows, C].  Returns immediately; drain() before reading h_out."""
+        from . import dist_teacher as DT
+        sg, s = self.sg, self.slots[self.step % self.depth]
+        cur = torch.cuda.current_stream(self.dev)
+        if self.step >= self.depth:
+            self.h2d.wait_event(s["computed"])   # the slot's previous forward has consumed its inputs
+            cur.wait_event(s["downloaded"])      # ... and its output rows have left the device
+        with torch.cuda.stream(self.h2d):
+            s["indptr"].copy_(h_indptr, non_blocking=True)
+            s["indices"].copy_(h_indices, non_blocking=True)
+            s["feats"].copy_(h_feats, non_blocking=True)
+            s["uploaded"].record(self.h2d)
+        cur.wait_event(s["uploaded"])
+        keep = (sg.indptr, sg.indices)
+        sg.indptr, sg.indices = s["indptr"], s["indices"]
+        try:
+            with torch.no_grad():
+                out = DT.sage_forward_sharded(sg, None, self.layers, self.norms, group=self.group,
+                                              gather_output=False, feats_local=s["feats"])
+        finally:
+            sg.indptr, sg.indices = keep
+        for c in range(sg.chunks):   # this rank's rows of the padded output, back in local order
+            a, e = sg.chunk_rows(c)
+            if e > a:
+                s0 = sg.slab_start(c)
+                s["out"][a:e].copy_(out[s0:s0 + e - a], non_blocking=True)
+        s["computed"].record(cur)
+        self.d2h.wait_event(s["computed"])
+        with torch.cuda.stream(self.d2h):
+            h_out.copy_(s["out"], non_blocking=True)
+            s["downloaded"].record(self.d2h)
+        self.step += 1
+
+    def drain(self):
+        cur = torch.cuda.current_stream(self.dev)
+        for s in self.slots:
+            cur.wait_event(s["downloaded"])
+            cur.wait_event(s["computed"])

@@ -27,7 +27,7 @@ def _problem():
     return n, src, dst, layers, norms, x
 
 
-def _worker(rank, world, port, q, chunks=1):
+def _worker(rank, world, port, q, chunks=1, local_feats=False):
     for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
     import warnings
@@ -39,15 +39,20 @@ def _worker(rank, world, port, q, chunks=1):
     n, src, dst, layers, norms, x = _problem()
     g = graph((src, dst), num_nodes=n)
     sg = DT.ShardedGraph(g, rank, world, chunks=chunks)
-    out = DT.sage_forward_sharded(sg, sg.to_padded(x), layers, norms, kernels=TorchKernels)
+    if local_feats:  # every rank ships only its own rows; the input replica is exchanged too
+        out = DT.sage_forward_sharded(sg, None, layers, norms, kernels=TorchKernels,
+                                      feats_local=x[sg.r0:sg.r0 + sg.rows].contiguous())
+    else:
+        out = DT.sage_forward_sharded(sg, sg.to_padded(x), layers, norms, kernels=TorchKernels)
     assert sg.total_rows == world * sg.rc * chunks and sg.rows_max == sg.rc * chunks
     q.put((rank, sg.from_padded(out).numpy(), sg.cuts))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,chunks", [(2, 1), (3, 1), (2, 3), (3, 4)])
-def test_sharded_forward_equals_single_process(world, chunks):
+@pytest.mark.parametrize("world,chunks,local_feats", [(2, 1, False), (3, 1, False), (2, 3, False),
+                                                      (3, 4, False), (2, 3, True), (3, 1, True)])
+def test_sharded_forward_equals_single_process(world, chunks, local_feats):
     import glnn_oracle as O
     n, src, dst, layers, norms, x = _problem()
     indptr, indices = O.csr_from_edges(src, dst, n)
@@ -55,8 +60,9 @@ def test_sharded_forward_equals_single_process(world, chunks):
     want = torch.log_softmax(O.sage_inference(indptr, indices, x, layers, bn), 1).numpy()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + world + 7 * chunks + (os.getpid() % 400)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, chunks)) for r in range(world)]
+    port = 29500 + world + 7 * chunks + 31 * int(local_feats) + (os.getpid() % 400)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, chunks, local_feats))
+             for r in range(world)]
     for p in procs:
         p.start()
     results = [q.get(timeout=120) for _ in range(world)]

@@ -44,7 +44,20 @@ def _worker(rank, world, port, q, chunks):
         o2 = DT.sage_forward_sharded(sg, sg.to_padded(feats), layers, norms, gather_output=False)
     mine = sg.local_rows_of(o2)
     err2 = float((mine - ref[sg.r0:sg.r0 + sg.rows]).abs().max() / ref.abs().max())
-    q.put((rank, max(err, err2)))
+    # host-facing sharded pipeline: every rank uploads its CSR slice + its OWN feature rows (the
+    # input replica is exchanged over NVLink) and downloads its rows; two steps through both slots
+    from glnn_b200.pipeline import HostShardedTeacherPipeline
+    pipe = HostShardedTeacherPipeline(sg, layers, norms, 100, 47, dev)
+    h_ptr, h_idx = sg.indptr.cpu().pin_memory(), sg.indices.cpu().pin_memory()
+    h_feats = feats[sg.r0:sg.r0 + sg.rows].cpu().pin_memory()
+    h_outs = [torch.empty(sg.rows, 47).pin_memory() for _ in range(3)]
+    for h in h_outs:
+        pipe.submit(h_ptr, h_idx, h_feats, h)
+    pipe.drain()
+    torch.cuda.synchronize()
+    want = ref[sg.r0:sg.r0 + sg.rows].cpu()
+    err3 = max(float((h - want).abs().max() / ref.abs().max()) for h in h_outs)
+    q.put((rank, max(err, err2, err3)))
     dist.barrier()
     dist.destroy_process_group()
 
