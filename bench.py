@@ -181,6 +181,11 @@ def run_reference(args):
     warnings.filterwarnings("ignore")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import glnn_oracle as O
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
     workload = args.workload
     s, src, dst = _cpu_problem(workload)
     n = s["n"]
@@ -207,7 +212,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -551,8 +556,8 @@ def run_b200(args):
     if args.light:
         if rank == 0:
             clocks.stop()
-            print(json.dumps({"metric": METRIC, "value": n / (ms * 1e-3), "unit": "nodes/s",
-                              "n_gpus": world, "ms_per_step": ms, "light": True}), flush=True)
+            _emit({"metric": METRIC, "value": n / (ms * 1e-3), "unit": "nodes/s",
+                   "n_gpus": world, "ms_per_step": ms, "light": True})
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
@@ -696,13 +701,32 @@ def run_b200(args):
             line["other_configs"] = other_configs(dev, torch, hbm_peak)
         except Exception as ex:
             line["other_configs"] = {"error": repr(ex)}
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def _emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    # stdout carries exactly one JSON line: anything a library prints there (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, torchrun notices) is sent to stderr instead
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

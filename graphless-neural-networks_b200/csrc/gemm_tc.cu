@@ -179,8 +179,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
   const int nkb = SPLIT ? min(nkb_total, kb0 + g.kb_per_split) - kb0 : nkb_total;
 
   if (tid == 0) {
+    // one arrival per producer WARP (lane 0 after __syncwarp): 512 per-thread arrivals on one
+    // mbarrier serialise on its shared-memory word
     for (int s = 0; s < S::STAGES; ++s) {
-      mbar_init(&full[s], NPROD);
+      mbar_init(&full[s], NPWARPS);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum, 1);
@@ -205,7 +207,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
         if (i >= S::STAGES - 1) {  // the oldest stage in flight has landed: hand it to the MMA warp
           cp_async_wait<S::STAGES - 2>();
           fence_proxy_async();
-          mbar_arrive(&full[(i - (S::STAGES - 1)) % S::STAGES]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[(i - (S::STAGES - 1)) % S::STAGES]);
         }
         const int s = i % S::STAGES, it = i / S::STAGES;
         if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
@@ -218,7 +221,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
       }
       cp_async_wait<0>();
       fence_proxy_async();
-      for (int i = max(0, nkb - (S::STAGES - 1)); i < nkb; ++i) mbar_arrive(&full[i % S::STAGES]);
+      __syncwarp();
+      if (lane == 0)
+        for (int i = max(0, nkb - (S::STAGES - 1)); i < nkb; ++i) mbar_arrive(&full[i % S::STAGES]);
     } else {
     TileIO<BM, A_K> ta;
     TileIO<BN, B_K> tb;
@@ -238,7 +243,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_bf16x3_kernel(const GemmArgs
         tb.load(g.B, g.ldb, n0, g.N, k0 + BK, g.K, tid);
       }
       fence_proxy_async();
-      mbar_arrive(&full[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
     }
     }
   } else if (lane == 0) {
