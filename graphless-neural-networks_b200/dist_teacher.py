@@ -136,13 +136,45 @@ def _cached(sg, key, make):
     return t
 
 
+def _push_mode():
+    """Exchange transport on CUDA: "push" (default) = every rank copies its slab straight into the
+    peers' replicas through peer-mapped symmetric memory (copy engines over NVLink: no SMs, no
+    staging, so it overlaps the aggregation kernels that fill every SM); "nccl" = all-gather."""
+    import os
+    return os.environ.get("GLNN_EXCHANGE", "push").lower() != "nccl"
+
+
+def _symm_replica(sg, key, rows, row_bytes, dev, group):
+    """uint8 [rows, row_bytes] replica allocated in symmetric memory (cached per shard): returns
+    (tensor, handle).  Collective: every rank reaches the same allocation in the same order."""
+    cache = sg.__dict__.setdefault("_bufs", {})
+    hit = cache.get(("symm",) + key)
+    if hit is None:
+        import torch.distributed._symmetric_memory as symm
+        flat = symm.empty(rows * row_bytes, dtype=torch.uint8, device=dev)
+        hdl = symm.rendezvous(flat, group or dist.group.WORLD)
+        flat.zero_()
+        data = flat.view(rows, row_bytes)
+        peers = {r: hdl.get_buffer(r, (rows, row_bytes), torch.uint8) for r in range(sg.world)
+                 if r != sg.rank}
+        torch.cuda.synchronize(dev)
+        hdl.barrier(channel=0)   # nobody pushes into a replica that is still being zeroed
+        hit = (data, hdl, peers)
+        cache[("symm",) + key] = hit
+        sg.__dict__.setdefault("_symm_by_ptr", {})[data.data_ptr()] = hit
+    return hit
+
+
 class _Exchange:
-    """Chunk-wise in-place all-gather of a replica buffer on a side stream, so that the exchange of
-    chunk c overlaps the computation of chunk c + 1 (CUDA); synchronous on CPU / gloo."""
+    """Chunk-wise in-place exchange of a replica buffer on a side stream, so that the exchange of
+    chunk c overlaps the computation of chunk c + 1 (CUDA); synchronous on CPU / gloo.  Replicas that
+    live in symmetric memory are exchanged by peer copies + one device-side barrier per layer, all
+    other buffers by NCCL all-gather."""
 
     def __init__(self, sg, group, cuda, mark):
         self.sg, self.group, self.cuda, self.mark = sg, group, cuda, mark
         self.stream = None
+        self.pending = None   # symmetric-memory handle whose pushes still need their barrier
         if cuda and sg.world > 1:
             self.stream = _cached(sg, ("comm_stream",), torch.cuda.Stream)
 
@@ -152,18 +184,31 @@ class _Exchange:
             return
         lo = c * sg.world * sg.rc
         whole = buf2d[lo: lo + sg.world * sg.rc]
-        mine = buf2d[sg.slab_start(c): sg.slab_start(c) + sg.rc]
+        s0 = sg.slab_start(c)
+        mine = buf2d[s0: s0 + sg.rc]
         if self.stream is None:
             dist.all_gather_into_tensor(whole, mine, group=self.group)
             return
         ev = torch.cuda.Event()
         ev.record()
         self.stream.wait_event(ev)
+        symm_hit = sg.__dict__.get("_symm_by_ptr", {}).get(buf2d.data_ptr())
         with torch.cuda.stream(self.stream):
-            dist.all_gather_into_tensor(whole, mine, group=self.group)
+            if symm_hit is None:
+                dist.all_gather_into_tensor(whole, mine, group=self.group)
+            else:
+                _, hdl, peers = symm_hit
+                for i in range(1, sg.world):   # staggered start: rank r first writes to r+1
+                    peer = (sg.rank + i) % sg.world
+                    peers[peer][s0: s0 + sg.rc].copy_(mine, non_blocking=True)
+                self.pending = hdl
 
     def wait(self, what):
         if self.stream is not None:
+            if self.pending is not None:   # every rank's pushes of this layer have landed
+                with torch.cuda.stream(self.stream):
+                    self.pending.barrier(channel=0)
+                self.pending = None
             torch.cuda.current_stream().wait_stream(self.stream)
         self.mark(what)
 
@@ -213,6 +258,9 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
 
     # ---- format helpers: a "replica" is what a gather reads, an "operand" what a projection reads
     def new_replica(key, d):
+        if cuda and world > 1 and _push_mode():
+            data, _, _ = _symm_replica(sg, key, sg.total_rows, k.Q24.row_bytes(d), dev, group)
+            return k.Q24(data, d)
         if cuda:
             return _cached(sg, key, lambda: k.Q24.empty(sg.total_rows, d, dev, zero=True))
         return _cached(sg, key, lambda: torch.zeros(sg.total_rows, d, dtype=torch.float32, device=dev))
