@@ -176,7 +176,16 @@ class _Exchange:
         self.stream = None
         self.pending = None   # symmetric-memory handle whose pushes still need their barrier
         if cuda and sg.world > 1:
-            self.stream = _cached(sg, ("comm_stream",), torch.cuda.Stream)
+            # high-priority side streams: whatever the driver uses for the transfer (copy engine, a
+            # copy kernel, NCCL's kernels) should not queue behind the aggregation grid that keeps
+            # every SM full.  Measured at N=4: neither priority nor one stream per peer changes the
+            # exposed exchange (~2 ms of a 1.4 GB-per-rank transfer): the transfer does not speed up
+            # beyond ~700 GB/s per rank while the HBM-saturating gather runs (profiles/r1i_bench_n4.json)
+            self.stream = _cached(sg, ("comm_stream",), lambda: torch.cuda.Stream(priority=-1))
+            # one stream per peer: the G-1 peer copies of a chunk run concurrently
+            self.peer_streams = _cached(sg, ("peer_streams",),
+                                        lambda: [torch.cuda.Stream(priority=-1)
+                                                 for _ in range(sg.world - 1)])
 
     def chunk(self, buf2d, c):
         sg = self.sg
@@ -191,21 +200,26 @@ class _Exchange:
             return
         ev = torch.cuda.Event()
         ev.record()
-        self.stream.wait_event(ev)
         symm_hit = sg.__dict__.get("_symm_by_ptr", {}).get(buf2d.data_ptr())
-        with torch.cuda.stream(self.stream):
-            if symm_hit is None:
+        if symm_hit is None:
+            self.stream.wait_event(ev)
+            with torch.cuda.stream(self.stream):
                 dist.all_gather_into_tensor(whole, mine, group=self.group)
-            else:
-                _, hdl, peers = symm_hit
-                for i in range(1, sg.world):   # staggered start: rank r first writes to r+1
-                    peer = (sg.rank + i) % sg.world
-                    peers[peer][s0: s0 + sg.rc].copy_(mine, non_blocking=True)
-                self.pending = hdl
+            return
+        _, hdl, peers = symm_hit
+        for i in range(1, sg.world):   # staggered targets: rank r's stream i writes to rank r+i
+            peer = (sg.rank + i) % sg.world
+            st = self.peer_streams[i - 1]
+            st.wait_event(ev)
+            with torch.cuda.stream(st):
+                peers[peer][s0: s0 + sg.rc].copy_(mine, non_blocking=True)
+        self.pending = hdl
 
     def wait(self, what):
         if self.stream is not None:
             if self.pending is not None:   # every rank's pushes of this layer have landed
+                for st in self.peer_streams:
+                    self.stream.wait_stream(st)
                 with torch.cuda.stream(self.stream):
                     self.pending.barrier(channel=0)
                 self.pending = None
