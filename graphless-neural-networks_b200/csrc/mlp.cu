@@ -903,7 +903,26 @@ struct StepCtx {
 constexpr int kSlotGrads = kSlots - 2, kSlotParams = kSlots - 1;
 
 #define BN_LAUNCH(name) (bv == 4 ? name<4> : name<1>)
+// Side stream + fork / join events of the calling thread (weight-gradient GEMMs run beside the
+// activation-gradient chain; works identically under stream capture and in direct launches).
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool ok = false;
+};
+static SideStream& side_stream() {
+  static thread_local SideStream s;
+  static const bool disabled = getenv("GLNN_MLP_NO_FORK") != nullptr;
+  if (!s.stream && !disabled) {
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) == cudaSuccess &&
+        cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) == cudaSuccess &&
+        cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) == cudaSuccess)
+      s.ok = true;
+  }
+  return s;
+}
 static int enqueue_step(const StepCtx& c, cudaStream_t st) {
+  SideStream& side = side_stream();
   const Dims& d = c.d;
   const int64_t R = d.R;
   const PassParams* pp = reinterpret_cast<const PassParams*>(c.ws + c.wl.pp);
@@ -981,10 +1000,19 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   for (int l = d.L - 1; l >= 0; --l) {
     const int din = in_dim(d, l), dout = out_dim(d, l);
     const PlaneRef& hin = (l == 0) ? xb : ap[l - 1];
-    // dW_l [dout, din] = dz^T [dout, R] * hin [R, din]   (both operands MN-major)
+    // dW_l [dout, din] = dz^T [dout, R] * hin [R, din]   (both operands MN-major).  Nothing on the
+    // way down to the input depends on it, so for l > 0 it runs on a forked side stream next to
+    // dA_{l-1} and the BatchNorm-backward statistics (it fills the SMs their partial waves leave
+    // idle) and is joined before bn_bwd_apply overwrites the dz planes it reads.
+    const bool forked = l > 0 && side.ok;
+    if (forked) {
+      GLNN_CUDA_OK(cudaEventRecord(side.fork, st));
+      GLNN_CUDA_OK(cudaStreamWaitEvent(side.stream, side.fork, 0));
+    }
     rc = gemm_p(*dz, 1, hin, 0, c.grads + c.pl.w[l], din, nullptr, dout, din, R, nullptr, nullptr,
-                nullptr, 0, st);
+                nullptr, 0, forked ? side.stream : st);
     if (rc != 0) return rc;
+    if (forked) GLNN_CUDA_OK(cudaEventRecord(side.join, side.stream));
     if (l == 0) break;
     // dA_{l-1} [R, din] = dz [R, dout] * W_l [dout, din]  (W as MN-major B operand)
     float* da = c.ws + c.wl.dh[l & 1];
@@ -1000,6 +1028,7 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
       GLNN_LAUNCH_OK("bn_bwd_stats_kernel");
     }
     GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[k], 0, sizeof(float) * d.H, st));
+    if (forked) GLNN_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0));
     BN_LAUNCH(bn_bwd_apply_kernel)<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
         da, dzp.hi, dzp.lo, dzp.ld, c.ws + c.wl.z[k], R, d.H, rs, part, gam, bet, c.ws + c.wl.mean[k],
         c.ws + c.wl.invstd[k], d.norm, d.p_drop, pp, ctr, k, nlay,
