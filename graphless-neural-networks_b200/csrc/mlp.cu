@@ -950,20 +950,30 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
     dp_wait_kernel<<<1, 32, 0, st>>>(dp, kSlotParams);
     GLNN_LAUNCH_OK("dp_wait_kernel");
   }
+  // Top of the step, two independent branches: the side stream turns the weights into planes (they
+  // changed in the previous Adam update, or were loaded from a state_dict between passes) and zeroes
+  // the bias-gradient accumulators while the main stream gathers the batch.
   PlaneRef wp[16], ap[16];
+  cudaStream_t ws_st = st;
+  if (side.ok) {
+    GLNN_CUDA_OK(cudaEventRecord(side.fork, st));
+    GLNN_CUDA_OK(cudaStreamWaitEvent(side.stream, side.fork, 0));
+    ws_st = side.stream;
+  }
   for (int l = 0; l < d.L; ++l) {
     wp[l] = plane_ref(c.ws, c.wl.wP[l], out_dim(d, l), in_dim(d, l));
     if (l < d.L - 1) ap[l] = plane_ref(c.ws, c.wl.aP[l], R, d.H);
-    // weights -> planes at the top of every step (they changed in the previous Adam update, or were
-    // loaded from a state_dict between passes)
     rc = split_planes(c.params + c.pl.w[l], in_dim(d, l), out_dim(d, l), in_dim(d, l), wp[l].hi,
-                      wp[l].lo, wp[l].ld, st);
+                      wp[l].lo, wp[l].ld, ws_st);
     if (rc != 0) return rc;
+    GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[l], 0, sizeof(float) * out_dim(d, l), ws_st));
   }
+  if (side.ok) GLNN_CUDA_OK(cudaEventRecord(side.join, side.stream));
 
   gather_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, st>>>(pp, ctr, R, d.Rg, d.rank * R, d.F,
                                                                     d.C, xb.hi, xb.lo, xb.ld, tgt);
   GLNN_LAUNCH_OK("gather_kernel");
+  if (side.ok) GLNN_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0));
 
   // forward
   const PlaneRef* h = &xb;
@@ -990,7 +1000,6 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
   }
 
   // loss + dlogits (+ last bias grad)
-  GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[d.L - 1], 0, sizeof(float) * d.C, st));
   loss_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, sizeof(float) * (d.C + 8), st>>>(
       c.ws + c.wl.logits, tgt, R, d.Rg, d.C, pp, dlog.hi, dlog.lo, dlog.ld, c.grads + c.pl.b[d.L - 1]);
   GLNN_LAUNCH_OK("loss_kernel");
@@ -1027,7 +1036,6 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
           d.norm, d.p_drop, pp, ctr, k, nlay, part, dp, nlay + k, d.Rg);
       GLNN_LAUNCH_OK("bn_bwd_stats_kernel");
     }
-    GLNN_CUDA_OK(cudaMemsetAsync(c.grads + c.pl.b[k], 0, sizeof(float) * d.H, st));
     if (forked) GLNN_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0));
     BN_LAUNCH(bn_bwd_apply_kernel)<<<dim3(col_tiles, row_tiles), blk, 0, st>>>(
         da, dzp.hi, dzp.lo, dzp.ld, c.ws + c.wl.z[k], R, d.H, rs, part, gam, bet, c.ws + c.wl.mean[k],
