@@ -47,8 +47,11 @@ def _ncu_traffic(name):
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        d = json.load(open(p))
-        return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), float(d["bf16_tflops"]), "measured (MEASURED_PEAKS.json)"
+        except (KeyError, TypeError, ValueError):   # unreadable / other schema: say so, do not crash
+            return 6650.0, 1590.0, "fallback (B200_PROFILING.md; MEASURED_PEAKS.json unreadable)"
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
