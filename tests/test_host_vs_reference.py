@@ -1,0 +1,256 @@
+"""CPU: the host-side helpers around the hot path (split helpers of
+the inductive runners, YAML config merge, evaluator, min-cut loss) against the REFERENCE'S OWN
+functions, imported unmodified from /root/reference over oracle/dgl_shim.  The reference tree only
+exists in the authoring container; elsewhere the comparisons that need it are skipped and the
+formula-level checks (restated from the cited lines) still run."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+
+@pytest.fixture(scope="module")
+def ref_utils():
+    if not os.path.isdir(REF):
+        pytest.skip("reference tree only exists in the authoring container")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import dgl_shim
+    dgl_shim.install()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_utils_for_tests", os.path.join(REF, "utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("n_train,n_val,n_test,rate,seed", [(140, 210, 2135, 0.2, 0), (8, 2, 90, 0.5, 3),
+                                                            (5, 5, 1, 0.2, 1), (100, 50, 1000, 0.9, 7)])
+def test_split_helpers_match_reference(ref_utils, n_train, n_val, n_test, rate, seed):
+    """idx_split / graph_split (utils.py:88-127): same seeded randperm, same cut, same obs_* ranges."""
+    from glnn_b200 import utils as U
+    perm = torch.randperm(n_train + n_val + n_test, generator=torch.Generator().manual_seed(seed + 11))
+    tr, va, te = perm[:n_train], perm[n_train:n_train + n_val], perm[n_train + n_val:]
+    want = ref_utils.graph_split(tr, va, te, rate, seed)
+    got = U.graph_split(tr, va, te, rate, seed)
+    assert len(got) == len(want) == 5
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
+    a, b = U.idx_split(te, rate, seed)
+    wa, wb = ref_utils.idx_split(te, rate, seed)
+    assert torch.equal(a, wa) and torch.equal(b, wb)
+    # the hidden part is int(n * rate) nodes and the two parts partition the test set
+    assert a.numel() == int(n_test * rate)
+    assert torch.equal(torch.cat([a, b]).sort().values, te.sort().values)
+
+
+def test_training_config_matches_reference_for_every_entry(ref_utils):
+    """train.conf.yaml is the reference's table and get_training_config merges it the same way
+    (utils.py:29-41) for every (dataset, model) pair, including the entries that are empty."""
+    import yaml
+    from glnn_b200 import utils as U
+    ours, theirs = os.path.join(ROOT, "train.conf.yaml"), os.path.join(REF, "train.conf.yaml")
+    full_o = yaml.load(open(ours), Loader=yaml.FullLoader)
+    full_r = yaml.load(open(theirs), Loader=yaml.FullLoader)
+    assert full_o == full_r
+    pairs = [(d, m) for d, models in full_r.items() if d != "global" for m in models]
+    assert len(pairs) > 30
+    for d, m in pairs:
+        assert U.get_training_config(ours, m, d) == ref_utils.get_training_config(theirs, m, d), (d, m)
+    with pytest.raises(KeyError):
+        U.get_training_config(ours, "MLP", "no-such-dataset")
+
+
+def test_evaluator_matches_reference(ref_utils):
+    from glnn_b200 import utils as U
+    gen = torch.Generator().manual_seed(0)
+    out = torch.randn(500, 7, generator=gen)
+    labels = torch.randint(0, 7, (500,), generator=gen)
+    for ds in ("cora", "ogbn-arxiv", "ogbn-products"):
+        assert U.get_evaluator(ds)(out, labels) == ref_utils.get_evaluator(ds)(out, labels)
+
+
+def test_min_cut_loss_equals_the_dense_formula():
+    """compute_min_cut_loss (utils.py:159-168): trace(S^T A S) / trace(S^T D S) with S = exp(out),
+    A the dense adjacency WITH multiplicities, D = diag(in-degree).  The reference densifies A; the
+    sparse restatement here must give the same number (multi-edges, self-loops, isolated nodes)."""
+    from glnn_b200 import utils as U
+    from glnn_b200.graph import graph
+    rng = np.random.default_rng(0)
+    n = 60
+    src = np.concatenate([rng.integers(0, n - 3, 400), np.arange(10), [5, 5, 5]])
+    dst = np.concatenate([rng.integers(0, n - 3, 400), np.arange(10), [9, 9, 9]])   # loops, triple edge
+    g = graph((torch.from_numpy(src), torch.from_numpy(dst)), num_nodes=n)
+    out = torch.log_softmax(torch.randn(n, 5, generator=torch.Generator().manual_seed(1)), 1)
+    S = out.double().exp()
+    A = torch.zeros(n, n, dtype=torch.float64)
+    for s, d in zip(src, dst):
+        A[d, s] += 1.0          # DGL adj(): row = destination, column = source
+    D = torch.diag(A.sum(1))    # in-degrees
+    want = ((S.t() @ A @ S).trace() / (S.t() @ D @ S).trace()).item()
+    got = U.compute_min_cut_loss(g, out)
+    assert abs(got - want) < 1e-12 * abs(want)
+    # orientation does not matter for the trace (A and A^T give the same numerator)
+    assert abs((S.t() @ A.t() @ S).trace().item() - (S.t() @ A @ S).trace().item()) < 1e-9
+
+
+@pytest.fixture(scope="module")
+def ref_modules(ref_utils):
+    """The reference's models.py / train_and_eval.py, imported unmodified over the DGL shim."""
+    import importlib
+    sys.path.insert(0, REF)
+    try:
+        mods = importlib.import_module("models"), importlib.import_module("train_and_eval")
+    finally:
+        sys.path.remove(REF)
+    return mods
+
+
+class _NullLogger:
+    def debug(self, *a, **k): pass
+    def info(self, *a, **k): pass
+
+
+@pytest.mark.parametrize("norm,patience,lamb", [("none", 3, 0.3), ("batch", 2, 0.0), ("none", 50, 1.0)])
+def test_distill_epoch_loop_matches_reference(ref_modules, norm, patience, lamb):
+    """a11: distill_run_transductive (train_and_eval.py:520-606) -- two passes per epoch, three
+    evaluations, early stopping on `score_val >= best`, restore of the best state, final evaluation
+    over all nodes -- run by the REFERENCE and by this repo's runner from the same seed on CPU (the
+    runner's generic autograd loop: CPU tensors never take the fused path).  Same RNG calls in the
+    same order => the epoch history, the scores, the returned log-probabilities and the restored
+    parameters must agree to fp32 rounding."""
+    import copy
+    import warnings
+    ref_models, ref_te = ref_modules
+    from glnn_b200 import train_and_eval as TE
+    from glnn_b200.models import Model
+    from glnn_b200.utils import get_evaluator, set_seed
+    gen = torch.Generator().manual_seed(4)
+    n, f, c = 300, 12, 4
+    feats = torch.randn(n, f, generator=gen)
+    labels = (feats[:, :c] + 0.5 * torch.randn(n, c, generator=gen)).argmax(1)
+    out_t = torch.log_softmax(2.0 * feats[:, :c] + 0.3 * torch.randn(n, c, generator=gen), 1)
+    perm = torch.randperm(n, generator=gen)
+    idx_l, idx_val, idx_test = perm[:90], perm[90:150], perm[150:]
+    idx_t = torch.cat([idx_l, idx_val, idx_test])
+    conf = dict(seed=2, device="cpu", batch_size=32, lamb=lamb, patience=patience, max_epoch=12,
+                eval_interval=1, model_name="MLP", num_layers=2, feat_dim=f, hidden_dim=16,
+                label_dim=c, dropout_ratio=0.0, norm_type=norm, learning_rate=0.01, weight_decay=5e-4)
+
+    def run(model_cls, runner, evaluator):
+        set_seed(conf["seed"])
+        model = model_cls(conf)
+        opt = torch.optim.Adam(model.parameters(), lr=conf["learning_rate"],
+                               weight_decay=conf["weight_decay"])
+        hist = []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out, s_val, s_test = runner(conf, model, feats, labels, out_t, (idx_l, idx_t, idx_val, idx_test),
+                                        torch.nn.NLLLoss(), torch.nn.KLDivLoss(reduction="batchmean",
+                                                                               log_target=True),
+                                        evaluator, opt, _NullLogger(), hist)
+        return out.detach(), s_val, s_test, hist, copy.deepcopy(model.state_dict())
+
+    want = run(ref_models.Model, ref_te.distill_run_transductive, get_evaluator("cora"))
+    got = run(Model, TE.distill_run_transductive, get_evaluator("cora"))
+    assert len(got[3]) == len(want[3]) and len(want[3]) >= 2      # same number of epochs run
+    assert np.allclose(np.array(got[3]), np.array(want[3]), rtol=1e-5, atol=1e-6)
+    assert abs(got[1] - want[1]) < 1e-6 and abs(got[2] - want[2]) < 1e-6
+    assert torch.allclose(got[0], want[0], rtol=1e-5, atol=1e-6)
+    assert set(got[4]) == set(want[4])
+    for k, v in want[4].items():
+        assert torch.allclose(got[4][k].float(), v.float(), rtol=1e-5, atol=1e-6), k
+
+
+@pytest.mark.parametrize("norm,lamb", [("none", 0.5), ("batch", 0.0)])
+def test_distill_inductive_epoch_loop_matches_reference(ref_utils, ref_modules, norm, lamb):
+    """distill_run_inductive (train_and_eval.py:609-742) with the reference's graph_split indices:
+    observed-subgraph training, four evaluation sets, `out[idx_obs] = obs_out` merge."""
+    import copy
+    import warnings
+    ref_models, ref_te = ref_modules
+    from glnn_b200 import train_and_eval as TE
+    from glnn_b200.models import Model
+    from glnn_b200.utils import get_evaluator, graph_split, set_seed
+    gen = torch.Generator().manual_seed(8)
+    n, f, c = 260, 10, 3
+    feats = torch.randn(n, f, generator=gen)
+    labels = (feats[:, :c] + 0.5 * torch.randn(n, c, generator=gen)).argmax(1)
+    out_t = torch.log_softmax(2.0 * feats[:, :c] + 0.3 * torch.randn(n, c, generator=gen), 1)
+    perm = torch.randperm(n, generator=gen)
+    idx_train, idx_val, idx_test = perm[:60], perm[60:110], perm[110:]
+    obs_tr, obs_val, obs_test, idx_obs, idx_test_ind = graph_split(idx_train, idx_val, idx_test, 0.2, 5)
+    want_split = ref_utils.graph_split(idx_train, idx_val, idx_test, 0.2, 5)
+    assert all(torch.equal(a, b) for a, b in zip((obs_tr, obs_val, obs_test, idx_obs, idx_test_ind), want_split))
+    obs_idx_l = obs_tr
+    obs_idx_t = torch.cat([obs_tr, obs_val, obs_test])      # train_student.py: soft labels on all observed
+    indices = (obs_idx_l, obs_idx_t, obs_val, obs_test, idx_obs, idx_test_ind)
+    conf = dict(seed=1, device="cpu", batch_size=32, lamb=lamb, patience=3, max_epoch=8,
+                eval_interval=1, model_name="MLP", num_layers=3, feat_dim=f, hidden_dim=16,
+                label_dim=c, dropout_ratio=0.0, norm_type=norm, learning_rate=0.01, weight_decay=0.0)
+
+    def run(model_cls, runner):
+        set_seed(conf["seed"])
+        model = model_cls(conf)
+        opt = torch.optim.Adam(model.parameters(), lr=conf["learning_rate"])
+        hist = []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = runner(conf, model, feats, labels, out_t, indices, torch.nn.NLLLoss(),
+                         torch.nn.KLDivLoss(reduction="batchmean", log_target=True),
+                         get_evaluator("cora"), opt, _NullLogger(), hist)
+        return res, hist, copy.deepcopy(model.state_dict())
+
+    (w_out, *w_scores), w_hist, w_sd = run(ref_models.Model, ref_te.distill_run_inductive)
+    (g_out, *g_scores), g_hist, g_sd = run(Model, TE.distill_run_inductive)
+    assert len(g_hist) == len(w_hist) >= 2 and len(g_hist[0]) == len(w_hist[0]) == 9
+    assert np.allclose(np.array(g_hist), np.array(w_hist), rtol=1e-5, atol=1e-6)
+    assert np.allclose(g_scores, w_scores, atol=1e-6) and len(w_scores) == 3
+    assert torch.allclose(g_out.detach(), w_out.detach(), rtol=1e-5, atol=1e-6)
+    for k, v in w_sd.items():
+        assert torch.allclose(g_sd[k].float(), v.float(), rtol=1e-5, atol=1e-6), k
+
+
+def test_run_transductive_mlp_teacher_matches_reference(ref_modules):
+    """run_transductive (train_and_eval.py:144-287) on the MLP branch (`--teacher MLP`): mini-batch
+    passes, three evaluations per epoch, early stopping, final evaluate over all nodes."""
+    import copy
+    import warnings
+    ref_models, ref_te = ref_modules
+    from glnn_b200 import train_and_eval as TE
+    from glnn_b200.models import Model
+    from glnn_b200.utils import get_evaluator, set_seed
+    gen = torch.Generator().manual_seed(21)
+    n, f, c = 240, 9, 3
+    feats = torch.randn(n, f, generator=gen)
+    labels = (feats[:, :c] + 0.7 * torch.randn(n, c, generator=gen)).argmax(1)
+    perm = torch.randperm(n, generator=gen)
+    indices = (perm[:80], perm[80:140], perm[140:])
+    conf = dict(seed=0, device="cpu", batch_size=16, patience=2, max_epoch=10, eval_interval=1,
+                model_name="MLP", num_layers=2, feat_dim=f, hidden_dim=12, label_dim=c,
+                dropout_ratio=0.0, norm_type="none", learning_rate=0.01, weight_decay=1e-3,
+                fan_out="5,5", num_workers=0)
+
+    def run(model_cls, runner):
+        set_seed(conf["seed"])
+        model = model_cls(conf)
+        opt = torch.optim.Adam(model.parameters(), lr=0.01, weight_decay=1e-3)
+        hist = []
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = runner(conf, model, None, feats, labels, indices, torch.nn.NLLLoss(),
+                         get_evaluator("cora"), opt, _NullLogger(), hist)
+        return res, hist, copy.deepcopy(model.state_dict())
+
+    (w_out, *w_scores), w_hist, w_sd = run(ref_models.Model, ref_te.run_transductive)
+    (g_out, *g_scores), g_hist, g_sd = run(Model, TE.run_transductive)
+    assert len(g_hist) == len(w_hist) >= 2
+    assert np.allclose(np.array(g_hist), np.array(w_hist), rtol=1e-5, atol=1e-6)
+    assert np.allclose(g_scores, w_scores, atol=1e-6)
+    assert torch.allclose(g_out.detach(), w_out.detach(), rtol=1e-5, atol=1e-6)
+    for k, v in w_sd.items():
+        assert torch.allclose(g_sd[k].float(), v.float(), rtol=1e-5, atol=1e-6), k
