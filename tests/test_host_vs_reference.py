@@ -254,3 +254,62 @@ def test_run_transductive_mlp_teacher_matches_reference(ref_modules):
     assert torch.allclose(g_out.detach(), w_out.detach(), rtol=1e-5, atol=1e-6)
     for k, v in w_sd.items():
         assert torch.allclose(g_sd[k].float(), v.float(), rtol=1e-5, atol=1e-6), k
+
+
+def test_cpf_loader_matches_reference_loader(ref_utils, tmp_path, monkeypatch):
+    """load_data for a CPF-format .npz (dataloader.py:42-111 + data_preprocess.py: standardize to the
+    largest connected component, binarize labels, seeded per-class split sampler, normalize_adj's
+    added self-loops) run by the REFERENCE'S loader over the shim and by glnn_b200.dataloader: same
+    nodes, same directed edge multiset, same features, labels and train / val / test indices."""
+    import importlib
+    import types
+    tz_stub = sys.modules.pop("pytz", None)   # pandas probes pytz.__version__: hide the shim's stand-in
+    try:
+        import pandas  # noqa: F401
+    finally:
+        if tz_stub is not None:
+            sys.modules["pytz"] = tz_stub
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_cli_and_data import write_cpf_npz
+
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+        for k, v in attrs.items():
+            if not hasattr(sys.modules[name], k):
+                setattr(sys.modules[name], k, v)
+    # imported by the reference's dataloader.py but never executed on the CPF path
+    stub("category_encoders", CatBoostEncoder=object)
+    stub("google_drive_downloader", GoogleDriveDownloader=object)
+    stub("dgl.data")
+    stub("dgl.data.utils", load_graphs=None)
+    stub("ogb.nodeproppred", DglNodePropPredDataset=object)
+    (tmp_path / "data").mkdir()
+    write_cpf_npz(tmp_path / "data" / "cora.npz")
+    monkeypatch.chdir(tmp_path)
+    saved = sys.modules.pop("dataloader", None)
+    sys.path.insert(0, REF)
+    try:
+        ref_dl = importlib.import_module("dataloader")
+        assert ref_dl.__file__.startswith(REF)
+        want = ref_dl.load_data("cora", "./data", seed=3, labelrate_train=20, labelrate_val=30, split_idx=0)
+    finally:
+        sys.path.remove(REF)
+        sys.modules.pop("dataloader", None)
+        sys.modules.pop("data_preprocess", None)
+        if saved is not None:
+            sys.modules["dataloader"] = saved
+    from glnn_b200.dataloader import load_data
+    got = load_data("cora", "./data", seed=3, labelrate_train=20, labelrate_val=30, split_idx=0)
+    gw, gg = want[0], got[0]
+    assert gg.num_nodes() == gw.num_nodes() and gg.num_edges() == gw.num_edges()
+    # both are CSR over destination nodes; neighbour lists compared as sorted multisets per row
+    assert torch.equal(gg.indptr.long().cpu(), gw.indptr.long())
+    n = gw.num_nodes()
+    rows = torch.repeat_interleave(torch.arange(n), gw.in_degrees())
+    key_w = (rows * n + gw.indices.long()).sort().values
+    key_g = (rows * n + gg.indices.long().cpu()).sort().values
+    assert torch.equal(key_g, key_w)
+    assert torch.equal(gg.ndata["feat"], gw.ndata["feat"])
+    for a, b in zip(got[1:], want[1:]):
+        assert torch.equal(a, b)
