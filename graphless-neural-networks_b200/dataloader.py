@@ -40,6 +40,17 @@ def load_out_t(out_t_dir):
 # ------------------------------------------------------------------------------------------------
 # OGB
 # ------------------------------------------------------------------------------------------------
+def arxiv_edges(src, dst, n):
+    """The reference's ogbn-arxiv preprocessing (dataloader.py:74-77): `g.add_edges(dsts, srcs)`
+    appends every edge reversed WITHOUT de-duplication (an edge present in both directions becomes
+    two parallel edges each way), `remove_self_loop()` drops every u -> u, `add_self_loop()` adds
+    exactly one per node.  Multiplicities are kept: the aggregation counts parallel edges."""
+    src, dst = torch.cat([src, dst]), torch.cat([dst, src])
+    keep = src != dst
+    loops = torch.arange(n, dtype=src.dtype)
+    return torch.cat([src[keep], loops]), torch.cat([dst[keep], loops])
+
+
 def load_ogb_data(dataset, dataset_path):
     try:
         from ogb.nodeproppred import NodePropPredDataset
@@ -51,10 +62,7 @@ def load_ogb_data(dataset, dataset_path):
     src, dst = (torch.from_numpy(graph_dict["edge_index"][i]).long() for i in (0, 1))
     n = int(graph_dict["num_nodes"])
     if dataset == "ogbn-arxiv":
-        src, dst = torch.cat([src, dst]), torch.cat([dst, src])
-        keep = src != dst
-        loops = torch.arange(n)
-        src, dst = torch.cat([src[keep], loops]), torch.cat([dst[keep], loops])
+        src, dst = arxiv_edges(src, dst, n)
     g = make_graph((src, dst), num_nodes=n)
     g.ndata["feat"] = torch.from_numpy(graph_dict["node_feat"]).float()
     labels = torch.from_numpy(labels).squeeze().long()

@@ -121,3 +121,19 @@ def test_cli_teacher_then_student_end_to_end(tmp_path):
                        text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert len(r.stdout.strip().split("\t")) == 2
+
+
+def test_arxiv_edge_preprocessing_known_answer():
+    """dataloader.py:74-77 on a 4-node multigraph: reverse edges appended without de-duplication,
+    original self-loops dropped, one self-loop per node added; in-degrees count multiplicities."""
+    from glnn_b200.dataloader import arxiv_edges
+    from glnn_b200.graph import graph
+    src = torch.tensor([0, 1, 2, 0, 3])
+    dst = torch.tensor([1, 0, 2, 1, 0])          # 0->1 twice, 1->0, a self-loop on 2, 3->0
+    s, d = arxiv_edges(src, dst, 4)
+    pairs = sorted(zip(s.tolist(), d.tolist()))
+    want = sorted([(0, 1)] * 3 + [(1, 0)] * 3 + [(3, 0), (0, 3)] + [(i, i) for i in range(4)])
+    assert pairs == want
+    g = graph((s, d), num_nodes=4)
+    assert g.in_degrees().tolist() == [3 + 1 + 1, 3 + 1, 1, 1 + 1]
+    assert g.num_edges() == 2 * 4 + 4             # 2 x (5 - 1 self-loop) + n
