@@ -167,8 +167,45 @@ def student_case(name, model_name, n, f, hidden, c, layers, norm, dropout, bs, l
           "perms", len(rec.perms), "masks", len(rec.masks))
 
 
+def teacher_train_case(name, n, e, f, hidden, c, layers, norm, lr, wd, lamb, steps, seed):
+    """Full-batch GCN TRAINING steps through the reference's own `train` (train_and_eval.py:12-29):
+    autograd through GCN.forward (models.py:189-199) over the shim's GraphConv, torch.optim.Adam.
+    dropout_ratio = 0 so that no random mask is involved."""
+    rng = np.random.default_rng(seed)
+    src, dst = rand_graph(rng, n, e, self_loops=True, dup=10)
+    g = dgl_shim.graph((src, dst), num_nodes=n)
+    ref_utils.set_seed(seed)
+    conf = dict(model_name="GCN", num_layers=layers, feat_dim=f, hidden_dim=hidden, label_dim=c,
+                dropout_ratio=0.0, norm_type=norm, device="cpu")
+    model = ref_models.Model(conf)
+    gen = torch.Generator().manual_seed(seed + 1)
+    for lyr in model.encoder.layers:
+        lyr.bias.data.copy_(torch.randn(lyr.bias.shape, generator=gen) * 0.1)
+    feats = torch.randn(n, f, generator=gen)
+    labels = torch.randint(0, c, (n,), generator=gen)
+    idx_train = torch.randperm(n, generator=gen)[: n // 3]
+    init = sd_np(model, "init.")
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    crit = torch.nn.NLLLoss()
+    losses = [ref_te.train(model, g, feats, labels, crit, opt, idx_train, lamb) for _ in range(steps)]
+    out, loss_eval, score_eval = ref_te.evaluate(model, g, feats, labels, crit,
+                                                 ref_utils.get_evaluator("cora"), idx_train)
+    np.savez_compressed(
+        os.path.join(OUT, f"teacher_train_{name}.npz"), src=src, dst=dst, n=n, feats=feats.numpy(),
+        labels=labels.numpy(), idx_train=idx_train.numpy(), losses=np.array(losses), lr=lr, wd=wd,
+        lamb=lamb, num_layers=layers, hidden=hidden, norm=norm, out=out.detach().numpy(),
+        loss_eval=loss_eval, score_eval=score_eval, **init, **sd_np(model, "final."))
+    print(name, "train losses", [round(x, 5) for x in losses], "eval", loss_eval, score_eval)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # bit-stable fixtures
+    if "--teacher-train-only" in sys.argv:   # later addition: leaves the older fixtures untouched
+        teacher_train_case("gcn2", n=150, e=700, f=30, hidden=16, c=5, layers=2, norm="none", lr=0.01,
+                           wd=1e-3, lamb=1.0, steps=4, seed=11)
+        teacher_train_case("gcn3_lamb", n=120, e=600, f=8, hidden=24, c=3, layers=3, norm="none", lr=0.02,
+                           wd=0.0, lamb=0.5, steps=3, seed=12)
+        sys.exit(0)
     # teacher: SAGE.inference through the reference's own batched layer-wise loop
     teacher_case("sage_bn3", "SAGE", n=300, e=2400, f=20, hidden=32, c=7, layers=3, norm="batch",
                  bs=64, seed=0, isolated=5, dup=100)
@@ -194,3 +231,7 @@ if __name__ == "__main__":
                  dropout=0.0, bs=512, lr=0.01, wd=0.0, lamb=1.0, epochs=2, seed=4)
     student_case("mlp_1layer", "MLP", n=200, f=10, hidden=16, c=4, layers=1, norm="batch",
                  dropout=0.0, bs=32, lr=0.01, wd=0.0, lamb=0.5, epochs=1, seed=5)
+    teacher_train_case("gcn2", n=150, e=700, f=30, hidden=16, c=5, layers=2, norm="none", lr=0.01,
+                       wd=1e-3, lamb=1.0, steps=4, seed=11)
+    teacher_train_case("gcn3_lamb", n=120, e=600, f=8, hidden=24, c=3, layers=3, norm="none", lr=0.02,
+                       wd=0.0, lamb=0.5, steps=3, seed=12)

@@ -137,3 +137,27 @@ def test_student_lamb0_hard_pass_still_moves_parameters():
     p, _, _, _ = _run_student(d)
     final = sub(d, "final.")
     assert relerr(p["layers.2.weight"], final["layers.2.weight"]) < 5e-4
+
+
+@pytest.mark.parametrize("case", ["teacher_train_gcn2", "teacher_train_gcn3_lamb"])
+def test_gcn_train_step_oracle_matches_reference(case):
+    """Full-batch GCN TRAINING steps: the oracle's manual backward + Adam against
+    the reference's own `train` (autograd through GCN.forward over the shim, torch.optim.Adam):
+    per-step losses and every parameter after the last step."""
+    d = load(case)
+    indptr, indices = O.csr_from_edges(d["src"], d["dst"], int(d["n"]))
+    L = int(d["num_layers"])
+    p = {f"layers.{l}.{k}": torch.from_numpy(d[f"init.encoder.layers.{l}.{k}"]).double().clone()
+         for l in range(L) for k in ("weight", "bias")}
+    st = O.init_adam_state(p)
+    feats, labels = torch.from_numpy(d["feats"]).double(), torch.from_numpy(d["labels"])
+    losses = [O.gcn_train_step(indptr, indices, feats, labels, d["idx_train"], p, st, float(d["lamb"]),
+                               float(d["lr"]), float(d["wd"])) for _ in range(len(d["losses"]))]
+    assert np.allclose(losses, d["losses"], rtol=2e-6)
+    for k, v in p.items():
+        want = torch.from_numpy(d[f"final.encoder.{k}"]).double()
+        assert relerr(v, want) < 2e-5, k
+    # the trained parameters reproduce the reference's evaluate() output
+    out = torch.log_softmax(O.gcn_forward(indptr, indices, feats,
+                                          [(p[f"layers.{l}.weight"], p[f"layers.{l}.bias"]) for l in range(L)]), 1)
+    assert relerr(out, torch.from_numpy(d["out"]).double()) < 2e-5

@@ -1,0 +1,76 @@
+"""GPU parity tests of the 'next' rows of the scope table that were written at
+the very end of round 1, AFTER the round's GPU budget was spent: they have never run on a B200.
+They are therefore marked xfail(strict=False): a pass shows up as XPASS, a failure as xfailed, and
+neither can turn the suite red or hide another test (this file also sorts last).  Promote them to
+hard tests (drop the marker) once they have run green."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "oracle"))
+from helpers import load, relerr, relerr_q  # noqa: E402
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="added without GPU access at the end of round 1; "
+                                                     "promote once it has run green on a B200")]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("case", ["teacher_train_gcn2", "teacher_train_gcn3_lamb"])
+def test_gcn_full_batch_train_steps_match_reference(dev, case):
+    """`train` (train_and_eval.py:12-29) on the B200 kernels -- autograd Functions over the
+    aggregation (backward = aggregation over the transposed CSR) and projection kernels, torch Adam --
+    against the fixture produced by the reference's own `train`: per-step losses and the parameters
+    after the last step."""
+    from glnn_b200 import graph as G, train_and_eval as TE
+    from glnn_b200.models import Model
+    d = load(case)
+    L = int(d["num_layers"])
+    model = Model(dict(model_name="GCN", num_layers=L, feat_dim=d["feats"].shape[1],
+                       hidden_dim=int(d["hidden"]), label_dim=d["out"].shape[1], dropout_ratio=0.0,
+                       norm_type=str(d["norm"]), device=dev))
+    model.load_state_dict({k[len("init."):]: torch.from_numpy(np.array(v)) for k, v in d.items()
+                           if k.startswith("init.")})
+    g = G.graph((d["src"], d["dst"]), num_nodes=int(d["n"])).to(dev)
+    feats, labels = torch.from_numpy(d["feats"]).to(dev), torch.from_numpy(d["labels"]).to(dev)
+    idx_train = torch.from_numpy(d["idx_train"]).to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=float(d["lr"]), weight_decay=float(d["wd"]))
+    losses = [TE.train(model, g, feats, labels, torch.nn.NLLLoss(), opt, idx_train, float(d["lamb"]))
+              for _ in range(len(d["losses"]))]
+    assert np.allclose(losses, d["losses"], rtol=1e-4)
+    sd = model.state_dict()
+    for k, v in d.items():
+        if k.startswith("final."):
+            # a few Adam steps amplify rounding noise on near-zero gradients: quantile bound + loose max
+            assert relerr_q(sd[k[len("final."):]].cpu(), v, 0.99) < 1e-3, k
+            assert relerr(sd[k[len("final."):]].cpu(), v) < 5e-2, k
+
+
+def test_feature_prop_matches_dense_formula(dev):
+    """feature_prop (utils.py:171-189): (D^-1/2 A D^-1/2)^k X hop by hop with D = in-degree clamped
+    to 1, on the aggregation kernel (both scalings fused), against a dense fp64 restatement."""
+    from glnn_b200 import graph as G, utils as U
+    rng = np.random.default_rng(5)
+    n, k = 300, 3
+    src = np.concatenate([rng.integers(0, n, 2000), rng.integers(0, n, 50)])
+    dst = np.concatenate([np.floor(n * rng.random(2000) ** 2).astype(np.int64), rng.integers(0, 20, 50)])
+    g = G.graph((torch.from_numpy(src), torch.from_numpy(dst)), num_nodes=n).to(dev)
+    x = torch.randn(n, 24, generator=torch.Generator().manual_seed(2))
+    A = torch.zeros(n, n, dtype=torch.float64)
+    for s, t in zip(src, dst):
+        A[t, s] += 1.0
+    norm = A.sum(1).clamp(min=1).pow(-0.5).unsqueeze(1)
+    want = x.double()
+    for _ in range(k):
+        want = (A @ (want * norm)) * norm
+    got = U.feature_prop(x.to(dev), g, k)
+    assert relerr(got.cpu(), want) < 1e-5
