@@ -74,3 +74,49 @@ def test_feature_prop_matches_dense_formula(dev):
         want = (A @ (want * norm)) * norm
     got = U.feature_prop(x.to(dev), g, k)
     assert relerr(got.cpu(), want) < 1e-5
+
+
+@pytest.mark.parametrize("kind", ["nll", "kl"])
+@pytest.mark.parametrize("hidden,norm", [(18, "batch"), (50, "batch"), (21, "none")])
+def test_student_step_hidden_not_multiple_of_4(dev, hidden, norm, kind):
+    """The column-wise BatchNorm kernels have a 4-columns-per-thread path (H % 4 == 0: every shape of
+    train.conf.yaml) and a scalar path; the golden fixtures only reach the scalar path without
+    BatchNorm (H = 17).  One step from identical state against the fp64 oracle at odd widths: loss,
+    last-layer gradients tight, lower layers to the quantile bound of the main gradient test."""
+    import glnn_oracle as O
+    from glnn_b200 import mlp_engine
+    from glnn_b200.models import Model
+    f, c, bs = 10, 5, 96
+    gen = torch.Generator().manual_seed(hidden)
+    n = bs + 7
+    feats = torch.randn(n, f, generator=gen)
+    labels = torch.randint(0, c, (n,), generator=gen)
+    out_t = torch.log_softmax(torch.randn(n, c, generator=gen) * 2, 1)
+    torch.manual_seed(3)
+    model = Model(dict(model_name="MLP", num_layers=3, feat_dim=f, hidden_dim=hidden, label_dim=c,
+                       dropout_ratio=0.0, norm_type=norm, device=dev))
+    p = {k[len("encoder."):]: (v.detach().cpu().clone().double() if v.is_floating_point()
+                               else v.detach().cpu().clone()) for k, v in model.state_dict().items()}
+    idx = torch.randperm(n, generator=gen)[:bs].view(1, bs)
+    tgt = labels if kind == "nll" else out_t.double()
+    logits, cache = O.mlp_forward(feats.double()[idx[0]], p, 3, norm, True)
+    loss, dlog = O.loss_and_dlogits(logits, tgt[idx[0]], kind, 0.6)
+    want = O.mlp_backward(dlog, cache, p, 3, norm, 0.0)
+    opt = torch.optim.Adam(model.parameters(), lr=0.01)
+    model.train()
+    got_loss = mlp_engine.train_pass(model.encoder, opt, feats.to(dev),
+                                     (labels if kind == "nll" else out_t).to(dev), idx.to(dev), 0.6)
+    assert abs(got_loss.item() - float(loss)) < 1e-4 * abs(float(loss))
+    got = mlp_engine.flat_grads(model.encoder)
+    for k, w in want.items():
+        if norm == "batch" and k.endswith(".bias") and not k.startswith("layers.2.") and k.startswith("layers."):
+            continue   # Linear bias in front of BatchNorm: mathematically zero, rounding noise only
+        if k.startswith("layers.2."):
+            assert relerr(got[k].cpu(), w) < 1e-4, k
+        else:
+            assert relerr_q(got[k].cpu(), w, 0.99) < 1e-2, k
+    if norm == "batch":   # running statistics after the step (momentum 0.1, unbiased variance)
+        sd = model.state_dict()
+        h0 = feats.double()[idx[0]] @ p["layers.0.weight"].t() + p["layers.0.bias"]
+        assert relerr(sd["encoder.norms.0.running_mean"].cpu(), 0.1 * h0.mean(0)) < 1e-4
+        assert relerr(sd["encoder.norms.0.running_var"].cpu(), 0.9 + 0.1 * h0.var(0, unbiased=True)) < 1e-4
