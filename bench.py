@@ -462,9 +462,62 @@ def other_configs(dev, torch, hbm_peak):
         for _ in range(5):
             O.gcn_forward(ip, ix, fc, layers)
         entry["cpu_port_evaluate_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 3)
+        # full-batch training step on the host cores: the oracle's forward + manual backward + Adam
+        # (pinned to the reference's own `train` by tests/test_oracle_golden.py; no dropout mask)
+        pp = {f"layers.{l}.{k}": sd[f"encoder.layers.{l}.{k}"].clone() for l in range(2)
+              for k in ("weight", "bias")}
+        stt = O.init_adam_state(pp)
+        lc, ic = labels.cpu(), idx_train.cpu()
+        O.gcn_train_step(ip, ix, fc, lc, ic, pp, stt, 1.0, 0.01, 1e-3)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            O.gcn_train_step(ip, ix, fc, lc, ic, pp, stt, 1.0, 0.01, 1e-3)
+        entry["cpu_port_train_step_ms"] = round((time.perf_counter() - t0) / 5 * 1e3, 3)
     except Exception as ex:
         entry["cpu_port_error"] = repr(ex)
     out["cora GCN teacher"] = entry
+    # ---- configs[2] at the level of the runner: ONE epoch of distill_run_transductive (hard-label
+    # pass + soft-label pass + three evaluations, train_and_eval.py:520-606) on the arxiv shape with
+    # the paper's student MLP3w4 -- wall clock through the public API, host syncs included.  Added at
+    # the end of round 1 without a GPU run: any failure is confined to this entry.
+    try:
+        s = SHAPES["ogbn-arxiv"]
+        n, dims = s["n"], DIMS["ogbn-arxiv"]
+        torch.manual_seed(0)
+        feats = torch.randn(n, dims[0], device=dev)
+        labels = torch.randint(0, dims[3], (n,), device=dev)
+        out_t = torch.log_softmax(torch.randn(n, dims[3], device=dev), 1)
+        perm = torch.randperm(n)
+        n_l, n_v, _ = s["split"]
+        idx_l, idx_val, idx_test = perm[:n_l], perm[n_l:n_l + n_v], perm[n_l + n_v:]
+        idx_t = torch.cat([idx_l, idx_val, idx_test])
+        conf = dict(seed=0, device=dev, batch_size=512, lamb=0.0, patience=50, max_epoch=1,
+                    eval_interval=1)
+        st = Model(dict(model_name="MLP3w4", num_layers=3, feat_dim=dims[0], hidden_dim=1024,
+                        label_dim=dims[3], dropout_ratio=0.5, norm_type="batch", device=dev))
+        opt = torch.optim.Adam(st.parameters(), lr=0.01)
+
+        class _Quiet:
+            def debug(self, *a, **k): pass
+            def info(self, *a, **k): pass
+        run = lambda: TE.distill_run_transductive(
+            conf, st, feats, labels, out_t, (idx_l, idx_t, idx_val, idx_test), torch.nn.NLLLoss(),
+            torch.nn.KLDivLoss(reduction="batchmean", log_target=True), get_evaluator("ogbn-arxiv"),
+            opt, _Quiet(), [])
+        run()                                   # warm-up: graph capture, workspace allocation
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        steps = n_l // 512 + n // 512
+        out["ogbn-arxiv student epoch (MLP3w4, distill_run_transductive)"] = {
+            "epoch_ms": round(dt * 1e3, 2), "train_steps": steps,
+            "train_nodes_per_s": steps * 512 / dt,
+            "includes": "hard-label pass (177 steps), soft-label pass (330 steps), 3 evaluations, "
+                        "best-state copy, final evaluation over all nodes; wall clock"}
+    except Exception as ex:
+        out["ogbn-arxiv student epoch (MLP3w4, distill_run_transductive)"] = {"error": repr(ex)}
     return out
 
 
