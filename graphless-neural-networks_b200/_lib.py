@@ -72,6 +72,9 @@ SIGNATURES = {
     "glnn_spmm_csr_q24_planes": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64,
                                            C.c_int, C.c_int, C.c_int, c_vp, c_vp, c_vp]),
     "glnn_spmm_csr": (C.c_int, [C.POINTER(SpmmDesc), c_vp]),
+    "glnn_s24_row_words": (c_i64, [C.c_int]),
+    "glnn_compact_s24": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, c_vp, c_vp]),
+    "glnn_spmm_csr_s24": (C.c_int, [C.POINTER(SpmmDesc), c_vp, c_i64, c_vp, c_vp]),
     "glnn_bn_fold_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, C.c_int, c_vp]),
     "glnn_log_softmax_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int, c_vp]),
     "glnn_nll_acc_f32": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),

@@ -72,6 +72,13 @@ struct SpmmArgs {
   // L2 residency hints: gathered rows of source ids < hot_below are loaded evict_last, all other
   // gathered rows, the index stream and the output stream evict_first (0 = no hints)
   int hot_below;
+  // optional sparse copy of the gathered matrix ("s24", see glnn_compact_s24): row = `cap` words
+  // [fp32 bits 31..8 | column 7..0] sorted by column, zero-padded, rows lds words apart; *cap_dev =
+  // max non-zeros per row.  Used by spmm_csr_s24_kernel only; Xq stays the self / hub / dense source.
+  const uint32_t* Xs;
+  int64_t lds;
+  const int* cap_dev;
+  int cap_limit;         // sparse path only when *cap_dev <= cap_limit
   // hub scratch (library-owned, per device and stream)
   int* hub_ctr;          // [0] tasks registered, [1] hub rows registered, [2] next task to run
   HubTask* hub_tasks;
@@ -574,6 +581,191 @@ __global__ void __launch_bounds__(kWarps * 32) spmm_hub_finish_kernel(const Spmm
   }
 }
 
+// ---- sparse rows ("s24") for post-ReLU embeddings: EXPERIMENTAL, opt-in ---------------------------
+// Written at the end of round 1 without a GPU run (tests/test_zz_next_rows_gpu.py holds its parity
+// test as a non-strict xfail); nothing on the default path calls it.  DESIGN.md section 8 item 3.
+//
+// q24 -> s24: one warp per row.  Lane l decodes its 8 columns, keeps the non-zeros as
+// [bits 31..8 | column], the warp packs them (prefix sum over the lanes) through shared memory and
+// writes the whole row -- entries, then zeros up to dq words -- with 16-byte stores.  The per-matrix
+// capacity (max non-zeros of a row) is reduced per CTA and published with one atomicMax.
+constexpr int kS24MaxD = 256;  // the column id has 8 bits
+
+__global__ void __launch_bounds__(kWarps * 32) compact_s24_kernel(const uint8_t* __restrict__ Q,
+                                                                  int64_t ldq, int64_t rows, int dq,
+                                                                  uint32_t* __restrict__ S,
+                                                                  int64_t lds, int* __restrict__ cap) {
+  __shared__ __align__(16) uint32_t s_row[kWarps][kS24MaxD];
+  __shared__ int s_max;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lds_row = (dq + 31) / 32 * 32;  // words written per row (entries, then zeros)
+  if (threadIdx.x == 0) s_max = 0;
+  __syncthreads();
+  int local_max = 0;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * kWarps + warp; row < rows;
+       row += static_cast<int64_t>(gridDim.x) * kWarps) {
+    const int col = lane * 8;
+    uint32_t wd[8];
+    uint32_t mask = 0u;  // bit i: column col + i is non-zero
+    if (col < dq) {
+      const uint8_t* r = Q + row * ldq;
+      float x[8];
+      decode_q24(*reinterpret_cast<const uint4*>(r + 2 * col),
+                 *reinterpret_cast<const uint2*>(r + 2 * dq + col), x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const uint32_t b = __float_as_uint(x[i]);
+        wd[i] = b | static_cast<uint32_t>(col + i);
+        if ((b << 1) != 0u) mask |= 1u << i;  // skips +0.0 and -0.0
+      }
+    }
+    const int cnt = __popc(mask);
+    int pre = cnt;  // inclusive prefix sum over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, pre, 31);
+    const int base = pre - cnt;
+    for (int i = lane; i < lds_row; i += 32) s_row[warp][i] = 0u;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if ((mask >> i) & 1u) s_row[warp][base + __popc(mask & ((1u << i) - 1u))] = wd[i];
+    __syncwarp();
+    uint32_t* out = S + row * lds;
+    for (int i = lane * 4; i < lds_row; i += 128)
+      *reinterpret_cast<uint4*>(out + i) = *reinterpret_cast<const uint4*>(&s_row[warp][i]);
+    __syncwarp();
+    local_max = max(local_max, total);
+  }
+  if (lane == 0 && local_max > 0) atomicMax(&s_max, local_max);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_max > 0) atomicMax(cap, s_max);
+}
+
+// acc_s[0..255] += sum over edges [beg, end) of the sparse rows.  Lanes take the entries
+// lane + 32 k of a row (columns of one instruction are nearly consecutive: few bank conflicts);
+// U rows are loaded before any is accumulated; zero words (padding) are skipped, so no two lanes of
+// an instruction ever touch the same accumulator (the columns of a row are distinct).
+__device__ __forceinline__ void gather_range_s24(const SpmmArgs& a, int64_t beg, int64_t end, int lane,
+                                                 int nseg, const Policies& pol,
+                                                 float* __restrict__ acc_s) {
+  constexpr int U = 4, KMAX = kS24MaxD / 32;
+  for (int64_t base = beg; base < end; base += 32) {
+    const int my = (base + lane < end) ? static_cast<int>(ld4(a.indices + base + lane, pol.cold)) : -1;
+    const int cnt = static_cast<int>(min(static_cast<int64_t>(32), end - base));
+    for (int j = 0; j < cnt; j += U) {
+      uint32_t w[U][KMAX];
+#pragma unroll
+      for (int t = 0; t < U; ++t) {
+        const int u = __shfl_sync(0xffffffffu, my, (j + t) & 31);
+        const bool live = (j + t < cnt) && u >= 0;
+        const uint32_t* r = a.Xs + static_cast<int64_t>(live ? u : 0) * a.lds + lane;
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) w[t][k] = (live && k < nseg) ? ld4(r + 32 * k, pol.cold) : 0u;
+      }
+#pragma unroll
+      for (int t = 0; t < U; ++t) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+          const uint32_t v = w[t][k];
+          if (v != 0u) acc_s[v & 0xffu] += __uint_as_float(v & 0xffffff00u);
+        }
+        __syncwarp();  // the next row's entries of a column may sit in another lane
+      }
+    }
+  }
+}
+
+// spmm_csr_kernel<32, 1, 8, false> with the non-hub rows gathered from the sparse copy when the
+// matrix is sparse enough (*cap_dev <= cap_limit); hubs, the self term and dense matrices use q24.
+__global__ void __launch_bounds__(kWarps * 32, GLNN_SPMM_MINB) spmm_csr_s24_kernel(const SpmmArgs a) {
+  constexpr int G = 32, VPL = 1, W = 8, NG = kWarps;
+  __shared__ float s_part[NG][G * VPL * W];
+  __shared__ int s_hub[NG];
+  __shared__ int s_nhub;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gl = lane, lane_base = 0, gidx = warp;
+  const unsigned gmask = 0xffffffffu;
+  const int64_t row0 = static_cast<int64_t>(blockIdx.x) * NG;
+  const Policies pol = make_policies(a.hot_below > 0);
+  const int cap = *a.cap_dev;
+  const bool sparse = cap <= a.cap_limit;
+  const int nseg = (cap + 31) >> 5;
+  if (threadIdx.x == 0) s_nhub = 0;
+  __syncthreads();
+  {
+    const int64_t row = row0 + gidx;
+    if (row < a.n_dst) {
+      const int64_t beg = load_ptr(a, row), end = load_ptr(a, row + 1);
+      const int64_t deg = end - beg;
+      if (deg > kHubT) {  // identical to spmm_csr_kernel: register the row, the q24 hub kernels finish it
+        int slot = -1;
+        if (gl == 0) {
+          const int ntask = static_cast<int>((deg + kHubSeg - 1) / kHubSeg);
+          const int s = atomicAdd(a.hub_ctr + 1, 1);
+          if (s < a.cap_rows) {
+            const int t0 = atomicAdd(a.hub_ctr + 0, ntask);
+            if (t0 + ntask <= a.cap_tasks) {
+              slot = s;
+              a.hub_rows[s] = row;
+              for (int t = 0; t < ntask; ++t) {
+                HubTask tk;
+                tk.beg = beg + static_cast<int64_t>(t) * kHubSeg;
+                tk.len = static_cast<int32_t>(min(static_cast<int64_t>(kHubSeg), end - tk.beg));
+                tk.slot = s;
+                a.hub_tasks[t0 + t] = tk;
+              }
+            } else {
+              a.hub_rows[s] = -1;
+              for (int t = t0; t < min(t0 + ntask, a.cap_tasks); ++t) {
+                HubTask tk;
+                tk.beg = 0; tk.len = 0; tk.slot = s;
+                a.hub_tasks[t] = tk;
+              }
+            }
+          }
+        }
+        slot = __shfl_sync(gmask, slot, lane_base);
+        if (slot >= 0) {
+          for (int c = gl; c < kHubAccLd; c += G)
+            a.hub_acc[static_cast<int64_t>(slot) * kHubAccLd + c] = 0.f;
+        } else if (gl == 0) {
+          s_hub[atomicAdd(&s_nhub, 1)] = gidx;
+        }
+      } else {
+        float acc[VPL][W];
+        if (sparse) {
+          float* acc_s = s_part[gidx];  // this warp's 256 accumulators
+#pragma unroll
+          for (int i = 0; i < W; ++i) acc_s[lane * W + i] = 0.f;
+          __syncwarp();
+          gather_range_s24(a, beg, end, lane, nseg, pol, acc_s);
+#pragma unroll
+          for (int i = 0; i < W; ++i) acc[0][i] = acc_s[lane * W + i];
+          __syncwarp();
+        } else {
+          zero_acc<VPL, W>(acc);
+          gather_range<G, VPL, W, false>(a, beg, end, gl, lane_base, gmask, pol, acc);
+        }
+        epilogue_store<G, VPL, W>(a, row, deg, gl, gmask, pol, acc);
+      }
+    }
+  }
+  __syncthreads();
+  const int nhub = s_nhub;  // only when the task list overflowed
+  for (int h = 0; h < nhub; ++h) {
+    const int64_t row = row0 + s_hub[h];
+    const int64_t beg = load_ptr(a, row), end = load_ptr(a, row + 1);
+    float acc[VPL][W];
+    cta_gather<G, VPL, W, false, NG>(a, beg, end, gidx, gl, lane_base, gmask, pol, s_part, acc);
+    if (gidx == 0) epilogue_store<G, VPL, W>(a, row, end - beg, gl, gmask, pol, acc);
+    __syncthreads();
+  }
+}
+
 template <int G, int VPL, int W>
 static int launch_cfg(const SpmmArgs& a, cudaStream_t st) {
   constexpr int NG = kWarps * (32 / G);
@@ -710,6 +902,10 @@ int spmm_run(const glnn_spmm_desc& d0, cudaStream_t st) {
     a.log_softmax = q.log_softmax > 0;
     a.d_valid = q.log_softmax;
     a.hot_below = q.hot_below;
+    a.Xs = nullptr;
+    a.lds = 0;
+    a.cap_dev = nullptr;
+    a.cap_limit = 0;
     a.hub_ctr = hs.ctr;
     a.hub_tasks = hs.tasks;
     a.hub_rows = hs.rows;
@@ -719,6 +915,68 @@ int spmm_run(const glnn_spmm_desc& d0, cudaStream_t st) {
     rc = q24 ? launch_width<8>(a, st) : ((vec && vec_out) ? launch_width<4>(a, st) : launch_width<1>(a, st));
     if (rc != 0) return rc;
   }
+  return 0;
+}
+
+// EXPERIMENTAL (see compact_s24_kernel): q24 -> s24 and the aggregation that reads it.
+int compact_s24(const uint8_t* Q, int64_t ldq, int64_t rows, int d, uint32_t* S, int64_t lds, int* cap_dev,
+                cudaStream_t st) {
+  const int dq = (d + 7) / 8 * 8;
+  GLNN_REQUIRE(Q && S && cap_dev, GLNN_ERR_ARG, "compact_s24: null pointer");
+  GLNN_REQUIRE(d > 0 && dq <= kS24MaxD, GLNN_ERR_SHAPE, "compact_s24: d must be in [1, %d]", kS24MaxD);
+  GLNN_REQUIRE(aligned16(Q) && ldq % 16 == 0 && ldq >= 3 * dq, GLNN_ERR_ALIGN, "compact_s24: bad q24 layout");
+  GLNN_REQUIRE(aligned16(S) && lds % 32 == 0 && lds >= (dq + 31) / 32 * 32, GLNN_ERR_ALIGN,
+               "compact_s24: lds must be a multiple of 32 words and >= roundup(d, 32)");
+  GLNN_CUDA_OK(cudaMemsetAsync(cap_dev, 0, sizeof(int), st));
+  if (rows == 0) return 0;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((rows + kWarps - 1) / kWarps, 16LL * sm_count()));
+  compact_s24_kernel<<<blocks, kWarps * 32, 0, st>>>(Q, ldq, rows, dq, S, lds, cap_dev);
+  GLNN_LAUNCH_OK("compact_s24_kernel");
+  return 0;
+}
+
+int spmm_run_s24(const glnn_spmm_desc& q, const uint32_t* S, int64_t lds, const int* cap_dev,
+                 cudaStream_t st) {
+  const int d = q.d, dq = (d + 7) / 8 * 8;
+  GLNN_REQUIRE(S && cap_dev && q.X_q24 && !q.X, GLNN_ERR_ARG,
+               "spmm_s24: needs the q24 matrix (self term, hubs, dense fallback) and its s24 copy");
+  GLNN_REQUIRE(dq > 128 && dq <= kS24MaxD, GLNN_ERR_SHAPE, "spmm_s24: 128 < roundup(d, 8) <= 256 only");
+  GLNN_REQUIRE(!q.src_scale && !q.log_softmax, GLNN_ERR_ARG, "spmm_s24: no src_scale / log_softmax");
+  GLNN_REQUIRE(aligned16(S) && lds % 32 == 0 && lds >= (dq + 31) / 32 * 32, GLNN_ERR_ALIGN,
+               "spmm_s24: lds must be a multiple of 32 words and >= roundup(d, 32)");
+  GLNN_REQUIRE(q.n_dst >= 0 && q.indptr && (q.Y || q.Y_hi), GLNN_ERR_ARG, "spmm_s24: null indptr / output");
+  if (q.n_dst == 0) return 0;
+  GLNN_REQUIRE(aligned16(q.X_q24) && q.ldq % 16 == 0 && q.ldq >= 3 * dq, GLNN_ERR_ALIGN, "spmm_s24: bad q24 layout");
+  GLNN_REQUIRE((q.Y_hi == nullptr) == (q.Y_lo == nullptr), GLNN_ERR_ARG, "spmm_s24: output planes come in pairs");
+  GLNN_REQUIRE((!q.Y || (q.ldy % 4 == 0 && q.ldy >= dq && aligned16(q.Y))) &&
+                   (!q.Y_hi || (q.ldyp % 8 == 0 && q.ldyp >= dq && aligned16(q.Y_hi) && aligned16(q.Y_lo))),
+               GLNN_ERR_ALIGN, "spmm_s24: output rows must be 16-byte aligned and >= roundup(d, 8) wide");
+  GLNN_REQUIRE(!q.self_add || q.n_src >= q.n_dst, GLNN_ERR_SHAPE, "spmm_s24: self_add needs n_src >= n_dst");
+  GLNN_REQUIRE((q.col_scale == nullptr) == (q.col_shift == nullptr) && q.relu >= 0 && q.relu <= 2,
+               GLNN_ERR_ARG, "spmm_s24: bad epilogue arguments");
+  HubScratch hs;
+  int rc = hub_scratch(st, &hs);
+  if (rc != 0) return rc;
+  SpmmArgs a;
+  a.indptr = q.indptr; a.indices = q.indices; a.X = nullptr; a.ldx = 0;
+  a.Xq = q.X_q24; a.ldq = q.ldq; a.dq = dq;
+  a.Y = q.Y; a.ldy = q.ldy; a.Yh = q.Y_hi; a.Yl = q.Y_lo; a.ldyp = q.ldyp;
+  a.n_dst = q.n_dst; a.d = d; a.indptr64 = q.indptr64;
+  a.self_add = q.self_add; a.mean_plus_one = q.mean_plus_one;
+  a.src_scale = nullptr; a.dst_scale = q.dst_scale; a.bias = q.bias;
+  a.col_scale = q.col_scale; a.col_shift = q.col_shift; a.relu = q.relu;
+  a.log_softmax = 0; a.d_valid = 0; a.hot_below = q.hot_below;
+  a.Xs = S; a.lds = lds; a.cap_dev = cap_dev;
+  a.cap_limit = (q.ldq * 4 / 5) / 4;  // sparse rows must be at least 20 % shorter than the q24 rows
+  a.hub_ctr = hs.ctr; a.hub_tasks = hs.tasks; a.hub_rows = hs.rows; a.hub_acc = hs.acc;
+  a.cap_tasks = kCapTasks; a.cap_rows = kCapRows;
+  const int64_t blocks = (a.n_dst + kWarps - 1) / kWarps;
+  GLNN_REQUIRE(blocks < (1LL << 31), GLNN_ERR_SHAPE, "spmm_s24: too many rows");
+  GLNN_CUDA_OK(cudaMemsetAsync(a.hub_ctr, 0, 4 * sizeof(int), st));
+  spmm_csr_s24_kernel<<<static_cast<unsigned>(blocks), kWarps * 32, 0, st>>>(a);
+  spmm_hub_kernel<32, 1, 8, false><<<static_cast<unsigned>(4 * sm_count()), kWarps * 32, 0, st>>>(a);
+  spmm_hub_finish_kernel<32, 1, 8><<<32, kWarps * 32, 0, st>>>(a);
+  GLNN_LAUNCH_OK("spmm_csr_s24_kernel");
   return 0;
 }
 
@@ -763,6 +1021,22 @@ int quantize_q24(const float* X, int64_t ldx, int64_t rows, int d, uint8_t* Q, i
 extern "C" int glnn_spmm_csr(const glnn_spmm_desc* desc, glnn_stream_t stream) {
   GLNN_REQUIRE(desc != nullptr, GLNN_ERR_ARG, "spmm: null descriptor");
   return glnn::spmm_run(*desc, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int64_t glnn_s24_row_words(int d) {
+  if (d <= 0) return 0;
+  return (static_cast<int64_t>(d) + 31) / 32 * 32;
+}
+
+extern "C" int glnn_compact_s24(const uint8_t* X_q24, int64_t ldq, int64_t rows, int d, uint32_t* X_s24,
+                                int64_t lds, int32_t* cap_dev, glnn_stream_t stream) {
+  return glnn::compact_s24(X_q24, ldq, rows, d, X_s24, lds, cap_dev, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int glnn_spmm_csr_s24(const glnn_spmm_desc* desc, const uint32_t* X_s24, int64_t lds,
+                                 const int32_t* cap_dev, glnn_stream_t stream) {
+  GLNN_REQUIRE(desc != nullptr, GLNN_ERR_ARG, "spmm_s24: null descriptor");
+  return glnn::spmm_run_s24(*desc, X_s24, lds, cap_dev, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int64_t glnn_q24_row_bytes(int d) {

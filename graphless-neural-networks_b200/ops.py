@@ -236,11 +236,12 @@ def gemm_planes_q24(a, b, trans_b=True, out=None, row_scale=None, bias=None, col
 
 def spmm(indptr, indices, x, d=None, out=None, out_planes=None, self_add=False, mean_plus_one=False,
          src_scale=None, dst_scale=None, bias=None, col_scale=None, col_shift=None, relu=0,
-         log_softmax=0, hot_below=0):
+         log_softmax=0, hot_below=0, s24=None):
     """glnn_spmm_csr (general form).  x: fp32 tensor [n_src, >= d] or Q24; result in `out` (fp32
     tensor) and/or `out_planes` (Planes); if neither is given an fp32 tensor is allocated.
     log_softmax = c > 0 ends the epilogue with log_softmax over the first c columns (fp32 out
-    [n_dst, c]); hot_below = k marks source ids < k as L2-resident (a pure performance hint)."""
+    [n_dst, c]); hot_below = k marks source ids < k as L2-resident (a pure performance hint).
+    s24 = S24 copy of the Q24 matrix x (EXPERIMENTAL, compact_s24): glnn_spmm_csr_s24."""
     lib = _lib.load()
     require_cuda(indptr, indices, out, src_scale, dst_scale, bias, col_scale, col_shift)
     _f32(out, src_scale, dst_scale, bias, col_scale, col_shift)
@@ -275,8 +276,34 @@ def spmm(indptr, indices, x, d=None, out=None, out_planes=None, self_add=False, 
     q.col_scale, q.col_shift, q.relu = ptr(col_scale), ptr(col_shift), int(relu)
     q.log_softmax, q.hot_below = int(log_softmax), int(hot_below)
     import ctypes
-    check(lib.glnn_spmm_csr(ctypes.byref(q), stream()), "glnn_spmm_csr")
+    if s24 is not None:
+        check(lib.glnn_spmm_csr_s24(ctypes.byref(q), ptr(s24.data), s24.data.stride(0), ptr(s24.cap),
+                                    stream()), "glnn_spmm_csr_s24")
+    else:
+        check(lib.glnn_spmm_csr(ctypes.byref(q), stream()), "glnn_spmm_csr")
     return out if out is not None else out_planes
+
+
+class S24:
+    """EXPERIMENTAL sparse copy of a post-ReLU Q24 matrix (include/glnn_b200.h, glnn_compact_s24):
+    .data int32 [rows, lds] words [fp32 bits 31..8 | column], .cap int32 [1] = max non-zeros per row
+    (device)."""
+
+    def __init__(self, data, cap, cols):
+        self.data, self.cap, self.cols = data, cap, cols
+
+
+def compact_s24(xq):
+    """glnn_compact_s24: Q24 -> S24 (d <= 256)."""
+    lib = _lib.load()
+    require_cuda(xq.data)
+    rows = xq.data.shape[0]
+    lds = int(lib.glnn_s24_row_words(xq.cols))
+    data = torch.empty(rows, lds, dtype=torch.int32, device=xq.data.device)
+    cap = torch.zeros(1, dtype=torch.int32, device=xq.data.device)
+    check(lib.glnn_compact_s24(ptr(xq.data), xq.ldq, rows, xq.cols, ptr(data), lds, ptr(cap), stream()),
+          "glnn_compact_s24")
+    return S24(data, cap, xq.cols)
 
 
 def new_planes(rows, cols, device):

@@ -185,6 +185,21 @@ typedef struct glnn_spmm_desc {
 
 GLNN_API int glnn_spmm_csr(const glnn_spmm_desc* desc, glnn_stream_t stream);
 
+/* EXPERIMENTAL, opt-in (nothing on the default path calls it; added at the end of round 1 without a
+ * GPU run -- DESIGN.md section 8 item 3): lossless sparse rows for post-ReLU embeddings.  "s24" row =
+ * the row's non-zeros as 32-bit words [fp32 bits 31..8 | column 7..0] sorted by column, followed by
+ * zero words up to lds (a multiple of 32 words, >= d rounded up to 32 = glnn_s24_row_words(d));
+ * d <= 256.  glnn_compact_s24 derives it from the q24 matrix and leaves the largest non-zero count
+ * of a row in *cap_dev (device memory).  glnn_spmm_csr_s24 = glnn_spmm_csr on desc (which must carry
+ * the q24 matrix: self term, hub rows and the dense fallback read it) gathering non-hub rows from the
+ * sparse copy whenever cap * 4 bytes <= 80 % of the q24 row; results are identical to glnn_spmm_csr
+ * except for the summation order inside hub rows.  128 < d <= 256, no src_scale, no log_softmax. */
+GLNN_API int64_t glnn_s24_row_words(int d);
+GLNN_API int glnn_compact_s24(const uint8_t* X_q24, int64_t ldq, int64_t rows, int d, uint32_t* X_s24,
+                     int64_t lds, int32_t* cap_dev, glnn_stream_t stream);
+GLNN_API int glnn_spmm_csr_s24(const glnn_spmm_desc* desc, const uint32_t* X_s24, int64_t lds,
+                      const int32_t* cap_dev, glnn_stream_t stream);
+
 /* K5 (eval): folds BatchNorm1d running statistics into a per-column affine for the epilogues
  * above: scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (models.py:139-141). */
 GLNN_API int glnn_bn_fold_f32(const float* gamma, const float* beta, const float* mean, const float* var,
