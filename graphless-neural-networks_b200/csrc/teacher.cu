@@ -19,6 +19,11 @@ int quantize_q24(const float* X, int64_t ldx, int64_t rows, int d, uint8_t* Q, i
                  cudaStream_t st);                                                    // spmm.cu
 int split_planes(const float* X, int64_t ldx, int64_t rows, int cols, uint16_t* hi, uint16_t* lo,
                  int64_t ldp, cudaStream_t st);                                      // planes.cu
+// EXPERIMENTAL sparse rows (spmm.cu), only reached with GLNN_S24=1
+int compact_s24(const uint8_t* Q, int64_t ldq, int64_t rows, int d, uint32_t* S, int64_t lds, int* cap_dev,
+                cudaStream_t st);
+int spmm_run_s24(const glnn_spmm_desc& q, const uint32_t* S, int64_t lds, const int* cap_dev,
+                 cudaStream_t st);
 
 static inline int pad4(int d) { return (d + 3) / 4 * 4; }
 static inline int pad8(int d) { return (d + 7) / 8 * 8; }
@@ -171,6 +176,9 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
   float* buf[3];
   for (int i = 0; i < 3; ++i) buf[i] = static_cast<float*>(workspace) + i * p.buf_floats;
   float* scratch = static_cast<float*>(workspace) + 3 * p.buf_floats;
+  // EXPERIMENTAL (never run on a GPU yet): GLNN_S24=1 gathers post-ReLU
+  // embeddings of 136..256 columns from a sparse copy of the q24 matrix (SAGE only)
+  static const bool use_s24 = getenv("GLNN_S24") != nullptr;
   auto project_first = [&](int l) {
     const glnn_gnn_layer& ly = layers[l];
     return gcn ? (ly.d_in > ly.d_out) : (pad4(ly.d_out) < ly.d_in);
@@ -276,7 +284,18 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
       q.hot_below = hot_rows(h.q24 ? h.ldq : 4 * h.ld);
       q.src_scale = gcn ? src_norm : nullptr;
       q.Y_hi = tp.hi; q.Y_lo = tp.lo; q.ldyp = tp.ldp;
-      if ((rc = spmm_run(q, st))) return rc;
+      const int64_t lds = glnn_s24_row_words(ly.d_in);
+      if (use_s24 && !gcn && h.q24 && l > 0 && pad8(ly.d_in) > 128 && pad8(ly.d_in) <= 256 &&
+          lds <= p.dmax) {
+        // h = ReLU(...) of the previous layer; buf[ob] is free until the projection below writes it
+        uint32_t* S = reinterpret_cast<uint32_t*>(buf[ob]);
+        static thread_local int* s24_cap = nullptr;  // library-owned counter (like the hub scratch)
+        if (!s24_cap) GLNN_CUDA_OK(cudaMalloc(&s24_cap, sizeof(int)));
+        if ((rc = compact_s24(h.q24, h.ldq, n, ly.d_in, S, lds, s24_cap, st))) return rc;
+        if ((rc = spmm_run_s24(q, S, lds, s24_cap, st))) return rc;
+      } else if ((rc = spmm_run(q, st))) {
+        return rc;
+      }
       if ((rc = weight_planes(ly, !gcn, 0, scratch, &w, st))) return rc;
       Act t;
       t.hi = tp.hi; t.lo = tp.lo; t.ldp = tp.ldp; t.d = ly.d_in;

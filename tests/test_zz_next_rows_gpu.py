@@ -163,3 +163,35 @@ def test_s24_sparse_rows_match_q24_gather(dev, d, zero_frac):
     want_f = ops.spmm(g.indptr, g.indices, xq, **kw)
     got_f = ops.spmm(g.indptr, g.indices, xq, s24=s, **kw)
     assert relerr(got_f.cpu(), want_f.cpu()) < 1e-6
+
+
+def test_s24_layer_planner_opt_in_matches_default(dev, tmp_path):
+    """GLNN_S24=1 (read once per process) routes the 256-wide post-ReLU aggregation of the SAGE
+    forward through the sparse copy; the forward's log-probabilities must equal the default path's."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = (
+        "import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+        "from glnn_b200 import graph as G\n"
+        "from glnn_b200.models import Model\n"
+        "from glnn_b200.workloads import randomise_bn_, synthetic_graph\n"
+        "dev = torch.device('cuda:0'); torch.manual_seed(0)\n"
+        "g = synthetic_graph(30000, 400000, mirror=True, self_loops=False, device=dev, seed=1)\n"
+        "m = randomise_bn_(Model(dict(model_name='SAGE', num_layers=3, feat_dim=100, hidden_dim=256,\n"
+        "    label_dim=47, dropout_ratio=0.5, norm_type='batch', device=dev))).eval()\n"
+        "x = torch.randn(30000, 100, generator=torch.Generator().manual_seed(2)).to(dev)\n"
+        "with torch.no_grad():\n"
+        "    out = m.encoder.inference(G.FullNeighborLoader(g), x, log_softmax=True)\n"
+        "np.save(sys.argv[1], out.cpu().numpy())\n" % root)
+    outs = []
+    for flag in (None, "1"):
+        env = dict(os.environ)
+        env.pop("GLNN_S24", None)
+        if flag:
+            env["GLNN_S24"] = flag
+        path = str(tmp_path / f"out_{flag}.npy")
+        r = subprocess.run([sys.executable, "-c", script, path], env=env, capture_output=True, text=True,
+                           timeout=300)
+        assert r.returncode == 0, r.stderr[-1500:]
+        outs.append(np.load(path))
+    assert relerr(outs[1], outs[0]) < 1e-6
