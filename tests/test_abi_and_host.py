@@ -3,6 +3,7 @@ ctypes signatures cover them all, and the host-side logic (graph container, batc
 model surface) behaves like the reference's.  No kernel is launched here."""
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -174,3 +175,31 @@ def test_training_config_yaml_wins(tmp_path):
     y.write_text("global:\n  num_layers: 2\n  hidden_dim: 128\nd:\n  M:\n    hidden_dim: 64\n  N:\n")
     assert get_training_config(str(y), "M", "d") == {"num_layers": 2, "hidden_dim": 64, "model_name": "M"}
     assert get_training_config(str(y), "N", "d")["hidden_dim"] == 128
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """bench.py --impl reference (CPU, small workload): exactly ONE line on stdout, valid JSON, with
+    the keys the driver's contract names for the reference arm."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                        "--workload", "ogbn-arxiv", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "nodes/s" and d["value"] > 0
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["sample"] and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}
+    # a non-zero rank of a torchrun launch exits 0 without work and without output
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                        capture_output=True, text=True, timeout=120, cwd=ROOT,
+                        env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
