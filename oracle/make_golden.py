@@ -198,6 +198,40 @@ def teacher_train_case(name, n, e, f, hidden, c, layers, norm, lr, wd, lamb, ste
     print(name, "train losses", [round(x, 5) for x in losses], "eval", loss_eval, score_eval)
 
 
+def sage_train_case(name, n, e, f, hidden, c, layers, lr, wd, lamb, steps, seed):
+    """Block-wise GraphSAGE TRAINING steps through the reference's own `train_sage`
+    (train_and_eval.py:32-56) and SAGE.forward (models.py:101-119) over the shim's SAGEConv("gcn"):
+    ONE batch holding every training seed, FULL neighbourhoods at every hop (blocks built with the
+    shim's make_block, rule R4), so that no sampling randomness is involved; dropout 0, no norm."""
+    rng = np.random.default_rng(seed)
+    src, dst = rand_graph(rng, n, e, isolated=4, dup=15)
+    g = dgl_shim.graph((src, dst), num_nodes=n)
+    ref_utils.set_seed(seed)
+    conf = dict(model_name="SAGE", num_layers=layers, feat_dim=f, hidden_dim=hidden, label_dim=c,
+                dropout_ratio=0.0, norm_type="none", device="cpu")
+    model = ref_models.Model(conf)
+    gen = torch.Generator().manual_seed(seed + 1)
+    feats = torch.randn(n, f, generator=gen)
+    labels = torch.randint(0, c, (n,), generator=gen)
+    seeds = torch.randperm(n, generator=gen)[: n // 4]
+    indptr, indices = g.indptr.numpy(), g.indices.numpy()
+    blocks, cur = [], seeds.numpy()
+    for _ in range(layers):
+        input_nodes, _, (blk,) = dgl_shim.make_block(indptr, indices, np.asarray(cur))
+        blocks.insert(0, blk)
+        cur = input_nodes.numpy()
+    loader = [(torch.from_numpy(cur), seeds, blocks)]
+    init = sd_np(model, "init.")
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    crit = torch.nn.NLLLoss()
+    losses = [ref_te.train_sage(model, loader, feats, labels, crit, opt, lamb) for _ in range(steps)]
+    np.savez_compressed(
+        os.path.join(OUT, f"teacher_train_{name}.npz"), src=src, dst=dst, n=n, feats=feats.numpy(),
+        labels=labels.numpy(), seeds=seeds.numpy(), losses=np.array(losses), lr=lr, wd=wd, lamb=lamb,
+        num_layers=layers, hidden=hidden, **init, **sd_np(model, "final."))
+    print(name, "train_sage losses", [round(x, 5) for x in losses])
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # bit-stable fixtures
     if "--teacher-train-only" in sys.argv:   # later addition: leaves the older fixtures untouched
@@ -205,6 +239,10 @@ if __name__ == "__main__":
                            wd=1e-3, lamb=1.0, steps=4, seed=11)
         teacher_train_case("gcn3_lamb", n=120, e=600, f=8, hidden=24, c=3, layers=3, norm="none", lr=0.02,
                            wd=0.0, lamb=0.5, steps=3, seed=12)
+        sage_train_case("sage2", n=160, e=900, f=12, hidden=16, c=4, layers=2, lr=0.01, wd=5e-4,
+                        lamb=1.0, steps=4, seed=13)
+        sage_train_case("sage3_lamb", n=140, e=700, f=9, hidden=20, c=3, layers=3, lr=0.02, wd=0.0,
+                        lamb=0.7, steps=3, seed=14)
         sys.exit(0)
     # teacher: SAGE.inference through the reference's own batched layer-wise loop
     teacher_case("sage_bn3", "SAGE", n=300, e=2400, f=20, hidden=32, c=7, layers=3, norm="batch",
@@ -235,3 +273,7 @@ if __name__ == "__main__":
                        wd=1e-3, lamb=1.0, steps=4, seed=11)
     teacher_train_case("gcn3_lamb", n=120, e=600, f=8, hidden=24, c=3, layers=3, norm="none", lr=0.02,
                        wd=0.0, lamb=0.5, steps=3, seed=12)
+    sage_train_case("sage2", n=160, e=900, f=12, hidden=16, c=4, layers=2, lr=0.01, wd=5e-4,
+                    lamb=1.0, steps=4, seed=13)
+    sage_train_case("sage3_lamb", n=140, e=700, f=9, hidden=20, c=3, layers=3, lr=0.02, wd=0.0,
+                    lamb=0.7, steps=3, seed=14)

@@ -161,3 +161,22 @@ def test_gcn_train_step_oracle_matches_reference(case):
     out = torch.log_softmax(O.gcn_forward(indptr, indices, feats,
                                           [(p[f"layers.{l}.weight"], p[f"layers.{l}.bias"]) for l in range(L)]), 1)
     assert relerr(out, torch.from_numpy(d["out"]).double()) < 2e-5
+
+
+@pytest.mark.parametrize("case", ["teacher_train_sage2", "teacher_train_sage3_lamb"])
+def test_sage_block_train_step_oracle_matches_reference(case):
+    """Block-wise GraphSAGE TRAINING steps: the oracle's manual backward through
+    full-neighbour blocks + Adam against the reference's own `train_sage` / SAGE.forward (autograd over
+    the shim's SAGEConv): per-step losses and every parameter after the last step."""
+    d = load(case)
+    indptr, indices = O.csr_from_edges(d["src"], d["dst"], int(d["n"]))
+    L = int(d["num_layers"])
+    p = {f"layers.{l}.fc_neigh.{k}": torch.from_numpy(d[f"init.encoder.layers.{l}.fc_neigh.{k}"]).double().clone()
+         for l in range(L) for k in ("weight", "bias")}
+    st = O.init_adam_state(p)
+    feats, labels = torch.from_numpy(d["feats"]).double(), torch.from_numpy(d["labels"])
+    losses = [O.sage_block_train_step(indptr, indices, feats, labels, d["seeds"], p, st, float(d["lamb"]),
+                                      float(d["lr"]), float(d["wd"])) for _ in range(len(d["losses"]))]
+    assert np.allclose(losses, d["losses"], rtol=2e-6)
+    for k, v in p.items():
+        assert relerr(v, torch.from_numpy(d[f"final.encoder.{k}"]).double()) < 2e-5, k
