@@ -122,6 +122,38 @@ def test_student_step_hidden_not_multiple_of_4(dev, hidden, norm, kind):
         assert relerr(sd["encoder.norms.0.running_var"].cpu(), 0.9 + 0.1 * h0.var(0, unbiased=True)) < 1e-4
 
 
+@pytest.mark.parametrize("case", ["teacher_train_sage2", "teacher_train_sage3_lamb"])
+def test_sage_block_train_steps_match_reference(dev, case):
+    """`train_sage` (train_and_eval.py:32-56) on the B200 kernels with the device-side neighbour
+    loader in its deterministic configuration -- one batch holding every seed, unshuffled, full
+    neighbourhoods (fan-out -1) -- against the fixture produced by the reference's own `train_sage`
+    over full-neighbour blocks: per-step losses and the parameters after the last step."""
+    from glnn_b200 import graph as G, teacher_train as TT, train_and_eval as TE
+    from glnn_b200.models import Model
+    d = load(case)
+    L = int(d["num_layers"])
+    init = {k[len("init."):]: torch.from_numpy(np.array(v)) for k, v in d.items() if k.startswith("init.")}
+    model = Model(dict(model_name="SAGE", num_layers=L, feat_dim=d["feats"].shape[1],
+                       hidden_dim=int(d["hidden"]),
+                       label_dim=init["encoder.layers.%d.fc_neigh.weight" % (L - 1)].shape[0],
+                       dropout_ratio=0.0, norm_type="none", device=dev))
+    model.load_state_dict(init)
+    g = G.graph((d["src"], d["dst"]), num_nodes=int(d["n"])).to(dev)
+    feats, labels = torch.from_numpy(d["feats"]).to(dev), torch.from_numpy(d["labels"]).to(dev)
+    seeds = torch.from_numpy(d["seeds"])
+    loader = TT.NeighborLoader(g, seeds, [-1] * L, batch_size=seeds.numel(), shuffle=False)
+    opt = torch.optim.Adam(model.parameters(), lr=float(d["lr"]), weight_decay=float(d["wd"]))
+    losses = [TE.train_sage(model, loader, feats, labels, torch.nn.NLLLoss(), opt, float(d["lamb"]))
+              for _ in range(len(d["losses"]))]
+    assert np.allclose(losses, d["losses"], rtol=1e-4)
+    sd = model.state_dict()
+    for k, v in d.items():
+        if k.startswith("final."):
+            assert relerr_q(sd[k[len("final."):]].cpu(), v, 0.99) < 1e-3, k
+            assert relerr(sd[k[len("final."):]].cpu(), v) < 5e-2, k
+
+
+# ---- experimental kernels last: a device fault here cannot affect any other test ----
 @pytest.mark.parametrize("d,zero_frac", [(256, 0.55), (200, 0.7), (256, 0.0)])
 def test_s24_sparse_rows_match_q24_gather(dev, d, zero_frac):
     """EXPERIMENTAL sparse rows: the s24 copy of a post-ReLU q24 matrix
@@ -195,34 +227,3 @@ def test_s24_layer_planner_opt_in_matches_default(dev, tmp_path):
         assert r.returncode == 0, r.stderr[-1500:]
         outs.append(np.load(path))
     assert relerr(outs[1], outs[0]) < 1e-6
-
-
-@pytest.mark.parametrize("case", ["teacher_train_sage2", "teacher_train_sage3_lamb"])
-def test_sage_block_train_steps_match_reference(dev, case):
-    """`train_sage` (train_and_eval.py:32-56) on the B200 kernels with the device-side neighbour
-    loader in its deterministic configuration -- one batch holding every seed, unshuffled, full
-    neighbourhoods (fan-out -1) -- against the fixture produced by the reference's own `train_sage`
-    over full-neighbour blocks: per-step losses and the parameters after the last step."""
-    from glnn_b200 import graph as G, teacher_train as TT, train_and_eval as TE
-    from glnn_b200.models import Model
-    d = load(case)
-    L = int(d["num_layers"])
-    init = {k[len("init."):]: torch.from_numpy(np.array(v)) for k, v in d.items() if k.startswith("init.")}
-    model = Model(dict(model_name="SAGE", num_layers=L, feat_dim=d["feats"].shape[1],
-                       hidden_dim=int(d["hidden"]),
-                       label_dim=init["encoder.layers.%d.fc_neigh.weight" % (L - 1)].shape[0],
-                       dropout_ratio=0.0, norm_type="none", device=dev))
-    model.load_state_dict(init)
-    g = G.graph((d["src"], d["dst"]), num_nodes=int(d["n"])).to(dev)
-    feats, labels = torch.from_numpy(d["feats"]).to(dev), torch.from_numpy(d["labels"]).to(dev)
-    seeds = torch.from_numpy(d["seeds"])
-    loader = TT.NeighborLoader(g, seeds, [-1] * L, batch_size=seeds.numel(), shuffle=False)
-    opt = torch.optim.Adam(model.parameters(), lr=float(d["lr"]), weight_decay=float(d["wd"]))
-    losses = [TE.train_sage(model, loader, feats, labels, torch.nn.NLLLoss(), opt, float(d["lamb"]))
-              for _ in range(len(d["losses"]))]
-    assert np.allclose(losses, d["losses"], rtol=1e-4)
-    sd = model.state_dict()
-    for k, v in d.items():
-        if k.startswith("final."):
-            assert relerr_q(sd[k[len("final."):]].cpu(), v, 0.99) < 1e-3, k
-            assert relerr(sd[k[len("final."):]].cpu(), v) < 5e-2, k
