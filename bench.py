@@ -174,7 +174,91 @@ def cpu_teacher_rate(indptr, indices, n, dims, stride, steps, warmup, batched_bs
     return len(rows) / dt, dt, len(rows)
 
 
+def bench_config(workload, n, e, dims, world):
+    """config of the JSON line: ONE builder for both arms so that the driver's same_config holds."""
+    return {"workload": f"{workload} SAGE teacher full-graph forward + log_softmax",
+            "nodes": n, "edges": e, "dims": dims, "norm": "batch(eval)",
+            "parallelism": "single GPU" if world == 1 else
+            f"dst-row sharded x{world}: per-layer exchange of the q24 layer output by peer pushes "
+            "into symmetric-memory replicas over NVLink (no NCCL on the forward), output left "
+            "sharded by rows",
+            "l2": "inputs (features 0.98 GB, CSR 0.5 GB, activations 2.5 GB) far exceed the "
+                  "126 MB L2; no flush needed"}
+
+
+def bench_model(workload, device):
+    """The benchmark's SAGE teacher: same seed, same init and BN buffers in both arms and on every
+    rank (built on the CPU generator, then moved)."""
+    import torch
+    from glnn_b200.models import Model
+    from glnn_b200.workloads import randomise_bn_
+    dims = DIMS[workload]
+    torch.manual_seed(0)
+    return randomise_bn_(Model(dict(model_name="SAGE", num_layers=3, feat_dim=dims[0],
+                                    hidden_dim=dims[1], label_dim=dims[3], dropout_ratio=0.5,
+                                    norm_type="batch", device=device)))
+
+
+def oracle_params(model):
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    L = model.encoder.num_layers
+    layers = [(sd[f"encoder.layers.{l}.fc_neigh.weight"], sd[f"encoder.layers.{l}.fc_neigh.bias"])
+              for l in range(L)]
+    norms = [tuple(sd[f"encoder.norms.{l}.{k}"] for k in ("weight", "bias", "running_mean",
+                                                           "running_var")) for l in range(L - 1)]
+    return layers, norms
+
+
+def use_all_host_threads(torch):
+    # torchrun exports OMP_NUM_THREADS=1 for its workers: the CPU legs take every core they may use
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, RuntimeError):
+        pass
+    return torch.get_num_threads()
+
+
+def oracle_full_forward(indptr, indices, feats_cpu, layers, norms):
+    """The CPU port's full-size forward (oracle/glnn_oracle.py: one SpMM + GEMM per layer, the
+    formulation equal to the reference's per-batch loop in eval mode) -> (log-probs, seconds)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import glnn_oracle as O
+    t0 = time.perf_counter()
+    want = torch.log_softmax(O.sage_inference(indptr, indices, feats_cpu, layers, norms), 1)
+    return want, time.perf_counter() - t0
+
+
+def parity_of(got, want, rtol=1e-4, atol=1e-5):
+    """SURVEY 8d gate on an output block: (max|a-b|, max|b|, #elements outside allclose, #elements,
+    #rows whose argmax differs) -- additive over row shards."""
+    import torch
+    got, want = got.double(), want.double()
+    diff = (got - want).abs()
+    viol = diff > (atol + rtol * want.abs())
+    return [float(diff.max()), float(want.abs().max()), int(viol.sum()), diff.numel(),
+            int((got.argmax(1) != want.argmax(1)).sum())]
+
+
+def parity_block(parts, seconds, cores):
+    """parts: parity_of() of every row shard."""
+    dmax = max(p[0] for p in parts)
+    bmax = max(p[1] for p in parts)
+    nviol, numel = sum(p[2] for p in parts), sum(p[3] for p in parts)
+    return {"against": "CPU oracle port, full-size forward on the same graph / features / weights "
+                       f"({seconds:.1f} s on {cores} host threads, outside the timed region)",
+            "output": "log-probabilities [N, C] (evaluate(), train_and_eval.py:97-98)",
+            "max_rel": dmax / max(bmax, 1e-30), "max_abs": dmax,
+            "allclose_rtol1e-4_atol1e-5": nviol == 0, "violating_elements": nviol, "elements": numel,
+            "argmax_mismatch_rows": sum(p[4] for p in parts)}
+
+
 def run_reference(args):
+    """Reference arm: the reference's algorithm for this path on the host cores.  The reference
+    itself (Python over DGL 0.6.1) cannot be installed (no DGL wheel, no network), so this is the
+    oracle port -- kind "port".  One FULL-SIZE forward is always run (calibration, reported); the
+    timed steps are full-size too when K + W of them fit in ~4 minutes, else a 1-in-`stride`
+    destination-row sample through all layers (every layer still gathers from full-size matrices)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -184,34 +268,49 @@ def run_reference(args):
     warnings.filterwarnings("ignore")
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import glnn_oracle as O
-    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
-    try:
-        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
-    except (AttributeError, RuntimeError):
-        pass
+    cores = use_all_host_threads(torch)
     workload = args.workload
     s, src, dst = _cpu_problem(workload)
     n = s["n"]
     indptr, indices = O.csr_from_edges(src.numpy(), dst.numpy(), n)
     del src, dst
     dims = DIMS[workload]
-    stride = 16 if n > 1000000 else 2
-    cores = torch.get_num_threads()
-    rate, dt, rows = cpu_teacher_rate(indptr, indices, n, dims, stride, args.steps, args.warmup)
-    brate, bdt, brows = cpu_teacher_rate(indptr, indices, n, dims, stride * 8, 1, 0,
+    model = bench_model(workload, "cpu").eval()
+    layers, norms = oracle_params(model)
+    torch.manual_seed(0)
+    feats = torch.randn(n, dims[0])
+    _, full_s = oracle_full_forward(indptr, indices, feats, layers, norms)
+    budget = 240.0
+    if full_s * (args.steps + args.warmup) <= budget:
+        for _ in range(args.warmup):
+            oracle_full_forward(indptr, indices, feats, layers, norms)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            oracle_full_forward(indptr, indices, feats, layers, norms)
+        dt = (time.perf_counter() - t0) / args.steps
+        rate = n / dt
+        sample = (f"the full workload: oracle port of SAGE.inference + log_softmax over all {n} nodes, "
+                  f"full-graph SpMM+GEMM formulation (torch CPU, {cores} threads), {dt:.2f} s/step")
+    else:
+        stride = max(2, int(np.ceil(full_s * (args.steps + args.warmup) / budget)))
+        rate, dt, rows = cpu_teacher_rate(indptr, indices, n, dims, stride, args.steps, args.warmup)
+        sample = (f"every {stride}th destination row ({rows} rows, all 3 layers, gathering from "
+                  f"full-size [N,d] matrices; torch CPU, {cores} threads) because {args.steps}+"
+                  f"{args.warmup} full-size forwards of {full_s:.1f} s exceed the time budget; the "
+                  f"full-size forward itself ran once: {n / full_s:.0f} nodes/s")
+    brate, bdt, brows = cpu_teacher_rate(indptr, indices, n, dims, 128 if n > 1000000 else 16, 1, 0,
                                          batched_bs=s["batch_size"])
-    sample = (f"oracle port of SAGE.inference on every {stride}th destination row ({rows} rows, all "
-              f"3 layers, gathering from full-size [N,d] matrices), full-graph SpMM+GEMM formulation "
-              f"(torch CPU, {cores} threads); the reference's per-batch block loop (bs "
-              f"{s['batch_size']}) on {brows} rows ran at {brate:.0f} nodes/s")
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "nodes/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": f"{workload} SAGE teacher forward (CPU sample)",
-                                        "nodes": n, "edges": int(indptr[-1]), "dims": dims},
+        "data": "synthetic", "config": bench_config(workload, n, int(indptr[-1]), dims, args.gpus),
         "cpu_baseline": {"value": rate, "unit": "nodes/s", "cores": cores, "kind": "port",
-                         "sample": sample, "batched_value": brate},
+                         "sample": sample, "full_forward_s": full_s,
+                         "full_forward_nodes_per_s": n / full_s,
+                         "batched_value": brate,
+                         "batched_note": f"the reference's per-batch block loop (bs {s['batch_size']}) "
+                                         f"on {brows} rows"},
         "e2e": {"value": rate, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -315,23 +414,39 @@ def teacher_kernel_breakdown(g, feats, model, iters, torch):
     return rows
 
 
-def student_step_rate(dev, torch, steps=20, warmup=3, world=1):
-    """Distillation steps of the products student MLP3w8 (100 -> 2048 -> 2048 -> 47, bs 4096, BN,
-    dropout 0.2, Adam) on synthetic teacher log-probabilities: KL pass of `steps` steps.  With
-    world > 1 the same global batches are split over the ranks (glnn_mlp_train_pass_dp)."""
-    from glnn_b200 import mlp_engine
+def _sustained_tc_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained") or d["bf16_tflops"]), "measured, sustained (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1400.0, "fallback (B200_PROFILING.md: ~1.4 PF/s sustained)"
+
+
+def student_block(dev, torch, name="MLP3w8", f=100, h=2048, c=47, bs=4096, p_drop=0.2, steps=20,
+                  warmup=3, world=1, cpu_steps=4, label="ogbn-products student"):
+    """The student half of the metric (BASELINE.json: "student-distill step"), one block per student:
+    device-timed KL + Adam steps (value), the tensor roofline of the step, the CPU oracle port's
+    train_mini_batch on the host cores (cpu_baseline), the same pass through the public
+    train_mini_batch with HOST features / teacher log-probabilities copied in every pass (e2e), and
+    the first-step loss against the oracle (parity).  With world > 1 the same global batches are
+    split over the ranks (glnn_mlp_train_pass_dp) and only the device-timed part is reported."""
+    from glnn_b200 import mlp_engine, train_and_eval as TE
     from glnn_b200.models import Model
     torch.manual_seed(0)
-    f, h, c, bs = 100, 2048, 47, 4096
-    n = bs * 64
-    model = Model(dict(model_name="MLP3w8", num_layers=3, feat_dim=f, hidden_dim=h, label_dim=c,
-                       dropout_ratio=0.2, norm_type="batch", device=dev)).train()
+    n = bs * max(steps, 16)
+    model = Model(dict(model_name=name, num_layers=3, feat_dim=f, hidden_dim=h, label_dim=c,
+                       dropout_ratio=p_drop, norm_type="batch", device=dev)).train()
+    init = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
     if world > 1:
         mlp_engine.enable_data_parallel(model.encoder)
     opt = torch.optim.Adam(model.parameters(), lr=0.01)
-    x = torch.randn(n, f, device=dev)
-    t = torch.log_softmax(torch.randn(n, c, device=dev), 1)
-    idx = torch.randperm(n)[: steps * bs].view(steps, bs).to(dev)
+    gen = torch.Generator().manual_seed(1)
+    x_h = torch.randn(n, f, generator=gen)
+    t_h = torch.log_softmax(torch.randn(n, c, generator=gen), 1)
+    x, t = x_h.to(dev), t_h.to(dev)
+    idx_h = torch.randperm(n, generator=gen)[: steps * bs].view(steps, bs)
+    idx = idx_h.to(dev)
     for _ in range(warmup):
         mlp_engine.train_pass(model.encoder, opt, x, t, idx[:2], 1.0)
     ms = _event_ms(lambda: mlp_engine.train_pass(model.encoder, opt, x, t, idx, 1.0), 2, torch)
@@ -344,13 +459,86 @@ def student_step_rate(dev, torch, steps=20, warmup=3, world=1):
         t_ms = torch.tensor([per_step], device=dev)
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         per_step = float(t_ms)
-    return {"config": "MLP3w8 100-2048-2048-47 bs4096 KL+Adam step (ogbn-products student)"
-                      + (f", data parallel x{world}: BN statistics, gradient reduce-scatter + Adam + "
-                         "parameter all-gather fused into the step's kernels over peer memory"
-                         if world > 1 else ""),
-            "value": bs / (per_step * 1e-3), "unit": "nodes/s", "ms_per_step": per_step,
-            "tflops": flops / (per_step * 1e-3) / 1e12, "params": P,
-            "launches_per_step": 23 if world == 1 else 25}
+    tc_peak, tc_src = _sustained_tc_peak()
+    mma_tflops = 3.0 * flops / (per_step * 1e-3) / 1e12 / world   # per GPU: bf16x3 = 3 bf16 MMAs per fp32 MAC
+    blk = {"config": f"{name} {f}-{h}-{h}-{c} bs{bs} KL+Adam step ({label})"
+                     + (f", data parallel x{world}: BN statistics, gradient reduce-scatter + Adam + "
+                        "parameter all-gather fused into the step's kernels over peer memory"
+                        if world > 1 else ""),
+           "metric": "nodes/sec student-distill step", "value": bs / (per_step * 1e-3), "unit": "nodes/s",
+           "ms_per_step": per_step, "tflops_fp32_equivalent": flops / (per_step * 1e-3) / 1e12,
+           "params": P, "launches_per_step": 23 if world == 1 else 25, "dtype": "f32 (bf16x3 on tcgen05)",
+           "roofline": {"bound": "tensor", "achieved": mma_tflops, "peak": tc_peak, "unit": "TFLOP/s",
+                        "frac": mma_tflops / tc_peak, "peak_source": tc_src,
+                        "algorithmic_flops_per_step": flops,
+                        "note": "achieved = 3 bf16 MMA products (hi*hi + hi*lo + lo*hi) per fp32 "
+                                "multiply-add of the step's algorithmic flops, per GPU"}}
+    if world > 1:
+        return blk
+    # ---- parity: first step's loss from the initial state against the fp64 oracle (dropout off)
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import glnn_oracle as O
+        m2 = Model(dict(model_name=name, num_layers=3, feat_dim=f, hidden_dim=h, label_dim=c,
+                        dropout_ratio=0.0, norm_type="batch", device=dev)).train()
+        m2.load_state_dict(init)
+        o2 = torch.optim.Adam(m2.parameters(), lr=0.01)
+        got = mlp_engine.train_pass(m2.encoder, o2, x, t, idx[:1], 1.0).item()
+        p64 = {k[len("encoder."):]: (v.double() if v.is_floating_point() else v.clone()) for k, v in init.items()}
+        logits, _ = O.mlp_forward(x_h.double()[idx_h[0]], p64, 3, "batch", True)
+        want, _ = O.loss_and_dlogits(logits, t_h.double()[idx_h[0]], "kl", 1.0)
+        blk["parity"] = {"first_step_kl_loss": got, "oracle_fp64": float(want),
+                         "rel_err": abs(got - float(want)) / abs(float(want)),
+                         "note": "gradients / Adam / eval outputs: tests/test_gpu_student.py"}
+        del m2, o2
+    except Exception as ex:
+        blk["parity"] = {"error": repr(ex)}
+    # ---- e2e: the public train_mini_batch with host inputs copied in every pass
+    try:
+        x_p, t_p = x_h[: steps * bs].pin_memory(), t_h[: steps * bs].pin_memory()
+        crit = torch.nn.KLDivLoss(reduction="batchmean", log_target=True)
+
+        def e2e_pass():
+            xd, td = x_p.to(dev, non_blocking=True), t_p.to(dev, non_blocking=True)
+            return TE.train_mini_batch(model, xd, td, bs, crit, opt, 1.0)   # returns the host float
+        e2e_pass()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            e2e_pass()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        blk["e2e"] = {"value": steps * bs / dt, "unit": "nodes/s", "ms_per_step": dt * 1e3 / steps,
+                      "h2d_bytes_per_step": int((x_p.numel() + t_p.numel()) * 4 / steps),
+                      "d2h_bytes_per_step": 4.0 / steps,
+                      "note": f"one pass = {steps} steps through train_and_eval.train_mini_batch: pinned "
+                              "host features + teacher log-probabilities copied in, CPU randperm, loss "
+                              "read back once per pass; wall clock"}
+    except Exception as ex:
+        blk["e2e"] = {"error": repr(ex)}
+    # ---- CPU baseline: the oracle port's train_mini_batch on the host cores
+    try:
+        import warnings
+        warnings.filterwarnings("ignore")
+        cores = use_all_host_threads(torch)
+        p32 = {k[len("encoder."):]: v.clone() for k, v in init.items()}
+        st = O.init_adam_state(p32)
+        O.train_mini_batch(p32, st, x_h, t_h, "kl", bs, idx_h[:1], 1.0, 3, "batch", 0.0, 0.01, 0.0)
+        t0 = time.perf_counter()
+        O.train_mini_batch(p32, st, x_h, t_h, "kl", bs, idx_h[1:1 + cpu_steps], 1.0, 3, "batch", 0.0, 0.01, 0.0)
+        dt = (time.perf_counter() - t0) / cpu_steps
+        blk["cpu_baseline"] = {"value": bs / dt, "unit": "nodes/s", "cores": cores, "kind": "port",
+                               "sample": f"{cpu_steps} KL + Adam steps of the oracle port's "
+                                         f"train_mini_batch (train_and_eval.py:59-86; torch CPU fp32, "
+                                         f"manual backward), {dt * 1e3:.1f} ms/step"}
+    except Exception as ex:
+        blk["cpu_baseline"] = {"error": repr(ex)}
+    return blk
+
+
+def student_step_rate(dev, torch, steps=20, warmup=3, world=1):
+    return student_block(dev, torch, steps=steps, warmup=warmup, world=world)
 
 
 def other_configs(dev, torch, hbm_peak):
@@ -397,26 +585,12 @@ def other_configs(dev, torch, hbm_peak):
         entry["cpu_port_error"] = repr(ex)
     out["ogbn-arxiv SAGE forward"] = entry
     # ---- configs[2]: arxiv students, bs 512, one soft-label (KL) pass of 100 steps
-    x = feats
-    t = torch.log_softmax(torch.randn(n, dims[3], device=dev), 1)
     for name, hidden, p_drop in (("MLP", 256, 0.2), ("MLP3w4", 1024, 0.5)):
-        torch.manual_seed(0)
-        st = Model(dict(model_name=name, num_layers=3, feat_dim=dims[0], hidden_dim=hidden,
-                        label_dim=dims[3], dropout_ratio=p_drop, norm_type="batch", device=dev)).train()
-        opt = torch.optim.Adam(st.parameters(), lr=0.01)
-        steps, bs = 100, 512
-        idx = torch.randperm(n)[: steps * bs].view(steps, bs).to(dev)
-        mlp_engine.train_pass(st.encoder, opt, x, t, idx[:4], 1.0)
-        ms = _event_ms(lambda: mlp_engine.train_pass(st.encoder, opt, x, t, idx, 1.0), 2, torch) / steps
-        sw, w1 = dims[0] * hidden + hidden * hidden + hidden * dims[3], dims[0] * hidden
-        st.eval()
-        ev_ms = _event_ms(lambda: mlp_engine.eval_forward(st.encoder, x), 3, torch)
-        out[f"ogbn-arxiv student {name} (3x{hidden}, bs 512, KL + Adam)"] = {
-            "ms_per_step": round(ms, 5), "nodes_per_s": bs / (ms * 1e-3),
-            "TFLOPs_fp32_equivalent": 2.0 * bs * (3 * sw - w1) / (ms * 1e-3) / 1e12,
-            "eval_all_nodes_ms": round(ev_ms, 4), "eval_nodes_per_s": n / (ev_ms * 1e-3),
-            "note": "one CUDA graph of 23 launches per step; at bs 512 the step is launch/latency-bound"}
-    del g, feats, x, t
+        blk = student_block(dev, torch, name=name, f=dims[0], h=hidden, c=dims[3], bs=512, p_drop=p_drop,
+                            steps=100, cpu_steps=20, label="ogbn-arxiv student")
+        blk["note"] = "one CUDA graph of 23 launches per step; at bs 512 the step is launch/latency-bound"
+        out[f"ogbn-arxiv student {name} (3x{hidden}, bs 512, KL + Adam)"] = blk
+    del g, feats
     # ---- configs[0]: GCN teacher on a cora-shaped graph (full-batch train step + evaluate)
     s = SHAPES["cora"]
     g = dataset_graph("cora", device=dev, seed=0)
@@ -533,8 +707,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     from glnn_b200 import _lib, dist_teacher as DT, graph as G, ops
     from glnn_b200.models import Model
-    from glnn_b200.workloads import (SHAPES, dataset_graph, randomise_bn_, sage_bytes_per_forward,
-                                     sage_gather_bytes)
+    from glnn_b200.workloads import SHAPES, dataset_graph, sage_bytes_per_forward, sage_gather_bytes
     _lib.load()
     workload = args.workload
     s = SHAPES[workload]
@@ -543,10 +716,8 @@ def run_b200(args):
 
     g = dataset_graph(workload, device=dev, seed=0)
     e = g.num_edges()
+    model = bench_model(workload, dev).eval()
     torch.manual_seed(0)
-    model = randomise_bn_(Model(dict(model_name="SAGE", num_layers=3, feat_dim=dims[0],
-                                     hidden_dim=dims[1], label_dim=dims[3], dropout_ratio=0.5,
-                                     norm_type="batch", device=dev))).eval()
     feats = torch.randn(n, dims[0], device=dev)
     loader = G.FullNeighborLoader(g)
     alg_bytes = sage_bytes_per_forward(n, e, dims)
@@ -599,6 +770,40 @@ def run_b200(args):
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t)
+
+    # ---- parity of the timed path's output at full size (outside the timed region): rank 0 runs the
+    # CPU oracle port once on the same graph / features / weights, every rank checks its own rows
+    parity = None
+    if not args.light and not args.no_parity:
+        want = torch.empty(n, dims[3], dtype=torch.float32, device=dev)
+        secs = torch.zeros(2, device=dev)
+        if rank == 0:
+            import warnings
+            warnings.filterwarnings("ignore")
+            cores = use_all_host_threads(torch)
+            layers_c, norms_c = oracle_params(model)
+            want_c, t_full = oracle_full_forward(g.indptr.cpu().numpy().astype("int64"),
+                                                 g.indices.cpu().numpy().astype("int64"), feats.cpu(),
+                                                 layers_c, norms_c)
+            want.copy_(want_c)
+            secs[0], secs[1] = t_full, cores
+            del want_c
+        if world > 1:
+            dist.broadcast(want, 0)
+            dist.broadcast(secs, 0)
+            mine = sg.local_rows_of(out)
+            part = parity_of(mine, want[sg.r0:sg.r0 + sg.rows])
+            parts = [None] * world
+            dist.all_gather_object(parts, part)
+        else:
+            parts = [parity_of(out, want)]
+        parity = parity_block(parts, float(secs[0]), int(secs[1]))
+        cpu_full = {"value": n / float(secs[0]), "unit": "nodes/s", "cores": int(secs[1]), "kind": "port",
+                    "sample": f"the full workload, one forward: oracle port of SAGE.inference + "
+                              f"log_softmax over all {n} nodes (full-graph SpMM+GEMM per layer, torch "
+                              f"CPU), {float(secs[0]):.1f} s"}
+        del want
+        torch.cuda.empty_cache()
 
     if world > 1:  # per-phase device times of one sharded forward on every rank (diagnostic)
         tm = []
@@ -688,13 +893,7 @@ def run_b200(args):
         "metric": METRIC, "value": n / (ms * 1e-3), "unit": "nodes/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": f"{workload} SAGE teacher full-graph forward + log_softmax",
-                   "nodes": n, "edges": e, "dims": dims, "norm": "batch(eval)",
-                   "parallelism": "single GPU" if world == 1 else f"dst-row sharded x{world}, one NCCL "
-                   "all-gather per layer exchange, output left sharded by rows",
-                   "l2": "inputs (features 0.98 GB, CSR 0.5 GB, activations 2.5 GB) far exceed the "
-                         "126 MB L2; no flush needed"},
+        "data": "synthetic", "config": bench_config(workload, n, e, dims, world),
         "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "nodes/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "overlap": "copy streams: step i+1 upload / step i-1 download overlap step i compute "
@@ -705,6 +904,9 @@ def run_b200(args):
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clk,
     }
+    if parity is not None:
+        line["parity"] = parity
+        line["cpu_baseline"] = cpu_full
     if world > 1:
         line["shards"] = gathered
         line["student"] = student
@@ -737,20 +939,20 @@ def run_b200(args):
             line["student"] = student_step_rate(dev, torch)
         except Exception as ex:  # keep the teacher line even if the student leg fails
             line["student"] = {"error": repr(ex)}
-        # CPU baseline on the host cores: same graph, bounded row sample
-        try:
-            import warnings
-            warnings.filterwarnings("ignore")
-            indptr = g.indptr.cpu().numpy().astype("int64")
-            indices = g.indices.cpu().numpy().astype("int64")
-            stride = 16 if n > 1000000 else 2
-            rate, dt, nrows = cpu_teacher_rate(indptr, indices, n, dims, stride, 2, 1)
-            line["cpu_baseline"] = {
-                "value": rate, "unit": "nodes/s", "cores": torch.get_num_threads(), "kind": "port",
-                "sample": f"oracle port (full-graph SpMM+GEMM per layer, torch CPU) on every "
-                          f"{stride}th destination row = {nrows} rows x 3 layers, {dt:.2f} s/step"}
-        except Exception as ex:
-            line["cpu_baseline"] = {"error": repr(ex)}
+        if "cpu_baseline" not in line:  # --no-parity: bounded row sample instead of the full forward
+            try:
+                import warnings
+                warnings.filterwarnings("ignore")
+                indptr = g.indptr.cpu().numpy().astype("int64")
+                indices = g.indices.cpu().numpy().astype("int64")
+                stride = 16 if n > 1000000 else 2
+                rate, dt, nrows = cpu_teacher_rate(indptr, indices, n, dims, stride, 2, 1)
+                line["cpu_baseline"] = {
+                    "value": rate, "unit": "nodes/s", "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": f"oracle port (full-graph SpMM+GEMM per layer, torch CPU) on every "
+                              f"{stride}th destination row = {nrows} rows x 3 layers, {dt:.2f} s/step"}
+            except Exception as ex:
+                line["cpu_baseline"] = {"error": repr(ex)}
         del g, feats, loader
         torch.cuda.empty_cache()
         try:
@@ -789,6 +991,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="ogbn-products", choices=sorted(DIMS))
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true",
+                    help="skip the full-size CPU oracle forward (parity block, cpu_baseline)")
     ap.add_argument("--light", action="store_true",
                     help="timed region only (used under ncu): no e2e / breakdown / student / CPU legs")
     args = ap.parse_args()

@@ -75,6 +75,7 @@ SIGNATURES = {
     "glnn_s24_row_words": (c_i64, [C.c_int]),
     "glnn_compact_s24": (C.c_int, [c_vp, c_i64, c_i64, C.c_int, c_vp, c_i64, c_vp, c_vp]),
     "glnn_spmm_csr_s24": (C.c_int, [C.POINTER(SpmmDesc), c_vp, c_i64, c_vp, c_vp]),
+    "glnn_exp_spmm_tma_q24": (C.c_int, [C.POINTER(SpmmDesc), C.c_int, c_vp]),
     "glnn_bn_fold_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_f32, c_vp, c_vp, C.c_int, c_vp]),
     "glnn_log_softmax_f32": (C.c_int, [c_vp, c_i64, c_vp, c_i64, c_i64, C.c_int, c_vp]),
     "glnn_nll_acc_f32": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, c_i64, c_vp, c_vp]),
@@ -84,6 +85,7 @@ SIGNATURES = {
     "glnn_mlp_train_pass": (C.c_int, [C.POINTER(MlpDesc), c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64,
                                       C.POINTER(AdamHParams), c_vp, c_i64, c_vp, C.c_int, c_vp, c_i64,
                                       c_i64, c_vp, C.c_uint64, c_f32, c_vp, c_vp, c_i64, c_vp]),
+    "glnn_adam_step_f32": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, C.POINTER(AdamHParams), c_vp]),
     "glnn_mlp_dp_control_bytes": (c_i64, [C.POINTER(MlpDesc), c_i64, C.c_int]),
     "glnn_mlp_dp_flat_count": (c_i64, [C.POINTER(MlpDesc), C.c_int]),
     "glnn_mlp_dp_init": (C.c_int, [c_vp, c_i64, c_vp]),

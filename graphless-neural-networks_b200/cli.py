@@ -79,12 +79,28 @@ def _result_dir(args, base, leaf):
     raise ValueError(f"Unknown experiment setting! {args.exp_setting}")
 
 
+# Teacher log-probabilities of teacher runs made in THIS process, keyed by their output directory
+# (SURVEY.md 8f row 3): a student run that follows in the same process (distill_pipeline, or two
+# main() calls) takes the device tensor from here instead of reading out.npz back from disk.  The
+# file is still written -- it is the reference's hand-off format (train_teacher.py:296-297).
+_OUT_T_ON_DEVICE = {}
+
+
+def _resolve_device(index):
+    """The reference's --device default is -1 = CPU (train_teacher.py:26).  This implementation has no
+    CPU path (every hot function is a CUDA kernel), so -1 means "the current CUDA device" here, and a
+    machine without CUDA is refused up front -- before any output directory is created."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("glnn_b200 needs a CUDA device (B200, sm_100a): there is no CPU path. "
+                           "Run the reference itself for a CPU run.")
+    return torch.device(f"cuda:{index}") if index >= 0 else torch.device("cuda", torch.cuda.current_device())
+
+
 def run(args, role):
     """One seed.  Returns [score_test] (tran) or [score_test_tran, score_test_ind] (ind)."""
     student = role == "student"
     set_seed(args.seed)
-    device = torch.device(f"cuda:{args.device}") if torch.cuda.is_available() and args.device >= 0 \
-        else "cpu"
+    device = _resolve_device(args.device)
 
     # the reference rewrites output_path (and the model name) for the ablations only when seed == 0,
     # so that repeat_run's later seeds inherit the rewritten values
@@ -139,9 +155,14 @@ def run(args, role):
     evaluator = get_evaluator(conf["dataset"])
     if student:
         criterion_t = torch.nn.KLDivLoss(reduction="batchmean", log_target=True)
-        out_t = load_out_t(out_t_dir)
+        out_t = _OUT_T_ON_DEVICE.get(str(out_t_dir))
+        if out_t is None:
+            out_t = load_out_t(out_t_dir)
+        else:
+            logger.info("teacher log-probabilities taken from device memory (same-process teacher run)")
         for name, idx in (("train", idx_train), ("val", idx_val), ("test", idx_test)):
-            logger.debug(f"teacher score on {name} data: {evaluator(out_t[idx], labels[idx])}")
+            logger.debug(f"teacher score on {name} data: "
+                         f"{evaluator(out_t[idx.to(out_t.device)], labels[idx].to(out_t.device))}")
 
     def propagate(x, graph):
         dev = device if device != "cpu" else x.device
@@ -185,6 +206,9 @@ def run(args, role):
     logger.info(f"# params {sum(p.numel() for p in model.parameters())}")
 
     np.savez(output_dir.joinpath("out"), out.detach().cpu().numpy())  # out.npz, key arr_0
+    if not student:
+        _OUT_T_ON_DEVICE.clear()   # one teacher output at a time stays resident
+        _OUT_T_ON_DEVICE[str(output_dir)] = out.detach()
     if args.save_results:
         np.savez(output_dir.joinpath("loss_and_score"), np.array(loss_and_score))
         torch.save(model.state_dict(), output_dir.joinpath("model.pth"))
@@ -192,6 +216,12 @@ def run(args, role):
         with open(output_dir.parent.joinpath("min_cut_loss"), "a+") as f:
             f.write(f"{compute_min_cut_loss(g, out) :.4f}\n")
     return score_lst
+
+
+def distill_pipeline(teacher_argv, student_argv):
+    """train_teacher.py then train_student.py in one process: the teacher's log-probabilities stay on
+    the device between the two (out.npz is still written).  Returns (teacher line, student line)."""
+    return main("teacher", teacher_argv), main("student", student_argv)
 
 
 def main(role, argv=None):

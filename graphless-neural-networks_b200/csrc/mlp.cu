@@ -770,21 +770,29 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
   }
 }
 
-// torch.optim.Adam (amsgrad=False, L2 weight decay) over the flat parameter buffer.
+// torch.optim.Adam (amsgrad=False, L2 weight decay) over the flat parameter buffer.  Hyper-parameters
+// and the step number come from the pass's device state (pp, ctr: the fused student step) or, when pp
+// is null, by value (glnn_adam_step_f32: teacher training, the injected-gradient parity test).
+struct AdamByValue {
+  float lr, beta1, beta2, eps, wd;
+  int64_t step;  // 1-based step number of this update
+};
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    int64_t n, const PassParams* __restrict__ pp,
-                                                   const int* __restrict__ ctr) {
+                                                   const int* __restrict__ ctr, const AdamByValue hv) {
   __shared__ float s_step, s_bc2;
+  const float lr = pp ? pp->lr : hv.lr;
+  const float b1 = pp ? pp->beta1 : hv.beta1, b2 = pp ? pp->beta2 : hv.beta2;
+  const float eps = pp ? pp->eps : hv.eps, wd = pp ? pp->wd : hv.wd;
   if (threadIdx.x == 0) {
-    const double t = static_cast<double>(pp->step0 + *ctr + 1);
-    const double bc1 = 1.0 - pow(static_cast<double>(pp->beta1), t);
-    const double bc2 = 1.0 - pow(static_cast<double>(pp->beta2), t);
-    s_step = static_cast<float>(static_cast<double>(pp->lr) / bc1);
+    const double t = static_cast<double>(pp ? pp->step0 + *ctr + 1 : hv.step);
+    const double bc1 = 1.0 - pow(static_cast<double>(b1), t);
+    const double bc2 = 1.0 - pow(static_cast<double>(b2), t);
+    s_step = static_cast<float>(static_cast<double>(lr) / bc1);
     s_bc2 = static_cast<float>(sqrt(bc2));
   }
   __syncthreads();
-  const float b1 = pp->beta1, b2 = pp->beta2, eps = pp->eps, wd = pp->wd;
   const float step_size = s_step, bc2s = s_bc2;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -1058,7 +1066,7 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
     GLNN_LAUNCH_OK("adam_dp_kernel");
   } else {
     const unsigned ablocks = static_cast<unsigned>(std::min<int64_t>((P + 255) / 256, 8LL * sm_count()));
-    adam_kernel<<<ablocks, 256, 0, st>>>(c.params, c.grads, c.m, c.v, P, pp, ctr);
+    adam_kernel<<<ablocks, 256, 0, st>>>(c.params, c.grads, c.m, c.v, P, pp, ctr, AdamByValue{});
     GLNN_LAUNCH_OK("adam_kernel");
   }
   advance_kernel<<<1, 32, 0, st>>>(ctr, d.norm ? c.nbt : nullptr, d.norm ? d.L - 1 : 0,
@@ -1266,6 +1274,21 @@ extern "C" int glnn_mlp_train_pass(const glnn_mlp_desc* desc, float* params, flo
                                num_batches_tracked, adam_step0, hp, X, ldx, target, target_kind, perm,
                                nb, bs, drop_masks, seed, lamb, loss_sum, workspace, workspace_bytes,
                                stream);
+}
+
+extern "C" int glnn_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                                  int64_t n, int64_t step, const glnn_adam_hparams* hp,
+                                  glnn_stream_t stream) {
+  using namespace glnn;
+  GLNN_REQUIRE(n >= 0 && step >= 1 && hp, GLNN_ERR_ARG, "adam_step: n >= 0, step >= 1, hp != NULL");
+  if (n == 0) return 0;
+  GLNN_REQUIRE(params && grads && exp_avg && exp_avg_sq, GLNN_ERR_ARG, "adam_step: null pointer");
+  const AdamByValue hv{hp->lr, hp->beta1, hp->beta2, hp->eps, hp->weight_decay, step};
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 8LL * sm_count()));
+  adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n,
+                                                                     nullptr, nullptr, hv);
+  GLNN_LAUNCH_OK("adam_kernel");
+  return 0;
 }
 
 extern "C" int64_t glnn_mlp_dp_control_bytes(const glnn_mlp_desc* desc, int64_t bs_global, int world) {

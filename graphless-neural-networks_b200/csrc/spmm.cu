@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(kWarps * 32) compact_s24_kernel(const uint8_t*
 // U rows are loaded before any is accumulated; zero words (padding) are skipped, so no two lanes of
 // an instruction ever touch the same accumulator (the columns of a row are distinct).
 __device__ __forceinline__ void gather_range_s24(const SpmmArgs& a, int64_t beg, int64_t end, int lane,
-                                                 int nseg, const Policies& pol,
+                                                 int cap8, const Policies& pol,
                                                  float* __restrict__ acc_s) {
   constexpr int U = 4, KMAX = kS24MaxD / 32;
   for (int64_t base = beg; base < end; base += 32) {
@@ -664,7 +664,8 @@ __device__ __forceinline__ void gather_range_s24(const SpmmArgs& a, int64_t beg,
         const bool live = (j + t < cnt) && u >= 0;
         const uint32_t* r = a.Xs + static_cast<int64_t>(live ? u : 0) * a.lds + lane;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k) w[t][k] = (live && k < nseg) ? ld4(r + 32 * k, pol.cold) : 0u;
+        for (int k = 0; k < KMAX; ++k)  // whole 32-byte sectors up to the capacity, nothing beyond
+          w[t][k] = (live && lane + 32 * k < cap8) ? ld4(r + 32 * k, pol.cold) : 0u;
       }
 #pragma unroll
       for (int t = 0; t < U; ++t) {
@@ -693,7 +694,7 @@ __global__ void __launch_bounds__(kWarps * 32, GLNN_SPMM_MINB) spmm_csr_s24_kern
   const Policies pol = make_policies(a.hot_below > 0);
   const int cap = *a.cap_dev;
   const bool sparse = cap <= a.cap_limit;
-  const int nseg = (cap + 31) >> 5;
+  const int cap8 = (cap + 7) & ~7;  // entries read per row: the capacity rounded up to a 32-byte sector
   if (threadIdx.x == 0) s_nhub = 0;
   __syncthreads();
   {
@@ -742,7 +743,7 @@ __global__ void __launch_bounds__(kWarps * 32, GLNN_SPMM_MINB) spmm_csr_s24_kern
 #pragma unroll
           for (int i = 0; i < W; ++i) acc_s[lane * W + i] = 0.f;
           __syncwarp();
-          gather_range_s24(a, beg, end, lane, nseg, pol, acc_s);
+          gather_range_s24(a, beg, end, lane, cap8, pol, acc_s);
 #pragma unroll
           for (int i = 0; i < W; ++i) acc[0][i] = acc_s[lane * W + i];
           __syncwarp();
@@ -764,6 +765,124 @@ __global__ void __launch_bounds__(kWarps * 32, GLNN_SPMM_MINB) spmm_csr_s24_kern
     if (gidx == 0) epilogue_store<G, VPL, W>(a, row, end - beg, gl, gmask, pol, acc);
     __syncthreads();
   }
+}
+
+// ---- EXPERIMENT (tools/exp_spmm_tma.py): neighbour rows pulled by TMA bulk copies -----------------
+// north_star names TMA for the neighbour pull.  This kernel is the A/B partner of spmm_csr_kernel
+// <32,1,8,false> on 256-wide q24 rows: one warp per destination row, lane 0 issues one
+// cp.async.bulk (global -> shared, mbarrier complete_tx) per neighbour ROW into a per-warp ring of
+// STAGES row buffers, the warp waits on the row's mbarrier, decodes its 8 columns from shared memory
+// and accumulates.  No hub path: it is only run on graphs without hubs.  Measured result and verdict:
+// profiles/README.md (r2 "TMA gather A/B") and DESIGN.md section 4.1.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+template <int STAGES>
+__global__ void __launch_bounds__(kWarps * 32) spmm_tma_q24_kernel(const SpmmArgs a) {
+  extern __shared__ __align__(128) uint8_t s_ring[];   // [kWarps][STAGES][ldq]
+  __shared__ __align__(8) uint64_t s_bar[kWarps][STAGES];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t row = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
+  const uint32_t row_bytes = static_cast<uint32_t>(a.ldq);
+  uint8_t* ring = s_ring + static_cast<size_t>(warp) * STAGES * row_bytes;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&s_bar[warp][s])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (row >= a.n_dst) return;
+  const Policies pol = make_policies(false);
+  const int64_t beg = load_ptr(a, row), end = load_ptr(a, row + 1);
+  const int64_t deg = end - beg;
+  float acc[1][8];
+  zero_acc<1, 8>(acc);
+  auto issue = [&](int64_t src, int stage) {  // lane 0 only
+    const uint32_t bar = smem_addr(&s_bar[warp][stage]);
+    const uint32_t dst = smem_addr(ring + static_cast<size_t>(stage) * row_bytes);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(row_bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(a.Xq + src * a.ldq), "r"(row_bytes), "r"(bar)
+        : "memory");
+  };
+  // ids are fetched 32 at a time (one coalesced load); the edge counter picks the ring stage and the
+  // barrier parity
+  int64_t issued = 0, done = 0;
+  // the id batch of the ISSUE pointer (it runs at most STAGES edges ahead of the consume pointer)
+  int my_i = -1;
+  int64_t my_i_base = -32;
+  auto id_issue = [&](int64_t j) -> int {
+    const int64_t b = j & ~int64_t(31);
+    if (b != my_i_base) {
+      my_i_base = b;
+      my_i = (beg + b + lane < end) ? static_cast<int>(ld4(a.indices + beg + b + lane, pol.cold)) : -1;
+    }
+    return __shfl_sync(0xffffffffu, my_i, static_cast<int>(j & 31));
+  };
+  for (; issued < deg && issued < STAGES; ++issued) {
+    const int u = id_issue(issued);
+    if (lane == 0) issue(u, static_cast<int>(issued % STAGES));
+  }
+  for (; done < deg; ++done) {
+    const int stage = static_cast<int>(done % STAGES);
+    const uint32_t parity = static_cast<uint32_t>((done / STAGES) & 1);
+    const uint32_t bar = smem_addr(&s_bar[warp][stage]);
+    uint32_t ok = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(parity)
+          : "memory");
+    }
+    const uint8_t* r = ring + static_cast<size_t>(stage) * row_bytes;
+    const uint4 h = *reinterpret_cast<const uint4*>(r + 16 * lane);
+    const uint2 m = *reinterpret_cast<const uint2*>(r + 2 * a.dq + 8 * lane);
+    float x[8];
+    decode_q24(h, m, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[0][i] += x[i];
+    __syncwarp();   // every lane has read the stage before it is refilled
+    if (issued < deg) {
+      const int u = id_issue(issued);
+      if (lane == 0) issue(u, stage);
+      ++issued;
+    }
+  }
+  epilogue_store<32, 1, 8>(a, row, deg, lane, 0xffffffffu, pol, acc);
+}
+
+int spmm_run_tma_exp(const glnn_spmm_desc& q, int stages, cudaStream_t st) {
+  const int d = q.d, dq = (d + 7) / 8 * 8;
+  GLNN_REQUIRE(q.X_q24 && !q.X && dq == 256 && q.ldq == 768 && aligned16(q.X_q24), GLNN_ERR_SHAPE,
+               "spmm_tma_exp: 256-wide q24 rows of 768 bytes only");
+  GLNN_REQUIRE(q.indptr && q.indices && (q.Y || q.Y_hi) && !q.src_scale && !q.log_softmax, GLNN_ERR_ARG,
+               "spmm_tma_exp: unsupported arguments");
+  GLNN_REQUIRE(stages == 4 || stages == 8, GLNN_ERR_ARG, "spmm_tma_exp: stages must be 4 or 8");
+  if (q.n_dst == 0) return 0;
+  SpmmArgs a{};
+  a.indptr = q.indptr; a.indices = q.indices; a.Xq = q.X_q24; a.ldq = q.ldq; a.dq = dq;
+  a.Y = q.Y; a.ldy = q.ldy; a.Yh = q.Y_hi; a.Yl = q.Y_lo; a.ldyp = q.ldyp;
+  a.n_dst = q.n_dst; a.d = d; a.indptr64 = q.indptr64;
+  a.self_add = q.self_add; a.mean_plus_one = q.mean_plus_one; a.dst_scale = q.dst_scale;
+  a.bias = q.bias; a.col_scale = q.col_scale; a.col_shift = q.col_shift; a.relu = q.relu;
+  const unsigned blocks = static_cast<unsigned>((q.n_dst + kWarps - 1) / kWarps);
+  const size_t smem = static_cast<size_t>(kWarps) * stages * q.ldq;
+  if (stages == 8) {
+    GLNN_CUDA_OK(cudaFuncSetAttribute(spmm_tma_q24_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    spmm_tma_q24_kernel<8><<<blocks, kWarps * 32, smem, st>>>(a);
+  } else {
+    GLNN_CUDA_OK(cudaFuncSetAttribute(spmm_tma_q24_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    spmm_tma_q24_kernel<4><<<blocks, kWarps * 32, smem, st>>>(a);
+  }
+  GLNN_LAUNCH_OK("spmm_tma_q24_kernel");
+  return 0;
 }
 
 template <int G, int VPL, int W>
@@ -1021,6 +1140,11 @@ int quantize_q24(const float* X, int64_t ldx, int64_t rows, int d, uint8_t* Q, i
 extern "C" int glnn_spmm_csr(const glnn_spmm_desc* desc, glnn_stream_t stream) {
   GLNN_REQUIRE(desc != nullptr, GLNN_ERR_ARG, "spmm: null descriptor");
   return glnn::spmm_run(*desc, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int glnn_exp_spmm_tma_q24(const glnn_spmm_desc* desc, int stages, glnn_stream_t stream) {
+  GLNN_REQUIRE(desc != nullptr, GLNN_ERR_ARG, "spmm_tma_exp: null descriptor");
+  return glnn::spmm_run_tma_exp(*desc, stages, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int64_t glnn_s24_row_words(int d) {

@@ -210,7 +210,9 @@ static int gnn_forward(bool gcn, const void* indptr, int indptr64, const int32_t
     const glnn_gnn_layer& ly = layers[l];
     const bool last = (l == L - 1);
     const int dpad = pad4(ly.d_out);
-    const int relu = last ? 0 : (gcn ? 2 : 1);
+    // GraphConv applies its activation inside the conv; the reference constructs the single layer of
+    // a 1-layer GCN WITH the activation (models.py:168-169), so its logits are ReLU'd
+    const int relu = (last && !(gcn && L == 1)) ? 0 : (gcn ? 2 : 1);
     const bool out_planes = !last && project_first(l + 1);
     // a hidden output that only feeds the NEXT layer's gather is written as q24 by the projection
     const bool out_q24 = use_q24 && !last && !out_planes && !project_first(l) && ly.d_out % 8 == 0 &&

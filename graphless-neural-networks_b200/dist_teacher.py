@@ -263,6 +263,14 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
             timings.append((name, ev))
 
     xch = _Exchange(sg, group, feats_any.is_cuda, mark)
+    if cuda and world > 1 and _push_mode():
+        # The replicas are cached and reused by the next call.  A fast rank must not push its slab of
+        # call k+1 into a peer's replica while that peer is still gathering from it in call k (an
+        # aggregate-first last layer with gather_output=False has no later synchronisation): one
+        # device-side barrier over symmetric memory, ordered after everything this rank enqueued.
+        hits = sg.__dict__.get("_symm_by_ptr")
+        if hits:
+            next(iter(hits.values()))[1].barrier(channel=1)
     mark("start")
 
     def proj_first(i):

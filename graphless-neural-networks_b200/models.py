@@ -207,7 +207,10 @@ class GCN(_Encoder):
                  norm_type="none"):
         super().__init__()
         self.dropout = nn.Dropout(dropout_ratio)
-        self._build(lambda i, a, b: GraphConv(a, b, activation if i != num_layers - 1 else None),
+        # the reference gives the ONLY layer of a 1-layer GCN the activation too (models.py:168-169):
+        # its logits pass through ReLU before log_softmax
+        self._build(lambda i, a, b: GraphConv(a, b, activation if (i != num_layers - 1 or num_layers == 1)
+                                              else None),
                     num_layers, input_dim, hidden_dim, output_dim, norm_type)
 
     def forward(self, g, feats, log_softmax=False):

@@ -93,6 +93,24 @@ def nll_acc(logp, labels, idx=None):
     return out
 
 
+def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), eps=1e-8,
+              weight_decay=0.0):
+    """glnn_adam_step_f32: in-place torch.optim.Adam update of a flat fp32 buffer (step is 1-based)."""
+    lib = _lib.load()
+    require_cuda(params, grads, exp_avg, exp_avg_sq)
+    _f32(params, grads, exp_avg, exp_avg_sq)
+    n = params.numel()
+    for t in (params, grads, exp_avg, exp_avg_sq):
+        if t.numel() != n or not t.is_contiguous():
+            raise ValueError("adam_step: contiguous buffers of equal length expected")
+    import ctypes
+    hp = _lib.AdamHParams(lr=float(lr), beta1=float(betas[0]), beta2=float(betas[1]), eps=float(eps),
+                          weight_decay=float(weight_decay))
+    check(lib.glnn_adam_step_f32(ptr(params), ptr(grads), ptr(exp_avg), ptr(exp_avg_sq), n, int(step),
+                                 ctypes.byref(hp), stream()), "glnn_adam_step_f32")
+    return params
+
+
 class Planes:
     """fp32 matrix kept as bf16 hi / lo planes (see include/glnn_b200.h): .hi/.lo int16 tensors
     [rows, ldp], logical width .cols."""
@@ -282,6 +300,21 @@ def spmm(indptr, indices, x, d=None, out=None, out_planes=None, self_add=False, 
     else:
         check(lib.glnn_spmm_csr(ctypes.byref(q), stream()), "glnn_spmm_csr")
     return out if out is not None else out_planes
+
+
+def exp_spmm_tma(indptr, indices, xq, out_planes, stages=8, self_add=True, mean_plus_one=True):
+    """glnn_exp_spmm_tma_q24 (EXPERIMENT, tools/exp_spmm_tma.py): 256-wide q24 aggregation with the
+    neighbour rows pulled by TMA bulk copies into shared memory."""
+    import ctypes
+    lib = _lib.load()
+    q = _lib.SpmmDesc()
+    q.indptr, q.indices, q.indptr64 = ptr(indptr), ptr(indices), int(indptr.dtype == torch.int64)
+    q.n_dst, q.n_src, q.d = indptr.numel() - 1, xq.data.shape[0], xq.cols
+    q.X_q24, q.ldq = ptr(xq.data), xq.ldq
+    q.Y_hi, q.Y_lo, q.ldyp = ptr(out_planes.hi), ptr(out_planes.lo), out_planes.hi.stride(0)
+    q.self_add, q.mean_plus_one = int(self_add), int(mean_plus_one)
+    check(lib.glnn_exp_spmm_tma_q24(ctypes.byref(q), int(stages), stream()), "glnn_exp_spmm_tma_q24")
+    return out_planes
 
 
 class S24:

@@ -106,8 +106,9 @@ def gcn_forward_train(enc, g, feats):
             h = _Aggregate.apply(h, fwd, bwd, None, False)
             h = _Linear.apply(h, conv.weight, None, False)
         h = h * nd.unsqueeze(1) + conv.bias
+        if conv._activation is not None:
+            h = conv._activation(h)
         if l != enc.num_layers - 1:
-            h = F.relu(h)
             h_list.append(h)
             if enc.norm_type != "none":
                 h = enc.norms[l](h)

@@ -200,6 +200,13 @@ GLNN_API int glnn_compact_s24(const uint8_t* X_q24, int64_t ldq, int64_t rows, i
 GLNN_API int glnn_spmm_csr_s24(const glnn_spmm_desc* desc, const uint32_t* X_s24, int64_t lds,
                       const int32_t* cap_dev, glnn_stream_t stream);
 
+/* EXPERIMENT, measurement only (tools/exp_spmm_tma.py; nothing on the product path calls it): the
+ * aggregation of 256-wide q24 rows (ldq = 768) with every neighbour row pulled by ONE TMA bulk copy
+ * (cp.async.bulk global -> shared, mbarrier complete_tx) into a per-warp ring of `stages` (4 or 8)
+ * row buffers instead of ld.global.nc into registers -- the A/B that settles the north_star's "TMA
+ * for the neighbour pull" clause with a number.  Same math as glnn_spmm_csr; no hub path. */
+GLNN_API int glnn_exp_spmm_tma_q24(const glnn_spmm_desc* desc, int stages, glnn_stream_t stream);
+
 /* K5 (eval): folds BatchNorm1d running statistics into a per-column affine for the epilogues
  * above: scale = gamma / sqrt(var + eps), shift = beta - mean * scale  (models.py:139-141). */
 GLNN_API int glnn_bn_fold_f32(const float* gamma, const float* beta, const float* mean, const float* var,
@@ -267,6 +274,14 @@ GLNN_API int glnn_mlp_train_pass(const glnn_mlp_desc* desc, float* params, float
                         int64_t bs, const uint8_t* drop_masks, uint64_t seed, float lamb,
                         float* loss_sum, void* workspace, int64_t workspace_bytes,
                         glnn_stream_t stream);
+
+/* K10 alone: one torch.optim.Adam update (amsgrad = False, L2 weight decay folded into the gradient,
+ * train_student.py:275-277 / train_teacher.py:234-236) of n contiguous fp32 parameters from given
+ * gradients -- the same kernel the fused student step ends with.  `step` is the 1-based number of
+ * this update (bias corrections 1 - beta^step are evaluated in double).  Used by teacher training
+ * (train / train_sage, train_and_eval.py:12-56) and by the injected-gradient parity test. */
+GLNN_API int glnn_adam_step_f32(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                       int64_t n, int64_t step, const glnn_adam_hparams* hp, glnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Student, data parallel over the GPUs of one box.  Same step as

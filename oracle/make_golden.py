@@ -232,8 +232,78 @@ def sage_train_case(name, n, e, f, hidden, c, layers, lr, wd, lamb, steps, seed)
     print(name, "train_sage losses", [round(x, 5) for x in losses])
 
 
+class _NullLogger:
+    def debug(self, *a, **k): pass
+    def info(self, *a, **k): pass
+
+
+def runner_case(name, inductive, n, f, hidden, c, layers, norm, bs, lr, wd, lamb, patience, max_epoch,
+                seed):
+    """Epoch-loop fixtures: the reference's own
+    distill_run_transductive (train_and_eval.py:520-606) or distill_run_inductive (:609-742), run
+    unmodified on CPU with dropout 0; torch.randperm is wrapped to RECORD every permutation the
+    passes drew (utils.graph_split's for the inductive split included, recorded separately)."""
+    gen = torch.Generator().manual_seed(seed + 3)
+    feats = torch.randn(n, f, generator=gen)
+    labels = (feats[:, :c] + 0.5 * torch.randn(n, c, generator=gen)).argmax(1)
+    out_t = torch.log_softmax(2.0 * feats[:, :c] + 0.3 * torch.randn(n, c, generator=gen), 1)
+    perm = torch.randperm(n, generator=gen)
+    n_tr, n_va = int(0.3 * n), int(0.2 * n)
+    idx_train, idx_val, idx_test = perm[:n_tr], perm[n_tr:n_tr + n_va], perm[n_tr + n_va:]
+    if inductive:
+        obs_tr, obs_val, obs_test, idx_obs, idx_test_ind = ref_utils.graph_split(
+            idx_train, idx_val, idx_test, 0.2, seed)
+        indices = (obs_tr, torch.cat([obs_tr, obs_val, obs_test]), obs_val, obs_test, idx_obs,
+                   idx_test_ind)
+        runner = ref_te.distill_run_inductive
+    else:
+        indices = (idx_train, torch.cat([idx_train, idx_val, idx_test]), idx_val, idx_test)
+        runner = ref_te.distill_run_transductive
+    conf = dict(seed=seed, device="cpu", batch_size=bs, lamb=lamb, patience=patience,
+                max_epoch=max_epoch, eval_interval=1, model_name="MLP", num_layers=layers, feat_dim=f,
+                hidden_dim=hidden, label_dim=c, dropout_ratio=0.0, norm_type=norm)
+    ref_utils.set_seed(seed)
+    model = ref_models.Model(conf)
+    init = sd_np(model, "init.")
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    hist = []
+    with Recorder() as rec:
+        res = runner(conf, model, feats, labels, out_t, indices, torch.nn.NLLLoss(),
+                     torch.nn.KLDivLoss(reduction="batchmean", log_target=True),
+                     ref_utils.get_evaluator("cora"), opt, _NullLogger(), hist)
+    out, scores = res[0], [float(x) for x in res[1:]]
+    extra = {f"perm.{i}": p.numpy() for i, p in enumerate(rec.perms)}
+    for i, ix in enumerate(indices):
+        extra[f"index.{i}"] = ix.numpy()
+    np.savez_compressed(
+        os.path.join(OUT, f"runner_{name}.npz"), feats=feats.numpy(), labels=labels.numpy(),
+        out_t=out_t.numpy(), inductive=int(inductive), num_layers=layers, hidden=hidden, norm=norm,
+        batch_size=bs, lr=lr, wd=wd, lamb=lamb, patience=patience, max_epoch=max_epoch, seed=seed,
+        hist=np.array(hist, dtype=np.float64), scores=np.array(scores), out=out.detach().numpy(),
+        n_perms=len(rec.perms), **init, **sd_np(model, "final."), **extra)
+    print(name, "epochs run", len(hist), "scores", scores, "perms", len(rec.perms))
+
+
+def run_runner_cases():
+    runner_case("tran_none2", False, n=600, f=16, hidden=32, c=5, layers=2, norm="none", bs=64, lr=0.01,
+                wd=5e-4, lamb=0.3, patience=3, max_epoch=6, seed=21)
+    runner_case("tran_bn3", False, n=700, f=12, hidden=24, c=4, layers=3, norm="batch", bs=64, lr=0.01,
+                wd=0.0, lamb=0.0, patience=2, max_epoch=5, seed=22)
+    runner_case("ind_none3", True, n=640, f=14, hidden=32, c=4, layers=3, norm="none", bs=64, lr=0.01,
+                wd=0.0, lamb=0.5, patience=3, max_epoch=5, seed=23)
+    runner_case("ind_bn2", True, n=560, f=10, hidden=16, c=3, layers=2, norm="batch", bs=32, lr=0.005,
+                wd=1e-3, lamb=1.0, patience=2, max_epoch=4, seed=24)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)  # bit-stable fixtures
+    if "--runners-only" in sys.argv:          # round-2 addition: leaves the older fixtures untouched
+        run_runner_cases()
+        sys.exit(0)
+    if "--gcn1-only" in sys.argv:
+        teacher_case("gcn_1layer", "GCN", n=90, e=400, f=12, hidden=8, c=5, layers=1, norm="none",
+                     bs=0, seed=6, self_loops=True, dup=10)
+        sys.exit(0)
     if "--teacher-train-only" in sys.argv:   # later addition: leaves the older fixtures untouched
         teacher_train_case("gcn2", n=150, e=700, f=30, hidden=16, c=5, layers=2, norm="none", lr=0.01,
                            wd=1e-3, lamb=1.0, steps=4, seed=11)
@@ -256,6 +326,8 @@ if __name__ == "__main__":
                  bs=0, seed=3, self_loops=True)
     teacher_case("gcn_agg_first", "GCN", n=120, e=500, f=8, hidden=24, c=3, layers=3, norm="batch",
                  bs=0, seed=4, self_loops=True, dup=20)
+    teacher_case("gcn_1layer", "GCN", n=90, e=400, f=12, hidden=8, c=5, layers=1, norm="none",
+                 bs=0, seed=6, self_loops=True, dup=10)
     # student: reference train_mini_batch / evaluate_mini_batch with autograd + torch.optim.Adam
     student_case("mlp_bn3", "MLP", n=500, f=20, hidden=32, c=7, layers=3, norm="batch", dropout=0.0,
                  bs=64, lr=0.01, wd=0.0, lamb=0.3, epochs=2, seed=0)
@@ -277,3 +349,4 @@ if __name__ == "__main__":
                     lamb=1.0, steps=4, seed=13)
     sage_train_case("sage3_lamb", n=140, e=700, f=9, hidden=20, c=3, layers=3, lr=0.02, wd=0.0,
                     lamb=0.7, steps=3, seed=14)
+    run_runner_cases()

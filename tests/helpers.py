@@ -7,7 +7,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-TEACHER_CASES = ["sage_bn3", "sage_none2", "sage_wide", "gcn_cora_like", "gcn_agg_first"]
+TEACHER_CASES = ["sage_bn3", "sage_none2", "sage_wide", "gcn_cora_like", "gcn_agg_first", "gcn_1layer"]
 STUDENT_CASES = ["mlp_bn3", "mlp_lamb0", "mlp_none2_wd", "mlp_dropout", "mlp_small_n", "mlp_1layer"]
 
 
@@ -71,6 +71,25 @@ def relerr_q(a, b, q=0.999):
 def relerr(a, b):
     a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def parity_report(a, b, rtol=1e-4, atol=1e-5):
+    """The two halves of SURVEY.md 8d's parity gate for an output tensor: max|a-b| / max|b| and
+    allclose(rtol, atol) elementwise, plus how far the worst element is from its allclose bound."""
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    diff = (a - b).abs()
+    bound = atol + rtol * b.abs()
+    viol = diff > bound
+    return {"max_rel": float(diff.max() / b.abs().max().clamp_min(1e-30)),
+            "allclose": not bool(viol.any()), "violating_frac": float(viol.double().mean()),
+            "worst_over_bound": float((diff / bound).max())}
+
+
+def assert_parity(a, b, what="", tol=1e-4, rtol=1e-4, atol=1e-5):
+    """SURVEY.md 8d gate: max|a-b| / max|b| <= 1e-4 AND allclose(rtol=1e-4, atol=1e-5)."""
+    r = parity_report(a, b, rtol, atol)
+    assert r["max_rel"] <= tol and r["allclose"], (what, r)
+    return r
 
 
 class TorchKernels:

@@ -123,6 +123,53 @@ def test_cli_teacher_then_student_end_to_end(tmp_path):
     assert len(r.stdout.strip().split("\t")) == 2
 
 
+@pytest.mark.gpu
+def test_teacher_to_student_hand_off_stays_on_device(tmp_path, monkeypatch):
+    """SURVEY 8f row 3 (train_teacher.py:296-297 -> dataloader.py:169-170): in one process the
+    student takes the teacher's log-probabilities from device memory; out.npz is still written in the
+    reference's format, and a student that reads the file back scores the same."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from glnn_b200 import cli, dataloader
+    (tmp_path / "data").mkdir()
+    write_cpf_npz(tmp_path / "data" / "cora.npz")
+    monkeypatch.chdir(tmp_path)
+    common = ["--dataset", "cora", "--device", "0", "--max_epoch", "12", "--patience", "12",
+              "--model_config_path", os.path.join(ROOT, "train.conf.yaml")]
+    calls = []
+    orig = cli.load_out_t
+    monkeypatch.setattr(cli, "load_out_t", lambda d: (calls.append(d), orig(d))[1])
+    t_line, s_line = cli.distill_pipeline(["--teacher", "SAGE"] + common,
+                                          ["--teacher", "SAGE", "--student", "MLP", "--lamb", "0.5",
+                                           "--dropout_ratio", "0"] + common)
+    assert calls == []                                     # no read-back of out.npz
+    t_dir = tmp_path / "outputs" / "transductive" / "cora" / "SAGE" / "seed_0"
+    key = str(t_dir)
+    assert key in cli._OUT_T_ON_DEVICE and cli._OUT_T_ON_DEVICE[key].is_cuda
+    on_disk = np.load(t_dir / "out.npz")["arr_0"]
+    assert on_disk.dtype == np.float32
+    assert np.array_equal(on_disk, cli._OUT_T_ON_DEVICE[key].cpu().numpy())   # same bits both ways
+    # the file path gives the same student (same seed, same inputs)
+    cli._OUT_T_ON_DEVICE.clear()
+    import shutil
+    shutil.rmtree(tmp_path / "outputs" / "transductive" / "cora" / "SAGE_MLP")
+    s_line2 = cli.main("student", ["--teacher", "SAGE", "--student", "MLP", "--lamb", "0.5",
+                                   "--dropout_ratio", "0"] + common)
+    assert len(calls) == 1
+    assert abs(float(s_line.split("\t")[0]) - float(s_line2.split("\t")[0])) < 0.02
+
+
+def test_cli_refuses_to_run_without_cuda_before_creating_outputs(tmp_path, monkeypatch):
+    """--device defaults to -1 (CPU) in the reference; this implementation has no CPU path and must
+    say so up front instead of failing deep inside a kernel wrapper after creating output_dir."""
+    from glnn_b200 import cli
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cli.main("teacher", ["--teacher", "GCN", "--dataset", "cora"])
+    assert not (tmp_path / "outputs").exists()
+
+
 def test_arxiv_edge_preprocessing_known_answer():
     """dataloader.py:74-77 on a 4-node multigraph: reverse edges appended without de-duplication,
     original self-loops dropped, one self-loop per node added; in-degrees count multiplicities."""

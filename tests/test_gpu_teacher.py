@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import glnn_oracle as O
-from helpers import TEACHER_CASES, load, relerr, sub
+from helpers import TEACHER_CASES, assert_parity, load, parity_report, relerr, sub
 
 pytestmark = pytest.mark.gpu
 
@@ -399,9 +399,11 @@ def test_teacher_matches_reference_golden(dev, case):
     with torch.no_grad():
         logits = model.inference(data, feats)
     assert relerr(logits.cpu(), d["logits"]) < TOL
+    assert_parity(logits.cpu(), d["logits"], "logits")      # + allclose(rtol=1e-4, atol=1e-5), SURVEY 8d
     out, loss, score = TE.evaluate(model, data, feats, labels, torch.nn.NLLLoss(),
                                    U.get_evaluator("cora"), torch.from_numpy(d["idx_eval"]).to(dev))
     assert relerr(out.cpu(), d["out"]) < TOL
+    assert_parity(out.cpu(), d["out"], "log-probabilities")
     assert abs(loss - float(d["loss"])) < 1e-4 * max(1.0, abs(float(d["loss"])))
     assert abs(score - float(d["score"])) < 1e-6
 
@@ -447,6 +449,21 @@ def test_teacher_midsize_vs_oracle(dev, model_name, dims):
     with torch.no_grad():
         got = model.inference(G.FullNeighborLoader(g) if model_name == "SAGE" else g, feats.to(dev))
     assert relerr(got.cpu(), want) < TOL
+    # both halves of the SURVEY 8d gate on the logits AND on the log-probabilities evaluate() returns,
+    # against the fp32 oracle (what the reference's CPU run computes) and the fp64 one (what both
+    # approximate); the fp32 oracle's own distance to fp64 is printed for scale
+    d64 = lambda t: t.double()
+    layers64 = [(d64(w), d64(b)) for w, b in layers]
+    norms64 = [tuple(d64(t) for t in nm) for nm in norms]
+    if model_name == "SAGE":
+        want64 = O.sage_inference(indptr, indices, feats.double(), layers64, norms64, batch_size=None)
+    else:
+        want64 = O.gcn_forward(indptr, indices, feats.double(), layers64, norms64)
+    r32 = assert_parity(got.cpu(), want, "logits vs fp32 oracle")
+    r64 = assert_parity(got.cpu(), want64, "logits vs fp64 oracle")
+    rlp = assert_parity(torch.log_softmax(got, 1).cpu(), torch.log_softmax(want64, 1), "log-probs")
+    print(f"{model_name}{dims}: B200 vs fp32 oracle {r32}, vs fp64 {r64}, log-probs {rlp}; "
+          f"fp32 oracle vs fp64 {parity_report(want, want64)}")
 
 
 def test_gcn_zero_in_degree_raises(dev):
@@ -490,6 +507,41 @@ def test_sage_host_entry_point(dev):
                                             keep[2].ctypes.data, arr, L, 1e-5, out.ctypes.data),
                "glnn_sage_inference_host")
     assert relerr(out, d["out"]) < TOL
+    assert_parity(out, d["out"], "host entry point log-probabilities")
+
+
+def test_full_size_products_forward_vs_oracle(dev):
+    """The BENCHED forward at full size (BASELINE.json configs[3]: 2,449,029 nodes, 123.7M edges,
+    100 -> 256 -> 256 -> 47, BatchNorm eval; q24 gathers, hub task list, persistent tcgen05
+    projections, fused log_softmax) against the CPU oracle's full-graph forward on the same inputs:
+    SURVEY 8d gate on the log-probabilities evaluate() returns -- max|a-b| / max|b| <= 1e-4 and
+    allclose(rtol=1e-4, atol=1e-5)."""
+    import os
+    from glnn_b200 import graph as G
+    from glnn_b200.models import Model
+    from glnn_b200.workloads import dataset_graph, randomise_bn_
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    g = dataset_graph("ogbn-products", device=dev, seed=0)
+    n = g.num_nodes()
+    torch.manual_seed(0)
+    model = randomise_bn_(Model(dict(model_name="SAGE", num_layers=3, feat_dim=100, hidden_dim=256,
+                                     label_dim=47, dropout_ratio=0.5, norm_type="batch", device=dev))).eval()
+    feats = torch.randn(n, 100, device=dev)
+    with torch.no_grad():
+        got = model.encoder.inference(G.FullNeighborLoader(g), feats, log_softmax=True).cpu()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    layers = [(sd[f"encoder.layers.{l}.fc_neigh.weight"], sd[f"encoder.layers.{l}.fc_neigh.bias"])
+              for l in range(3)]
+    norms = [tuple(sd[f"encoder.norms.{l}.{k}"] for k in ("weight", "bias", "running_mean", "running_var"))
+             for l in range(2)]
+    indptr, indices = g.indptr.cpu().numpy().astype(np.int64), g.indices.cpu().numpy().astype(np.int64)
+    feats_c = feats.cpu()
+    del g, feats
+    torch.cuda.empty_cache()
+    want = torch.log_softmax(O.sage_inference(indptr, indices, feats_c, layers, norms), 1)
+    r = assert_parity(got, want, "full-size products log-probabilities")
+    print("full-size products forward vs oracle:", r)
+    assert bool((got.argmax(1) == want.argmax(1)).double().mean() > 0.99999)
 
 
 def test_full_size_products_properties(dev):
