@@ -20,8 +20,8 @@ class MlpDesc(C.Structure):
 
 
 class AdamHParams(C.Structure):
-    _fields_ = [("lr", c_f32), ("beta1", c_f32), ("beta2", c_f32), ("eps", c_f32),
-                ("weight_decay", c_f32)]
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double)]
 
 
 class GnnLayer(C.Structure):
@@ -40,6 +40,14 @@ class SpmmDesc(C.Structure):
 
 class DpGroup(C.Structure):
     _fields_ = [("world", c_i32), ("rank", c_i32), ("base", c_vp * 8), ("bytes", c_i64)]
+
+
+class ActDesc(C.Structure):
+    _fields_ = [("n", c_i64), ("d", c_i32), ("relu_post", c_i32), ("X", c_vp), ("ldx", c_i64),
+                ("Y", c_vp), ("ldy", c_i64), ("gamma", c_vp), ("beta", c_vp), ("running_mean", c_vp),
+                ("running_var", c_vp), ("save_mean", c_vp), ("save_invstd", c_vp), ("eps", c_f32),
+                ("momentum", c_f32), ("p_drop", c_f32), ("relu_input", c_i32), ("seed", C.c_uint64),
+                ("keep_mask", c_vp)]
 
 
 class SageLayerHost(C.Structure):
@@ -101,6 +109,18 @@ SIGNATURES = {
     "glnn_gcn_forward": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64,
                                    C.POINTER(GnnLayer), C.c_int, c_vp, c_i64, C.c_int, c_vp, c_i64,
                                    c_vp]),
+    "glnn_nll_loss_grad_f32": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_i64,
+                                         c_vp, c_vp]),
+    "glnn_act_train_fwd_f32": (C.c_int, [C.POINTER(ActDesc), c_vp, c_vp]),
+    "glnn_act_train_bwd_f32": (C.c_int, [C.POINTER(ActDesc), c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp,
+                                         c_vp, c_vp]),
+    "glnn_spmm_csr_scatter_f32": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64,
+                                            C.c_int, C.c_int, c_vp]),
+    "glnn_sample_count": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, C.c_int, c_vp, c_vp]),
+    "glnn_sample_neighbors": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_i64, C.c_int, C.c_uint64, c_vp, c_vp,
+                                        c_vp]),
+    "glnn_block_mark": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "glnn_block_relabel": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
     "glnn_sage_inference_host": (C.c_int, [c_vp, c_vp, c_i64, c_vp, C.POINTER(SageLayerHost),
                                            C.c_int, c_f32, c_vp]),
 }

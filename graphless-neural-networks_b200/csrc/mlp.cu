@@ -41,6 +41,23 @@ namespace glnn {
 int split_planes(const float* X, int64_t ldx, int64_t rows, int cols, uint16_t* hi, uint16_t* lo,
                  int64_t ldp, cudaStream_t st);  // planes.cu
 
+// torch.optim.Adam hyper-parameters as the update kernels take them.  The host keeps them in DOUBLE,
+// as torch does: 1 - beta is formed in double and only then rounded to fp32 (fp32(1 - 0.999) differs
+// from 1.f - fp32(0.999) by 1.3e-5 relative -- found by the injected-gradient test), and the bias
+// corrections 1 - beta^t are evaluated in double from the double betas.
+struct AdamHp {
+  double lr, beta1, beta2;
+  float b1, b2, omb1, omb2, eps, wd;
+};
+static inline AdamHp make_adam_hp(const glnn_adam_hparams& h) {
+  AdamHp a;
+  a.lr = h.lr; a.beta1 = h.beta1; a.beta2 = h.beta2;
+  a.b1 = static_cast<float>(h.beta1); a.b2 = static_cast<float>(h.beta2);
+  a.omb1 = static_cast<float>(1.0 - h.beta1); a.omb2 = static_cast<float>(1.0 - h.beta2);
+  a.eps = static_cast<float>(h.eps); a.wd = static_cast<float>(h.weight_decay);
+  return a;
+}
+
 struct PassParams {       // device-resident, rewritten once per pass
   const float* X;
   int64_t ldx;
@@ -52,7 +69,7 @@ struct PassParams {       // device-resident, rewritten once per pass
   uint64_t seed;
   int32_t kind;
   float lamb;
-  float lr, beta1, beta2, eps, wd;
+  AdamHp hp;
 };
 
 struct Dims {
@@ -773,38 +790,39 @@ __global__ void __launch_bounds__(256) loss_kernel(const float* __restrict__ log
 // torch.optim.Adam (amsgrad=False, L2 weight decay) over the flat parameter buffer.  Hyper-parameters
 // and the step number come from the pass's device state (pp, ctr: the fused student step) or, when pp
 // is null, by value (glnn_adam_step_f32: teacher training, the injected-gradient parity test).
-struct AdamByValue {
-  float lr, beta1, beta2, eps, wd;
-  int64_t step;  // 1-based step number of this update
-};
+__device__ __forceinline__ void adam_scalars(const AdamHp& h, double t, float* step_size, float* bc2_sqrt) {
+  const double bc1 = 1.0 - pow(h.beta1, t);
+  const double bc2 = 1.0 - pow(h.beta2, t);
+  *step_size = static_cast<float>(h.lr / bc1);
+  *bc2_sqrt = static_cast<float>(sqrt(bc2));
+}
+__device__ __forceinline__ float adam_update(const AdamHp& h, float step_size, float bc2s, float p,
+                                             float g, float* m, float* v) {
+  if (h.wd != 0.f) g = fmaf(h.wd, p, g);
+  const float mi = *m * h.b1 + g * h.omb1;          // exp_avg.mul_(beta1).add_(grad, alpha=1 - beta1)
+  const float vi = *v * h.b2 + g * g * h.omb2;      // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+  *m = mi;
+  *v = vi;
+  const float denom = sqrtf(vi) / bc2s + h.eps;
+  return p - step_size * (mi / denom);
+}
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v,
                                                    int64_t n, const PassParams* __restrict__ pp,
-                                                   const int* __restrict__ ctr, const AdamByValue hv) {
+                                                   const int* __restrict__ ctr, const AdamHp hv,
+                                                   int64_t step_by_value) {
   __shared__ float s_step, s_bc2;
-  const float lr = pp ? pp->lr : hv.lr;
-  const float b1 = pp ? pp->beta1 : hv.beta1, b2 = pp ? pp->beta2 : hv.beta2;
-  const float eps = pp ? pp->eps : hv.eps, wd = pp ? pp->wd : hv.wd;
-  if (threadIdx.x == 0) {
-    const double t = static_cast<double>(pp ? pp->step0 + *ctr + 1 : hv.step);
-    const double bc1 = 1.0 - pow(static_cast<double>(b1), t);
-    const double bc2 = 1.0 - pow(static_cast<double>(b2), t);
-    s_step = static_cast<float>(static_cast<double>(lr) / bc1);
-    s_bc2 = static_cast<float>(sqrt(bc2));
-  }
+  const AdamHp h = pp ? pp->hp : hv;
+  if (threadIdx.x == 0)
+    adam_scalars(h, static_cast<double>(pp ? pp->step0 + *ctr + 1 : step_by_value), &s_step, &s_bc2);
   __syncthreads();
   const float step_size = s_step, bc2s = s_bc2;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float gi = g[i];
-    const float pi = p[i];
-    if (wd != 0.f) gi = fmaf(wd, pi, gi);
-    const float mi = m[i] * b1 + gi * (1.f - b1);
-    const float vi = v[i] * b2 + gi * gi * (1.f - b2);
+    float mi = m[i], vi = v[i];
+    p[i] = adam_update(h, step_size, bc2s, p[i], g[i], &mi, &vi);
     m[i] = mi;
     v[i] = vi;
-    const float denom = sqrtf(vi) / bc2s + eps;
-    p[i] = pi - step_size * (mi / denom);
   }
 }
 
@@ -822,15 +840,9 @@ __global__ void __launch_bounds__(256) adam_dp_kernel(const DpDev dp, float* __r
                                                       int slot_params) {
   __shared__ float s_step, s_bc2;
   const uint32_t epoch = dp_epoch(dp);
-  if (threadIdx.x == 0) {
-    const double t = static_cast<double>(pp->step0 + *ctr + 1);
-    const double bc1 = 1.0 - pow(static_cast<double>(pp->beta1), t);
-    const double bc2 = 1.0 - pow(static_cast<double>(pp->beta2), t);
-    s_step = static_cast<float>(static_cast<double>(pp->lr) / bc1);
-    s_bc2 = static_cast<float>(sqrt(bc2));
-  }
+  const AdamHp h = pp->hp;
+  if (threadIdx.x == 0) adam_scalars(h, static_cast<double>(pp->step0 + *ctr + 1), &s_step, &s_bc2);
   dp_wait_all(dp, slot_grads, epoch);  // includes __syncthreads
-  const float b1 = pp->beta1, b2 = pp->beta2, eps = pp->eps, wd = pp->wd;
   const float step_size = s_step, bc2s = s_bc2;
   float* p_loc = reinterpret_cast<float*>(dp.base[dp.rank] + dp.off_params);
   // lo, hi are multiples of 4 and the buffers 16-byte aligned
@@ -850,13 +862,7 @@ __global__ void __launch_bounds__(256) adam_dp_kernel(const DpDev dp, float* __r
     float gi[4] = {g.x, g.y, g.z, g.w}, pi[4] = {p4.x, p4.y, p4.z, p4.w};
     float mi[4] = {m4.x, m4.y, m4.z, m4.w}, vi[4] = {v4.x, v4.y, v4.z, v4.w}, po[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (wd != 0.f) gi[j] = fmaf(wd, pi[j], gi[j]);
-      mi[j] = mi[j] * b1 + gi[j] * (1.f - b1);
-      vi[j] = vi[j] * b2 + gi[j] * gi[j] * (1.f - b2);
-      const float denom = sqrtf(vi[j]) / bc2s + eps;
-      po[j] = pi[j] - step_size * (mi[j] / denom);
-    }
+    for (int j = 0; j < 4; ++j) po[j] = adam_update(h, step_size, bc2s, pi[j], gi[j], &mi[j], &vi[j]);
     *reinterpret_cast<float4*>(m + i) = make_float4(mi[0], mi[1], mi[2], mi[3]);
     *reinterpret_cast<float4*>(v + i) = make_float4(vi[0], vi[1], vi[2], vi[3]);
     const float4 out = make_float4(po[0], po[1], po[2], po[3]);
@@ -1066,7 +1072,7 @@ static int enqueue_step(const StepCtx& c, cudaStream_t st) {
     GLNN_LAUNCH_OK("adam_dp_kernel");
   } else {
     const unsigned ablocks = static_cast<unsigned>(std::min<int64_t>((P + 255) / 256, 8LL * sm_count()));
-    adam_kernel<<<ablocks, 256, 0, st>>>(c.params, c.grads, c.m, c.v, P, pp, ctr, AdamByValue{});
+    adam_kernel<<<ablocks, 256, 0, st>>>(c.params, c.grads, c.m, c.v, P, pp, ctr, AdamHp{}, 0);
     GLNN_LAUNCH_OK("adam_kernel");
   }
   advance_kernel<<<1, 32, 0, st>>>(ctr, d.norm ? c.nbt : nullptr, d.norm ? d.L - 1 : 0,
@@ -1238,8 +1244,7 @@ static int train_pass_impl(const glnn_dp_group* grp, const glnn_mlp_desc* desc, 
   memset(&pp, 0, sizeof(pp));
   pp.X = X; pp.ldx = ldx; pp.target = target; pp.perm = perm_dev; pp.masks = drop_masks;
   pp.loss_sum = loss_sum; pp.step0 = adam_step0; pp.seed = seed; pp.kind = target_kind;
-  pp.lamb = lamb; pp.lr = hp->lr; pp.beta1 = hp->beta1; pp.beta2 = hp->beta2; pp.eps = hp->eps;
-  pp.wd = hp->weight_decay;
+  pp.lamb = lamb; pp.hp = make_adam_hp(*hp);
   GLNN_CUDA_OK(cudaMemcpyAsync(c.ws + c.wl.pp, &pp, sizeof(pp), cudaMemcpyHostToDevice, st));
   GLNN_CUDA_OK(cudaMemsetAsync(c.ws + c.wl.ctr, 0, sizeof(int), st));
   // `pp` lives on this stack frame: the copy above must have been staged before we return
@@ -1283,10 +1288,10 @@ extern "C" int glnn_adam_step_f32(float* params, const float* grads, float* exp_
   GLNN_REQUIRE(n >= 0 && step >= 1 && hp, GLNN_ERR_ARG, "adam_step: n >= 0, step >= 1, hp != NULL");
   if (n == 0) return 0;
   GLNN_REQUIRE(params && grads && exp_avg && exp_avg_sq, GLNN_ERR_ARG, "adam_step: null pointer");
-  const AdamByValue hv{hp->lr, hp->beta1, hp->beta2, hp->eps, hp->weight_decay, step};
+  const AdamHp hv = make_adam_hp(*hp);
   const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 8LL * sm_count()));
   adam_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n,
-                                                                     nullptr, nullptr, hv);
+                                                                     nullptr, nullptr, hv, step);
   GLNN_LAUNCH_OK("adam_kernel");
   return 0;
 }

@@ -144,6 +144,17 @@ def _push_mode():
     return os.environ.get("GLNN_EXCHANGE", "push").lower() != "nccl"
 
 
+def _replicate_projection():
+    """Exchange policy for an aggregate-first layer whose successor is aggregate-first as well
+    (ogbn-products layer 0: 100 -> 256).  "1" (default): ship the NARROW aggregated operand (d_in
+    columns as bf16 hi/lo planes) and let every rank project all N rows itself -- the projection is
+    HBM-bound and cheap (0.5 ms for all 2.45 M rows), the exchange is what limits scaling (round 1:
+    3.9 of 9.75 ms exposed at N=8 for 1.65 GB per rank of 256-wide q24 rows; the planes of the
+    100-wide operand are 0.89 GB).  "0": project the owned rows and ship the wide q24 output."""
+    import os
+    return os.environ.get("GLNN_DIST_REPLICATE", "1") not in ("", "0")
+
+
 def _symm_replica(sg, key, rows, row_bytes, dev, group):
     """uint8 [rows, row_bytes] replica allocated in symmetric memory (cached per shard): returns
     (tensor, handle).  Collective: every rank reaches the same allocation in the same order."""
@@ -430,6 +441,29 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
             wpl = k.split_planes(w) if cuda else None
             agg = new_operand(("agg", l), d_in)
             nxt_pf = (not last) and proj_first(l + 1)
+            ldp = (d_in + 7) // 8 * 8
+            if cuda and world > 1 and not last and not nxt_pf and _push_mode() and \
+                    _replicate_projection() and 4 * ldp < k.Q24.row_bytes(d_out):
+                # exchange the narrow aggregated operand, project ALL rows on every rank
+                raw, _, _ = _symm_replica(sg, ("aggrep", l), sg.total_rows, 4 * ldp, dev, group)
+                both = raw.view(torch.int16)                       # row = [hi (ldp) | lo (ldp)]
+                hi, lo = both[:, :ldp], both[:, ldp:]
+                for c in range(C):
+                    a, e = sg.chunk_rows(c)
+                    s0 = sg.slab_start(c)
+                    if e > a:
+                        k.spmm(sg.indptr[a:e + 1], sg.indices, h_rep, d=d_in,
+                               out_planes=k.Planes(hi[s0:s0 + e - a], lo[s0:s0 + e - a], d_in),
+                               dst_scale=sg.inv_deg1[a:e])
+                    xch.chunk(raw, c)
+                mark(f"L{l} spmm d={d_in}")
+                xch.wait(f"L{l} exchange aggregated operand ({d_in} wide, planes)")
+                y_rep = _cached(sg, ("yrep_local", l), lambda: k.Q24.empty(sg.total_rows, d_out, dev, zero=True))
+                k.gemm_planes_q24(k.Planes(hi, lo, d_in), wpl, out=y_rep, bias=b, col_scale=scale,
+                                  col_shift=shift, relu=relu)
+                mark(f"L{l} gemm {d_in}->{d_out} (all {sg.total_rows} rows, replicated)")
+                h_rep, h_op = y_rep, None
+                continue
             if last:
                 dest = ("final", out)
             elif nxt_pf:

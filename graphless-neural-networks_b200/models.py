@@ -137,6 +137,13 @@ class SAGEConv(nn.Module):
         nn.init.xavier_uniform_(self.fc_neigh.weight, gain=nn.init.calculate_gain("relu"))
 
 
+def _fwd_flags(log_softmax, exact):
+    import os
+    if exact is None:
+        exact = os.environ.get("GLNN_EXACT", "0") not in ("", "0")
+    return (1 if log_softmax else 0) | (2 if exact else 0)
+
+
 def _as_graph(data):
     if isinstance(data, FullNeighborLoader):
         return data.g
@@ -155,13 +162,20 @@ class SAGE(_Encoder):
                     output_dim, norm_type)
 
     def forward(self, blocks, feats):
-        """Sampled-block forward used by teacher training (models.py:101-119); autograd runs over
-        the aggregation / projection kernels (teacher_train.py)."""
+        """Sampled-block forward (models.py:101-119) on the kernels, in the module's current mode
+        (train: batch statistics + dropout).  It returns plain tensors: there is no autograd through
+        glnn_b200 -- training goes through train_and_eval.train_sage, whose backward is a hand-written
+        kernel sequence (teacher_train.py)."""
         from . import teacher_train
-        return teacher_train.sage_forward_blocks(self, blocks, feats)
+        if not self.training:
+            raise NotImplementedError("block-wise eval forward is not on the GLNN path: the reference "
+                                      "evaluates SAGE with inference() (train_and_eval.py:97)")
+        h_list, h, _ = teacher_train.sage_forward_blocks(self, blocks, feats)
+        return h_list, h
 
-    def inference(self, data, feats, log_softmax=False):
-        """Full-neighbour layer-wise inference for every node (models.py:121-148)."""
+    def inference(self, data, feats, log_softmax=False, exact=None):
+        """Full-neighbour layer-wise inference for every node (models.py:121-148).  exact=True (or
+        env GLNN_EXACT=1) selects the plain-fp32 mode of glnn_sage_forward (see include/glnn_b200.h)."""
         g = _as_graph(data)
         _lib.require_cuda(feats)
         g = g.to(feats.device)
@@ -181,7 +195,7 @@ class SAGE(_Encoder):
         _lib.check(lib.glnn_sage_forward(
             g.indptr.data_ptr(), int(g.indptr.dtype == torch.int64), g.indices.data_ptr(), n,
             feats.data_ptr(), feats.stride(0), layers, self.num_layers, out.data_ptr(),
-            out.stride(0), int(log_softmax), ws.data_ptr(), ws.numel(), _lib.stream()),
+            out.stride(0), _fwd_flags(log_softmax, exact), ws.data_ptr(), ws.numel(), _lib.stream()),
             "glnn_sage_forward")
         del keep
         return out
@@ -213,10 +227,13 @@ class GCN(_Encoder):
                                               else None),
                     num_layers, input_dim, hidden_dim, output_dim, norm_type)
 
-    def forward(self, g, feats, log_softmax=False):
-        if self.training and torch.is_grad_enabled():
+    def forward(self, g, feats, log_softmax=False, exact=None):
+        if self.training:
+            # train mode (batch statistics, dropout) on the kernels; plain tensors, no autograd --
+            # training goes through train_and_eval.train (hand-written backward, teacher_train.py)
             from . import teacher_train
-            return teacher_train.gcn_forward_train(self, g, feats)
+            h_list, h, _ = teacher_train.gcn_forward_train(self, _as_graph(g), feats)
+            return h_list, (h.log_softmax(1) if log_softmax else h)
         g = _as_graph(g)
         _lib.require_cuda(feats)
         g = g.to(feats.device)
@@ -238,7 +255,7 @@ class GCN(_Encoder):
         _lib.check(lib.glnn_gcn_forward(
             g.indptr.data_ptr(), int(g.indptr.dtype == torch.int64), g.indices.data_ptr(), n,
             ns.data_ptr(), nd.data_ptr(), feats.data_ptr(), feats.stride(0), layers,
-            self.num_layers, out.data_ptr(), out.stride(0), int(log_softmax), ws.data_ptr(),
+            self.num_layers, out.data_ptr(), out.stride(0), _fwd_flags(log_softmax, exact), ws.data_ptr(),
             ws.numel(), _lib.stream()), "glnn_gcn_forward")
         del keep
         return [], out

@@ -111,6 +111,130 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), 
     return params
 
 
+def nll_loss_grad(logits, labels, rows=None, label_rows=None, lamb=1.0, dlogits=None, loss_out=None):
+    """glnn_nll_loss_grad_f32 -> (dlogits, loss_out).  rows / label_rows: int64 selections (see the
+    header); dlogits is zero-initialised here when a subset of the rows is selected."""
+    lib = _lib.load()
+    require_cuda(logits, labels, rows, label_rows, dlogits, loss_out)
+    _f32(logits, dlogits, loss_out)
+    for t in (labels, rows, label_rows):
+        if t is not None and t.dtype != torch.int64:
+            raise ValueError("labels / rows / label_rows must be int64")
+    m = logits.shape[0] if rows is None else rows.numel()
+    if label_rows is not None and label_rows.numel() != m:
+        raise ValueError("label_rows must have one entry per selected row")
+    if dlogits is None:
+        mk = torch.empty if rows is None else torch.zeros
+        dlogits = mk(logits.shape[0], logits.shape[1], dtype=torch.float32, device=logits.device)
+    if loss_out is None:
+        loss_out = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    check(lib.glnn_nll_loss_grad_f32(ptr(logits), _ld(logits), logits.shape[1], ptr(labels), ptr(rows),
+                                     ptr(label_rows), m, float(lamb), ptr(dlogits), _ld(dlogits),
+                                     ptr(loss_out), stream()), "glnn_nll_loss_grad_f32")
+    return dlogits, loss_out
+
+
+class ActBlock:
+    """[BatchNorm1d] -> [ReLU] -> [Dropout] in train mode (glnn_act_train_fwd_f32 / _bwd_f32): keeps
+    what the backward needs (the input, the saved batch statistics, the dropout seed / mask)."""
+
+    def __init__(self, x, bn=None, relu_post=False, relu_input=False, p_drop=0.0, seed=0, keep_mask=None):
+        import ctypes
+        require_cuda(x, keep_mask)
+        _f32(x)
+        self.x, self.bn, self.keep_mask = x, bn, keep_mask
+        n, d = x.shape
+        q = _lib.ActDesc()
+        q.n, q.d, q.relu_post, q.relu_input = n, d, int(relu_post), int(relu_input)
+        q.X, q.ldx = ptr(x), _ld(x)
+        q.p_drop, q.seed = float(p_drop), int(seed) & ((1 << 64) - 1)
+        if keep_mask is not None:
+            if keep_mask.dtype != torch.uint8 or keep_mask.numel() != n * d or not keep_mask.is_contiguous():
+                raise ValueError("keep_mask must be a contiguous uint8 [n, d] tensor")
+            q.keep_mask = ptr(keep_mask)
+        self.scratch = None
+        if bn is not None:
+            self.stats = torch.empty(2, d, dtype=torch.float32, device=x.device)
+            self.scratch = torch.empty(2, d, dtype=torch.float32, device=x.device)
+            q.gamma, q.beta = ptr(bn.weight), ptr(bn.bias)
+            q.running_mean, q.running_var = ptr(bn.running_mean), ptr(bn.running_var)
+            q.save_mean, q.save_invstd = ptr(self.stats[0]), ptr(self.stats[1])
+            q.eps, q.momentum = float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1)
+        self.q = q
+        self._byref = ctypes.byref
+
+    def forward(self):
+        lib = _lib.load()
+        y = torch.empty(self.x.shape[0], self.x.shape[1], dtype=torch.float32, device=self.x.device)
+        self.q.Y, self.q.ldy = ptr(y), _ld(y)
+        check(lib.glnn_act_train_fwd_f32(self._byref(self.q), ptr(self.scratch), stream()),
+              "glnn_act_train_fwd_f32")
+        if self.bn is not None:
+            self.bn.num_batches_tracked += 1
+        return y
+
+    def backward(self, dy, want_dbias=True):
+        """-> (dX, dgamma, dbeta, dbias)."""
+        lib = _lib.load()
+        require_cuda(dy)
+        _f32(dy)
+        n, d = self.x.shape
+        dev = self.x.device
+        dx = torch.empty(n, d, dtype=torch.float32, device=dev)
+        dg = db = None
+        if self.bn is not None:
+            dg = torch.empty(d, dtype=torch.float32, device=dev)
+            db = torch.empty(d, dtype=torch.float32, device=dev)
+        dbias = torch.empty(d, dtype=torch.float32, device=dev) if want_dbias else None
+        check(lib.glnn_act_train_bwd_f32(self._byref(self.q), ptr(dy), _ld(dy), ptr(dx), _ld(dx), ptr(dg),
+                                         ptr(db), ptr(dbias), ptr(self.scratch), stream()),
+              "glnn_act_train_bwd_f32")
+        return dx, dg, db, dbias
+
+
+def spmm_scatter(indptr, indices, dy, scale, dx, self_add=False):
+    """glnn_spmm_csr_scatter_f32: dx[u] += scale[v] * dy[v] over the edges u -> v (dx pre-initialised)."""
+    lib = _lib.load()
+    require_cuda(indptr, indices, dy, scale, dx)
+    _f32(dy, scale, dx)
+    check(lib.glnn_spmm_csr_scatter_f32(ptr(indptr), int(indptr.dtype == torch.int64), ptr(indices), ptr(dy),
+                                        _ld(dy), ptr(scale), ptr(dx), _ld(dx), indptr.numel() - 1,
+                                        dy.shape[1], int(self_add), stream()), "glnn_spmm_csr_scatter_f32")
+    return dx
+
+
+def sample_neighbors(indptr, indices, seeds, fanout, rng_seed):
+    """glnn_sample_count + glnn_sample_neighbors -> (block indptr int64 [m+1], sampled global source
+    ids int32 [total]) for int64 `seeds`."""
+    lib = _lib.load()
+    require_cuda(indptr, indices, seeds)
+    if seeds.dtype != torch.int64:
+        raise ValueError("seeds must be int64")
+    m = seeds.numel()
+    i64 = int(indptr.dtype == torch.int64)
+    ptr_out = torch.zeros(m + 1, dtype=torch.int64, device=seeds.device)
+    check(lib.glnn_sample_count(ptr(indptr), i64, ptr(seeds), m, int(fanout), ptr(ptr_out[1:]), stream()),
+          "glnn_sample_count")
+    ptr_out[1:].cumsum_(0)
+    total = int(ptr_out[-1])
+    src = torch.empty(total, dtype=torch.int32, device=seeds.device)
+    check(lib.glnn_sample_neighbors(ptr(indptr), i64, ptr(indices), ptr(seeds), m, int(fanout),
+                                    int(rng_seed) & ((1 << 64) - 1), ptr(ptr_out), ptr(src), stream()),
+          "glnn_sample_neighbors")
+    return ptr_out, src
+
+
+def block_mark(src, flag):
+    lib = _lib.load()
+    check(lib.glnn_block_mark(ptr(src), src.numel(), ptr(flag), stream()), "glnn_block_mark")
+
+
+def block_relabel(src, node_map):
+    lib = _lib.load()
+    check(lib.glnn_block_relabel(ptr(src), src.numel(), ptr(node_map), stream()), "glnn_block_relabel")
+    return src
+
+
 class Planes:
     """fp32 matrix kept as bf16 hi / lo planes (see include/glnn_b200.h): .hi/.lo int16 tensors
     [rows, ldp], logical width .cols."""

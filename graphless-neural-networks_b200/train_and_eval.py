@@ -5,7 +5,8 @@ routed to libglnn_b200.so:
                                        host read of the loss per PASS instead of per step)
   evaluate_mini_batch (ref :108-136) -> mlp_engine.eval_forward + fused NLL/accuracy reduction
   evaluate           (ref :89-105)   -> SAGE.inference / GCN.forward kernels + fused reduction
-  train / train_sage (ref :12-56)    -> teacher training, a 'next' row: autograd around the kernels
+  train / train_sage (ref :12-56)    -> teacher_train: forward + hand-written backward + Adam as a
+                                       kernel sequence, device-side neighbour sampling
 
 The runners keep the reference's bookkeeping (early stopping on `>=`, in-memory best state, log
 line formats, loss_and_score rows) because the experiment scripts parse them.
@@ -68,17 +69,14 @@ def _loss_and_score(out, labels, criterion, evaluator, idx_eval):
 # 1. step functions
 # ------------------------------------------------------------------------------------------------
 def train(model, data, feats, labels, criterion, optimizer, idx_train, lamb=1):
-    """Full-batch GNN step (GCN teacher).  Autograd runs over the B200 aggregation / projection
-    kernels (teacher_train.py)."""
-    model.train()
-    logits = model(data, feats)
-    out = logits.log_softmax(dim=1)
-    loss = criterion(out[idx_train], labels[idx_train])
-    loss_val = loss.item()
-    optimizer.zero_grad()
-    (loss * lamb).backward()
-    optimizer.step()
-    return loss_val
+    """Full-batch GNN step (GCN teacher, ref :12-29): forward, log_softmax + NLL, hand-written
+    backward and Adam as one kernel sequence (teacher_train.gcn_train_step) -- no autograd."""
+    from . import teacher_train
+    if not isinstance(model.encoder, GCN):
+        raise NotImplementedError("train(): full-batch training is implemented for the GCN teacher "
+                                  "(SAGE trains with train_sage, MLP with train_mini_batch)")
+    return teacher_train.gcn_train_step(model, data, feats, labels, criterion, optimizer, idx_train,
+                                        lamb).item()
 
 
 def train_sage(model, dataloader, feats, labels, criterion, optimizer, lamb=1):

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define GLNN_ABI_VERSION 1
+#define GLNN_ABI_VERSION 2
 
 #define GLNN_ERR_ARG (-1)       /* null pointer / negative size / unsupported flag combination  */
 #define GLNN_ERR_SHAPE (-2)     /* dimension outside the supported range                        */
@@ -245,8 +245,11 @@ typedef struct glnn_mlp_desc {
   float bn_momentum;   /* 0.1 */
 } glnn_mlp_desc;
 
+/* torch.optim.Adam hyper-parameters (L2 decay, train_student.py:275), in DOUBLE like the Python
+ * floats torch reads them from: 1 - beta and the bias corrections 1 - beta^t are formed in double and
+ * rounded to fp32 once, exactly as torch does (ABI version 2; version 1 carried floats). */
 typedef struct glnn_adam_hparams {
-  float lr, beta1, beta2, eps, weight_decay; /* torch.optim.Adam, L2 decay (train_student.py:275) */
+  double lr, beta1, beta2, eps, weight_decay;
 } glnn_adam_hparams;
 
 /* Number of fp32 elements in the flat parameter buffer / in bn_stats. */
@@ -345,9 +348,16 @@ GLNN_API int glnn_mlp_eval(const glnn_mlp_desc* desc, const float* params, const
  *   norm="both": h = act(D_in^-1/2 A (D_out^-1/2 h) W + b), W first iff d_in > d_out (DGL's rule),
  *   ReLU inside the conv then BN(eval) on hidden layers.  src_norm/dst_norm are the clamped
  *   out/in-degree^-1/2 vectors [n].
- * If log_softmax != 0 the output is log-probabilities (evaluate, train_and_eval.py:97-98).
+ * The `log_softmax` argument is a flag word: GLNN_FWD_LOG_SOFTMAX (1) makes the output
+ * log-probabilities (evaluate, train_and_eval.py:97-98); GLNN_FWD_EXACT (2) selects plain fp32
+ * arithmetic end to end (fp32 gathers, SIMT fp32 projections, DGL's operation order): several times
+ * slower, but its error is fp32 rounding only (~1e-6 of max|logit|), so the raw LOGITS meet
+ * allclose(rtol=1e-4, atol=1e-5) as well; the default mode holds max|a-b|/max|b| <= 1e-4 on logits
+ * (measured ~1e-5) and the allclose form on the log-probabilities.
  * All pointers (including those inside glnn_gnn_layer) are DEVICE pointers.
  */
+#define GLNN_FWD_LOG_SOFTMAX 1
+#define GLNN_FWD_EXACT 2
 typedef struct glnn_gnn_layer {
   const float* weight;   /* SAGE: [d_out, d_in] (nn.Linear);  GCN: [d_in, d_out] (GraphConv) */
   const float* bias;     /* [d_out] */
@@ -368,6 +378,84 @@ GLNN_API int glnn_gcn_forward(const void* indptr, int indptr64, const int32_t* i
                      const glnn_gnn_layer* layers, int num_layers, float* out, int64_t ldo,
                      int log_softmax, void* workspace, int64_t workspace_bytes,
                      glnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Teacher TRAINING: the pieces `train` (train_and_eval.py:12-29) and
+ * `train_sage` (:32-56) need around the aggregation / projection kernels so that one training step is
+ * a kernel sequence with a hand-written backward (no autograd); the sequence itself is laid out by
+ * glnn_b200/teacher_train.py.  The backward of an aggregation is the aggregation over the transposed
+ * CSR (full-batch GCN: built once) or glnn_spmm_csr_scatter_f32 (sampled blocks: no transpose).
+ *
+ * glnn_nll_loss_grad_f32: log_softmax + NLLLoss(mean) over m selected rows and the gradient of
+ *   lamb * loss w.r.t. the logits (train_and_eval.py:21-27,46-53).  Row i of the selection is logits
+ *   row r = rows ? rows[i] : i with label labels[label_rows ? label_rows[i] : r].  Writes
+ *   dlogits[r, 0:c] = lamb / m * (softmax - onehot) for the selected rows only (the caller zeroes
+ *   dlogits when the selection is a subset) and ADDS the unscaled mean loss to *loss_out. */
+GLNN_API int glnn_nll_loss_grad_f32(const float* logits, int64_t ld, int c, const int64_t* labels,
+                           const int64_t* rows, const int64_t* label_rows, int64_t m, float lamb,
+                           float* dlogits, int64_t lddl, float* loss_out, glnn_stream_t stream);
+
+/* The block between two convolutions in TRAIN mode: [BatchNorm1d] -> [ReLU] -> [Dropout]
+ * (SAGE.forward, models.py:113-118) or, for GCN whose ReLU lives inside the conv, [BatchNorm1d] ->
+ * [Dropout] applied to the post-ReLU conv output (models.py:194-198; relu_input = 1 makes the backward
+ * end with the mask X > 0).  BatchNorm uses batch statistics, updates running_mean / running_var with
+ * `momentum` (unbiased variance) and leaves mean / 1/sqrt(var + eps) in save_mean / save_invstd for
+ * the backward.  Dropout keeps an element iff keep_mask[row * d + col] != 0 (parity mode) or, without
+ * a mask, iff a counter-based hash of (seed, row, col) is >= p_drop; kept elements are scaled by
+ * 1 / (1 - p_drop).  The backward recomputes everything from X: only X, the saved statistics and the
+ * seed / mask are kept between the two calls.  scratch: 2 * d floats (BatchNorm only). */
+typedef struct glnn_act_desc {
+  int64_t n;                 /* rows */
+  int32_t d;                 /* columns */
+  int32_t relu_post;         /* SAGE: ReLU after the norm */
+  const float* X;            /* [n, d] block input */
+  int64_t ldx;
+  float* Y;                  /* [n, d] block output (forward only) */
+  int64_t ldy;
+  const float* gamma;        /* BatchNorm1d weight / bias, NULL = no norm */
+  const float* beta;
+  float* running_mean;       /* updated by the forward; may be NULL */
+  float* running_var;
+  float* save_mean;          /* [d] */
+  float* save_invstd;        /* [d] */
+  float eps, momentum;
+  float p_drop;
+  int32_t relu_input;        /* GCN: X = relu(z); the backward multiplies by (X > 0) */
+  uint64_t seed;
+  const uint8_t* keep_mask;  /* optional [n, d] */
+} glnn_act_desc;
+
+GLNN_API int glnn_act_train_fwd_f32(const glnn_act_desc* desc, float* scratch, glnn_stream_t stream);
+/* dX = gradient w.r.t. X given dY; dgamma / dbeta (BatchNorm, may be NULL); dbias (may be NULL) =
+ * column sums of dX = gradient of a bias added in front of the block. */
+GLNN_API int glnn_act_train_bwd_f32(const glnn_act_desc* desc, const float* dY, int64_t lddy, float* dX,
+                           int64_t lddx, float* dgamma, float* dbeta, float* dbias, float* scratch,
+                           glnn_stream_t stream);
+
+/* Transposed aggregation by scatter: dX[u, :] += scale[v] * dY[v, :] for every edge u -> v of the CSR
+ * over destinations (+ dX[v, :] += scale[v] * dY[v, :] with self_add): the backward of
+ * glnn_spmm_csr_f32(self_add, dst_scale = scale) for a sampled block, without building its transpose.
+ * dX must be initialised by the caller (zeros); fp32 atomics, so sums agree to rounding only. */
+GLNN_API int glnn_spmm_csr_scatter_f32(const void* indptr, int indptr64, const int32_t* indices,
+                              const float* dY, int64_t lddy, const float* scale, float* dX, int64_t lddx,
+                              int64_t n_dst, int d, int self_add, glnn_stream_t stream);
+
+/* Neighbour sampling for `train_sage` (dgl MultiLayerNeighborSampler + NodeDataLoader,
+ * train_and_eval.py:179-190) on the device.  glnn_sample_count: counts[i] = min(in_degree(seeds[i]),
+ * fanout) (fanout < 0: the whole neighbourhood).  glnn_sample_neighbors: with out_ptr = exclusive
+ * prefix sum of the counts, writes for every seed its sampled in-edge SOURCES (global ids) to
+ * out_src[out_ptr[i] ...]: all of them when in_degree <= fanout, else `fanout` distinct edges drawn
+ * uniformly without replacement (Floyd's algorithm on a counter-based hash of (rng_seed, seed node)),
+ * in CSR order.  fanout <= 64.  glnn_block_mark sets flag[src] = 1 for every sampled source and
+ * glnn_block_relabel rewrites global ids to block-local ids through map[node] (dst nodes first,
+ * models.py:105-109). */
+GLNN_API int glnn_sample_count(const void* indptr, int indptr64, const int64_t* seeds, int64_t m, int fanout,
+                      int64_t* counts, glnn_stream_t stream);
+GLNN_API int glnn_sample_neighbors(const void* indptr, int indptr64, const int32_t* indices,
+                          const int64_t* seeds, int64_t m, int fanout, uint64_t rng_seed,
+                          const int64_t* out_ptr, int32_t* out_src, glnn_stream_t stream);
+GLNN_API int glnn_block_mark(const int32_t* src, int64_t total, uint8_t* flag, glnn_stream_t stream);
+GLNN_API int glnn_block_relabel(int32_t* src, int64_t total, const int32_t* map, glnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry point (what an out-of-process / non-torch caller binds; used for the e2e

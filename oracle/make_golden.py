@@ -167,7 +167,15 @@ def student_case(name, model_name, n, f, hidden, c, layers, norm, dropout, bs, l
           "perms", len(rec.perms), "masks", len(rec.masks))
 
 
-def teacher_train_case(name, n, e, f, hidden, c, layers, norm, lr, wd, lamb, steps, seed):
+def _mask_extras(rec):
+    extra = {}
+    for i, m in enumerate(rec.masks):
+        extra[f"mask.{i}"] = np.packbits(m.numpy(), axis=None)
+        extra[f"maskshape.{i}"] = np.array(m.shape)
+    return extra
+
+
+def teacher_train_case(name, n, e, f, hidden, c, layers, norm, lr, wd, lamb, steps, seed, dropout=0.0):
     """Full-batch GCN TRAINING steps through the reference's own `train` (train_and_eval.py:12-29):
     autograd through GCN.forward (models.py:189-199) over the shim's GraphConv, torch.optim.Adam.
     dropout_ratio = 0 so that no random mask is involved."""
@@ -176,7 +184,7 @@ def teacher_train_case(name, n, e, f, hidden, c, layers, norm, lr, wd, lamb, ste
     g = dgl_shim.graph((src, dst), num_nodes=n)
     ref_utils.set_seed(seed)
     conf = dict(model_name="GCN", num_layers=layers, feat_dim=f, hidden_dim=hidden, label_dim=c,
-                dropout_ratio=0.0, norm_type=norm, device="cpu")
+                dropout_ratio=dropout, norm_type=norm, device="cpu")
     model = ref_models.Model(conf)
     gen = torch.Generator().manual_seed(seed + 1)
     for lyr in model.encoder.layers:
@@ -187,18 +195,20 @@ def teacher_train_case(name, n, e, f, hidden, c, layers, norm, lr, wd, lamb, ste
     init = sd_np(model, "init.")
     opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
     crit = torch.nn.NLLLoss()
-    losses = [ref_te.train(model, g, feats, labels, crit, opt, idx_train, lamb) for _ in range(steps)]
+    with Recorder() as rec:   # dropout keep-masks the reference drew (none when dropout == 0)
+        losses = [ref_te.train(model, g, feats, labels, crit, opt, idx_train, lamb) for _ in range(steps)]
     out, loss_eval, score_eval = ref_te.evaluate(model, g, feats, labels, crit,
                                                  ref_utils.get_evaluator("cora"), idx_train)
     np.savez_compressed(
         os.path.join(OUT, f"teacher_train_{name}.npz"), src=src, dst=dst, n=n, feats=feats.numpy(),
         labels=labels.numpy(), idx_train=idx_train.numpy(), losses=np.array(losses), lr=lr, wd=wd,
         lamb=lamb, num_layers=layers, hidden=hidden, norm=norm, out=out.detach().numpy(),
-        loss_eval=loss_eval, score_eval=score_eval, **init, **sd_np(model, "final."))
+        dropout=dropout, loss_eval=loss_eval, score_eval=score_eval, **init, **sd_np(model, "final."),
+        **_mask_extras(rec))
     print(name, "train losses", [round(x, 5) for x in losses], "eval", loss_eval, score_eval)
 
 
-def sage_train_case(name, n, e, f, hidden, c, layers, lr, wd, lamb, steps, seed):
+def sage_train_case(name, n, e, f, hidden, c, layers, lr, wd, lamb, steps, seed, norm="none", dropout=0.0):
     """Block-wise GraphSAGE TRAINING steps through the reference's own `train_sage`
     (train_and_eval.py:32-56) and SAGE.forward (models.py:101-119) over the shim's SAGEConv("gcn"):
     ONE batch holding every training seed, FULL neighbourhoods at every hop (blocks built with the
@@ -208,7 +218,7 @@ def sage_train_case(name, n, e, f, hidden, c, layers, lr, wd, lamb, steps, seed)
     g = dgl_shim.graph((src, dst), num_nodes=n)
     ref_utils.set_seed(seed)
     conf = dict(model_name="SAGE", num_layers=layers, feat_dim=f, hidden_dim=hidden, label_dim=c,
-                dropout_ratio=0.0, norm_type="none", device="cpu")
+                dropout_ratio=dropout, norm_type=norm, device="cpu")
     model = ref_models.Model(conf)
     gen = torch.Generator().manual_seed(seed + 1)
     feats = torch.randn(n, f, generator=gen)
@@ -224,11 +234,13 @@ def sage_train_case(name, n, e, f, hidden, c, layers, lr, wd, lamb, steps, seed)
     init = sd_np(model, "init.")
     opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
     crit = torch.nn.NLLLoss()
-    losses = [ref_te.train_sage(model, loader, feats, labels, crit, opt, lamb) for _ in range(steps)]
+    with Recorder() as rec:
+        losses = [ref_te.train_sage(model, loader, feats, labels, crit, opt, lamb) for _ in range(steps)]
     np.savez_compressed(
         os.path.join(OUT, f"teacher_train_{name}.npz"), src=src, dst=dst, n=n, feats=feats.numpy(),
         labels=labels.numpy(), seeds=seeds.numpy(), losses=np.array(losses), lr=lr, wd=wd, lamb=lamb,
-        num_layers=layers, hidden=hidden, **init, **sd_np(model, "final."))
+        num_layers=layers, hidden=hidden, norm=norm, dropout=dropout, **init, **sd_np(model, "final."),
+        **_mask_extras(rec))
     print(name, "train_sage losses", [round(x, 5) for x in losses])
 
 
@@ -284,6 +296,18 @@ def runner_case(name, inductive, n, f, hidden, c, layers, norm, bs, lr, wd, lamb
     print(name, "epochs run", len(hist), "scores", scores, "perms", len(rec.perms))
 
 
+def run_teacher_train_bn_drop_cases():
+    """Round-2 additions: BatchNorm in train mode and dropout (recorded keep-masks) in teacher training."""
+    teacher_train_case("gcn3_bn", n=130, e=650, f=10, hidden=16, c=4, layers=3, norm="batch", lr=0.01,
+                       wd=5e-4, lamb=1.0, steps=3, seed=31)
+    teacher_train_case("gcn2_drop", n=140, e=700, f=20, hidden=16, c=5, layers=2, norm="none", lr=0.01,
+                       wd=1e-3, lamb=1.0, steps=3, seed=32, dropout=0.5)
+    sage_train_case("sage3_bn", n=150, e=800, f=10, hidden=16, c=4, layers=3, lr=0.01, wd=0.0,
+                    lamb=1.0, steps=3, seed=33, norm="batch")
+    sage_train_case("sage2_bn_drop", n=150, e=800, f=12, hidden=24, c=3, layers=2, lr=0.01, wd=5e-4,
+                    lamb=0.8, steps=3, seed=34, norm="batch", dropout=0.3)
+
+
 def run_runner_cases():
     runner_case("tran_none2", False, n=600, f=16, hidden=32, c=5, layers=2, norm="none", bs=64, lr=0.01,
                 wd=5e-4, lamb=0.3, patience=3, max_epoch=6, seed=21)
@@ -299,6 +323,9 @@ if __name__ == "__main__":
     torch.set_num_threads(1)  # bit-stable fixtures
     if "--runners-only" in sys.argv:          # round-2 addition: leaves the older fixtures untouched
         run_runner_cases()
+        sys.exit(0)
+    if "--bn-drop-only" in sys.argv:
+        run_teacher_train_bn_drop_cases()
         sys.exit(0)
     if "--gcn1-only" in sys.argv:
         teacher_case("gcn_1layer", "GCN", n=90, e=400, f=12, hidden=8, c=5, layers=1, norm="none",
@@ -350,3 +377,4 @@ if __name__ == "__main__":
     sage_train_case("sage3_lamb", n=140, e=700, f=9, hidden=20, c=3, layers=3, lr=0.02, wd=0.0,
                     lamb=0.7, steps=3, seed=14)
     run_runner_cases()
+    run_teacher_train_bn_drop_cases()

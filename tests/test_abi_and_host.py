@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
-    assert lib.glnn_version() == 1
+    assert lib.glnn_version() == 2
     assert isinstance(lib.glnn_last_error(), bytes)
 
 
