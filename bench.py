@@ -474,6 +474,26 @@ def student_block(dev, torch, name="MLP3w8", f=100, h=2048, c=47, bs=4096, p_dro
                         "note": "achieved = 3 bf16 MMA products (hi*hi + hi*lo + lo*hi) per fp32 "
                                 "multiply-add of the step's algorithmic flops, per GPU"}}
     if world > 1:
+        # e3: evaluate_mini_batch sharded by contiguous node ranges + all-gather of the log-probs,
+        # against the same rows evaluated by this rank alone (every rank holds the same parameters)
+        try:
+            model.eval()
+            grp = model.encoder._dp_group
+            ev_ms = _event_ms(lambda: mlp_engine.eval_forward(model.encoder, x), 3, torch)
+            sharded = mlp_engine.eval_forward(model.encoder, x)
+            model.encoder._dp_group = None
+            alone = mlp_engine.eval_forward(model.encoder, x)
+            model.encoder._dp_group = grp
+            d = torch.tensor([float((sharded - alone).abs().max())], device=dev)
+            dist.all_reduce(d, op=dist.ReduceOp.MAX)
+            t_ev = torch.tensor([ev_ms], device=dev)
+            dist.all_reduce(t_ev, op=dist.ReduceOp.MAX)
+            blk["eval_sharded"] = {"rows": n, "ms": float(t_ev), "nodes_per_s": n / (float(t_ev) * 1e-3),
+                                   "max_abs_diff_vs_unsharded": float(d),
+                                   "note": "evaluate_mini_batch over contiguous node ranges per rank + "
+                                           "all-gather of the log-probabilities (SURVEY 8e row 3)"}
+        except Exception as ex:
+            blk["eval_sharded"] = {"error": repr(ex)}
         return blk
     # ---- parity: first step's loss from the initial state against the fp64 oracle (dropout off)
     try:
@@ -818,7 +838,8 @@ def run_b200(args):
         if rank == 0:
             clocks.stop()
             _emit({"metric": METRIC, "value": n / (ms * 1e-3), "unit": "nodes/s",
-                   "n_gpus": world, "ms_per_step": ms, "light": True})
+                   "n_gpus": world, "ms_per_step": ms, "light": True,
+                   "shards": gathered if world > 1 else None})
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()

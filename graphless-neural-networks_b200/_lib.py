@@ -35,7 +35,8 @@ class SpmmDesc(C.Structure):
                 ("ldq", c_i64), ("Y", c_vp), ("ldy", c_i64), ("Y_hi", c_vp), ("Y_lo", c_vp),
                 ("ldyp", c_i64), ("self_add", c_i32), ("mean_plus_one", c_i32), ("src_scale", c_vp),
                 ("dst_scale", c_vp), ("bias", c_vp), ("col_scale", c_vp), ("col_shift", c_vp),
-                ("relu", c_i32), ("log_softmax", c_i32), ("hot_below", c_i32), ("reserved", c_i32)]
+                ("relu", c_i32), ("log_softmax", c_i32), ("hot_below", c_i32), ("reserved", c_i32),
+                ("Y_init", c_vp), ("ldyi", c_i64)]
 
 
 class DpGroup(C.Structure):
@@ -109,6 +110,7 @@ SIGNATURES = {
     "glnn_gcn_forward": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64,
                                    C.POINTER(GnnLayer), C.c_int, c_vp, c_i64, C.c_int, c_vp, c_i64,
                                    c_vp]),
+    "glnn_peer_push": (C.c_int, [c_vp, C.POINTER(c_vp), C.c_int, c_i64, C.c_int, c_vp]),
     "glnn_nll_loss_grad_f32": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_vp, c_vp, c_i64, c_f32, c_vp, c_i64,
                                          c_vp, c_vp]),
     "glnn_act_train_fwd_f32": (C.c_int, [C.POINTER(ActDesc), c_vp, c_vp]),

@@ -32,17 +32,23 @@ namespace tall {
 using namespace tc;
 
 constexpr int BM = 128;
-constexpr int BK = 64;
+// k-block of one pipeline stage: a template parameter.  64 (SWIZZLE_128B rows) gives 2 / 3 / 4 stages
+// at N = 256 / 128 / 64; 32 (SWIZZLE_64B rows) halves the stage and doubles the ring depth.  Round 2
+// measured both on the products forward (GLNN_TALL_BK): 1.17 / 1.27 / 0.60 ms (64) against 1.23 /
+// 1.31 / 0.71 ms (32) for the three projections -- the deeper ring does not help, so the ring depth
+// is not what holds the kernel at 41 % tensor-pipe activity; 64 stays the default.
 constexpr int EPI_WARPS = 8;
 constexpr int NTHREADS = 64 + EPI_WARPS * 32;
 constexpr int SLAB = 32;  // columns per epilogue slab
 
-template <int BN>
+template <int BN, int BK>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 2;  // one bf16 plane of one stage
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int STAGES = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int STAGES = (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) * (64 / BK);
+  static constexpr uint32_t SBO = 8 * BK * 2;            // bytes between 8-row groups of a plane
+  static constexpr uint32_t LAYOUT = BK == 64 ? 2 : 4;   // SWIZZLE_128B / SWIZZLE_64B
   static constexpr int STAGING = EPI_WARPS * 16 * SLAB * 4;  // 16 rows x 32 fp32 columns per epilogue warp
   static constexpr int EPI_VEC = 3 * BN * 4;                 // bias, BN scale, BN shift (padded to BN)
   static constexpr int TOTAL = STAGES * STAGE + STAGING + EPI_VEC + 1024 /*alignment slack*/ +
@@ -87,12 +93,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
-template <int BN>
+template <int BN, int BK>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tall_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap map_ah,
                  const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_bh,
                  const __grid_constant__ CUtensorMap map_bl) {
-  using S = Cfg<BN>;
+  using S = Cfg<BN, BK>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B atoms
   float* epi_vec = reinterpret_cast<float*>(tiles + S::STAGES * S::STAGE + S::STAGING);
@@ -178,9 +184,10 @@ gemm_tall_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap map_ah,
           mbar_wait(&full[s], (it / S::STAGES) & 1);
           tc_fence_after();
           const uint32_t st = smem_u32(tiles + s * S::STAGE);
-          const uint64_t a_hi = make_desc(st, 16, 1024), a_lo = make_desc(st + S::A_BYTES, 16, 1024);
-          const uint64_t b_hi = make_desc(st + 2 * S::A_BYTES, 16, 1024),
-                         b_lo = make_desc(st + 2 * S::A_BYTES + S::B_BYTES, 16, 1024);
+          const uint64_t a_hi = make_desc(st, 16, S::SBO, S::LAYOUT),
+                         a_lo = make_desc(st + S::A_BYTES, 16, S::SBO, S::LAYOUT);
+          const uint64_t b_hi = make_desc(st + 2 * S::A_BYTES, 16, S::SBO, S::LAYOUT),
+                         b_lo = make_desc(st + 2 * S::A_BYTES + S::B_BYTES, 16, S::SBO, S::LAYOUT);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t dk = static_cast<uint64_t>(k * 2);  // 16 bf16 = 32 bytes, in 16-byte units
@@ -303,39 +310,41 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// bf16 matrix [rows, cols] with row stride ld elements; box = 64 columns x box_rows rows, 128-byte
-// swizzle, out-of-bounds elements read as zero (ragged K, ragged last row tile, N < BN).
+// bf16 matrix [rows, cols] with row stride ld elements; box = bk columns x box_rows rows, swizzle
+// over the box row (128 bytes at bk = 64, 64 bytes at bk = 32), out-of-bounds elements read as zero
+// (ragged K, ragged last row tile, N < BN).
 static int make_map(CUtensorMap* map, const uint16_t* base, int64_t rows, int64_t cols, int64_t ld,
-                    int box_rows) {
+                    int box_rows, int bk) {
   EncodeTiledFn fn = encode_fn();
   GLNN_REQUIRE(fn != nullptr, GLNN_ERR_DEVICE, "gemm_tall: cuTensorMapEncodeTiled not available");
   const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(bk), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), dims,
-                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GLNN_REQUIRE(r == CUDA_SUCCESS, GLNN_ERR_ARG, "gemm_tall: cuTensorMapEncodeTiled failed (%d)",
                static_cast<int>(r));
   return 0;
 }
 
-template <int BN>
+template <int BN, int BK>
 static int launch(const GemmArgs& g, cudaStream_t st) {
-  using S = Cfg<BN>;
+  using S = Cfg<BN, BK>;
   static bool configured = false;
-  auto kern = gemm_tall_kernel<BN>;
+  auto kern = gemm_tall_kernel<BN, BK>;
   if (!configured) {
     GLNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
   }
   CUtensorMap mah, mal, mbh, mbl;
   int rc;
-  if ((rc = make_map(&mah, g.Ah, g.M, g.K, g.lda, BM))) return rc;
-  if ((rc = make_map(&mal, g.Al, g.M, g.K, g.lda, BM))) return rc;
-  if ((rc = make_map(&mbh, g.Bh, g.N, g.K, g.ldb, BN))) return rc;
-  if ((rc = make_map(&mbl, g.Bl, g.N, g.K, g.ldb, BN))) return rc;
+  if ((rc = make_map(&mah, g.Ah, g.M, g.K, g.lda, BM, BK))) return rc;
+  if ((rc = make_map(&mal, g.Al, g.M, g.K, g.lda, BM, BK))) return rc;
+  if ((rc = make_map(&mbh, g.Bh, g.N, g.K, g.ldb, BN, BK))) return rc;
+  if ((rc = make_map(&mbl, g.Bl, g.N, g.K, g.ldb, BN, BK))) return rc;
   const int ntiles = static_cast<int>((g.M + BM - 1) / BM);
   const int grid = std::min(ntiles, sm_count());
   kern<<<grid, NTHREADS, S::TOTAL, st>>>(g, mah, mal, mbh, mbl);
@@ -355,9 +364,16 @@ int gemm_tall_planes(const GemmArgs& g, cudaStream_t st, bool* taken) {
   if (g.M < static_cast<int64_t>(tall::BM) * sm_count()) return 0;
   if (g.M >= (1LL << 31) - tall::BM) return 0;  // TMA coordinates are int32
   int rc;
-  if (g.N > 128) rc = tall::launch<256>(g, st);
-  else if (g.N > 64) rc = tall::launch<128>(g, st);
-  else rc = tall::launch<64>(g, st);
+  static const bool bk64 = !(getenv("GLNN_TALL_BK") != nullptr && atoi(getenv("GLNN_TALL_BK")) == 32);
+  if (bk64) {  // default
+    if (g.N > 128) rc = tall::launch<256, 64>(g, st);
+    else if (g.N > 64) rc = tall::launch<128, 64>(g, st);
+    else rc = tall::launch<64, 64>(g, st);
+  } else {
+    if (g.N > 128) rc = tall::launch<256, 32>(g, st);
+    else if (g.N > 64) rc = tall::launch<128, 32>(g, st);
+    else rc = tall::launch<64, 32>(g, st);
+  }
   if (rc != 0) return rc;
   *taken = true;
   return 0;

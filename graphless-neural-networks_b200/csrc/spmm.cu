@@ -72,6 +72,10 @@ struct SpmmArgs {
   // L2 residency hints: gathered rows of source ids < hot_below are loaded evict_last, all other
   // gathered rows, the index stream and the output stream evict_first (0 = no hints)
   int hot_below;
+  // optional initial value of the accumulators: acc[v, :] starts from Yinit[v, :] (fp32, ldyi) instead
+  // of zero -- the second pass of an aggregation that was split by source block (dist_teacher.py)
+  const float* Yinit;
+  int64_t ldyi;
   // optional sparse copy of the gathered matrix ("s24", see glnn_compact_s24): row = `cap` words
   // [fp32 bits 31..8 | column 7..0] sorted by column, zero-padded, rows lds words apart; *cap_dev =
   // max non-zeros per row.  Used by spmm_csr_s24_kernel only; Xq stays the self / hub / dense source.
@@ -348,6 +352,11 @@ __device__ __forceinline__ void epilogue_store(const SpmmArgs& a, int64_t row, i
     if (col >= a.d) continue;
     float self[W];
     if (a.self_add) load_chunk<W>(a, row, col, self, pol.cold);
+    if (a.Yinit) {
+#pragma unroll
+      for (int w = 0; w < W; ++w)
+        if (col + w < a.d) acc[p][w] += __ldg(a.Yinit + row * a.ldyi + col + w);
+    }
 #pragma unroll
     for (int w = 0; w < W; ++w) {
       float x = acc[p][w];
@@ -982,6 +991,7 @@ int spmm_run(const glnn_spmm_desc& d0, cudaStream_t st) {
   GLNN_REQUIRE(!q.log_softmax || (q.Y && !q.Y_hi && d <= 512 && q.ldy >= q.log_softmax), GLNN_ERR_ARG,
                "spmm: the log_softmax epilogue writes fp32 Y only, d <= 512, ldy >= log_softmax");
   GLNN_REQUIRE(q.hot_below >= 0, GLNN_ERR_ARG, "spmm: hot_below must be >= 0");
+  GLNN_REQUIRE(!q.Y_init || q.ldyi >= d, GLNN_ERR_SHAPE, "spmm: ldyi < d");
   HubScratch hs;
   int rc = hub_scratch(st, &hs);
   if (rc != 0) return rc;
@@ -1021,6 +1031,8 @@ int spmm_run(const glnn_spmm_desc& d0, cudaStream_t st) {
     a.log_softmax = q.log_softmax > 0;
     a.d_valid = q.log_softmax;
     a.hot_below = q.hot_below;
+    a.Yinit = q.Y_init ? q.Y_init + c0 : nullptr;
+    a.ldyi = q.ldyi;
     a.Xs = nullptr;
     a.lds = 0;
     a.cap_dev = nullptr;
@@ -1085,6 +1097,7 @@ int spmm_run_s24(const glnn_spmm_desc& q, const uint32_t* S, int64_t lds, const 
   a.src_scale = nullptr; a.dst_scale = q.dst_scale; a.bias = q.bias;
   a.col_scale = q.col_scale; a.col_shift = q.col_shift; a.relu = q.relu;
   a.log_softmax = 0; a.d_valid = 0; a.hot_below = q.hot_below;
+  a.Yinit = q.Y_init; a.ldyi = q.ldyi;
   a.Xs = S; a.lds = lds; a.cap_dev = cap_dev;
   a.cap_limit = (q.ldq * 4 / 5) / 4;  // sparse rows must be at least 20 % shorter than the q24 rows
   a.hub_ctr = hs.ctr; a.hub_tasks = hs.tasks; a.hub_rows = hs.rows; a.hub_acc = hs.acc;

@@ -51,7 +51,9 @@ class ShardedGraph:
         self.cuts = nnz_balanced_cuts(g.indptr, world)
         rows_max = max(max(self.cuts[i + 1] - self.cuts[i] for i in range(world)), 1)
         if chunks is None:  # pipeline the exchange only when a chunk is still a big kernel
-            chunks = 4 if (world > 1 and rows_max >= 4 * 32768) else 1
+            import os
+            want = int(os.environ.get("GLNN_DIST_CHUNKS", "4"))
+            chunks = want if (world > 1 and rows_max >= want * 32768) else 1
         self.chunks = chunks
         self.rc = (rows_max + chunks - 1) // chunks          # rows per chunk and rank
         self.rows_max = self.rc * chunks                      # padded rows per rank
@@ -88,6 +90,43 @@ class ShardedGraph:
         owner.clamp_(0, self.world - 1)
         local = nodes - self._cuts_t[owner]
         return (local // self.rc) * (self.world * self.rc) + owner * self.rc + local % self.rc
+
+    def early_owners(self):
+        """Source owners whose slabs a rank waits for FIRST when the consuming aggregation is split
+        into two passes: itself and the next world/2 - 1 ranks (so that every rank is "early" for
+        world/2 - 1 peers and "late" for the others)."""
+        h = max(1, self.world // 2)
+        return [(self.rank + i) % self.world for i in range(h)]
+
+    def early_receivers(self):
+        """Peers that need THIS rank's slab first (those that list it among their early owners)."""
+        h = max(1, self.world // 2)
+        return [(self.rank - i) % self.world for i in range(1, h)]
+
+    def split_by_owner(self):
+        """The local CSR cut into two CSRs over the same rows: edges whose source row is owned by an
+        early owner (the self edge included) and the rest.  Cached."""
+        hit = self.__dict__.get("_split")
+        if hit is None:
+            dev = self.indices.device
+            cols = self.indices.to(torch.int64)
+            owner = (cols // self.rc) % self.world
+            early_mask = torch.zeros(self.world, dtype=torch.bool, device=dev)
+            early_mask[torch.tensor(self.early_owners(), device=dev)] = True
+            is_early = early_mask[owner]
+            ptr = self.indptr.to(torch.int64)
+            deg = ptr[1:] - ptr[:-1]
+            row = torch.repeat_interleave(torch.arange(self.rows, device=dev), deg)
+            out = []
+            for m in (is_early, ~is_early):
+                cnt = torch.bincount(row[m], minlength=self.rows)
+                p = torch.zeros(self.rows + 1, dtype=torch.int64, device=dev)
+                torch.cumsum(cnt, 0, out=p[1:])
+                idx = self.indices[m].contiguous()          # boolean mask keeps the CSR order
+                out.append((p.to(torch.int32) if idx.numel() < 2 ** 31 else p, idx))
+            hit = tuple(out)
+            self._split = hit
+        return hit
 
     def chunk_rows(self, c):
         """Local row range [a, b) of chunk c (may be empty for the last chunks of a short shard)."""
@@ -144,15 +183,40 @@ def _push_mode():
     return os.environ.get("GLNN_EXCHANGE", "push").lower() != "nccl"
 
 
+def _push_engine():
+    """Who moves a slab to the peers: "sm" (default) = glnn_peer_push, a small kernel whose posted
+    stores run the links at ~0.75 TB/s per direction; "ce" = one cudaMemcpyPeerAsync per peer on the
+    copy engines (round 1: 0.37-0.45 TB/s per rank at N=8 under the HBM-saturating gather)."""
+    import os
+    return os.environ.get("GLNN_PUSH_ENGINE", "sm").lower()
+
+
+def _push_ctas():
+    import os
+    return int(os.environ.get("GLNN_PUSH_CTAS", "32"))
+
+
+def _two_pass():
+    """Two-pass consumption of an exchanged replica (GLNN_DIST_TWO_PASS, default on): the producing
+    layer pushes every chunk to the peers that need it first, then to the others; the consuming
+    aggregation runs a first pass over the edges whose sources are already here (own rows + early
+    owners: half of the edges) while the late slabs are still in flight, and a second pass over the
+    rest on top of the fp32 partial sums (glnn_spmm_csr Y_init)."""
+    import os
+    return os.environ.get("GLNN_DIST_TWO_PASS", "1") not in ("", "0")
+
+
 def _replicate_projection():
     """Exchange policy for an aggregate-first layer whose successor is aggregate-first as well
-    (ogbn-products layer 0: 100 -> 256).  "1" (default): ship the NARROW aggregated operand (d_in
+    (ogbn-products layer 0: 100 -> 256).  "1" (opt-in, GLNN_DIST_REPLICATE): ship the NARROW aggregated operand (d_in
     columns as bf16 hi/lo planes) and let every rank project all N rows itself -- the projection is
     HBM-bound and cheap (0.5 ms for all 2.45 M rows), the exchange is what limits scaling (round 1:
     3.9 of 9.75 ms exposed at N=8 for 1.65 GB per rank of 256-wide q24 rows; the planes of the
-    100-wide operand are 0.89 GB).  "0": project the owned rows and ship the wide q24 output."""
+    100-wide operand are 0.89 GB).  "0" (default): project the owned rows and ship the wide q24
+    output.  Measured at N=2: replication costs 1.38 ms for the all-rows projection and loses 0.6 ms
+    per forward; it only pays where the exchange cannot be hidden."""
     import os
-    return os.environ.get("GLNN_DIST_REPLICATE", "1") not in ("", "0")
+    return os.environ.get("GLNN_DIST_REPLICATE", "0") not in ("", "0")
 
 
 def _symm_replica(sg, key, rows, row_bytes, dev, group):
@@ -198,6 +262,38 @@ class _Exchange:
                                         lambda: [torch.cuda.Stream(priority=-1)
                                                  for _ in range(sg.world - 1)])
 
+    def chunk_two_phase(self, buf2d, c, events):
+        """Two-phase variant of chunk(): records the chunk's ready event; the pushes themselves are
+        issued by flush_two_phase() -- first every chunk to the EARLY receivers, then to the rest."""
+        ev = torch.cuda.Event()
+        ev.record()
+        events.append((c, ev))
+
+    def flush_two_phase(self, buf2d, events):
+        """Issues, on the push stream: [chunk -> early receivers] for all chunks, a barrier across the
+        ranks ("early slabs have landed everywhere"), [chunk -> late receivers] for all chunks, a second
+        barrier.  Returns (early_done, late_done) events for the consumer to wait on."""
+        sg = self.sg
+        _, hdl, peers = sg.__dict__["_symm_by_ptr"][buf2d.data_ptr()]
+        early = sg.early_receivers()
+        late = [(sg.rank + i) % sg.world for i in range(1, sg.world) if (sg.rank + i) % sg.world not in early]
+        st = self.peer_streams[0]
+        done = []
+        for group, channel in ((early, 2), (late, 3)):
+            for c, ev in events:
+                s0 = sg.slab_start(c)
+                st.wait_event(ev)
+                if group:
+                    with torch.cuda.stream(st):
+                        ops.peer_push(buf2d[s0: s0 + sg.rc], [peers[p][s0: s0 + sg.rc] for p in group],
+                                      _push_ctas())
+            with torch.cuda.stream(st):
+                hdl.barrier(channel=channel)
+                e = torch.cuda.Event()
+                e.record()
+            done.append(e)
+        return done
+
     def chunk(self, buf2d, c):
         sg = self.sg
         if sg.world == 1:
@@ -218,12 +314,21 @@ class _Exchange:
                 dist.all_gather_into_tensor(whole, mine, group=self.group)
             return
         _, hdl, peers = symm_hit
-        for i in range(1, sg.world):   # staggered targets: rank r's stream i writes to rank r+i
-            peer = (sg.rank + i) % sg.world
-            st = self.peer_streams[i - 1]
+        if _push_engine() == "sm":
+            # one SM-driven kernel: a 16-byte load of the slab feeds G-1 posted NVLink stores
+            # (staggered targets: rank r writes r+1, r+2, ... first)
+            order = [(sg.rank + i) % sg.world for i in range(1, sg.world)]
+            st = self.peer_streams[0]
             st.wait_event(ev)
             with torch.cuda.stream(st):
-                peers[peer][s0: s0 + sg.rc].copy_(mine, non_blocking=True)
+                ops.peer_push(mine, [peers[p][s0: s0 + sg.rc] for p in order], _push_ctas())
+        else:
+            for i in range(1, sg.world):   # copy engines: rank r's stream i writes to rank r+i
+                peer = (sg.rank + i) % sg.world
+                st = self.peer_streams[i - 1]
+                st.wait_event(ev)
+                with torch.cuda.stream(st):
+                    peers[peer][s0: s0 + sg.rc].copy_(mine, non_blocking=True)
         self.pending = hdl
 
     def wait(self, what):
@@ -344,6 +449,7 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
                 k.gemm(op_rows, w, trans_b=True, out=buf[s0:s0 + (b_row - a)], **kw)
 
     # ---- layer loop
+    pending = None             # (early_done, late_done) events of a replica whose slabs are still landing
     h_rep, h_op = None, None   # replica (gather input) / operand (projection input) of the current h
     if not proj_first(0):
         d0 = layers[0][0].shape[1]
@@ -387,13 +493,34 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
                     h_op = k.split_planes(mine)
                 else:
                     h_op[: sg.rows] = mine
+            two_phase = cuda and world > 1 and _push_mode() and _push_engine() == "sm" and _two_pass()
+            z_events = []
             for c in range(C):
                 a, e = sg.chunk_rows(c)
                 if e > a:
                     project(rows_of(h_op, a, e), wp, wpl, None, None, None, 0, ("replica", z_rep), a, e, c)
-                xch.chunk(replica_2d(z_rep), c)
+                if two_phase:
+                    xch.chunk_two_phase(replica_2d(z_rep), c, z_events)
+                else:
+                    xch.chunk(replica_2d(z_rep), c)
             mark(f"L{l} gemm {d_in}->{dpad}")
-            xch.wait(f"L{l} exchange z ({dpad} wide)")
+            z_init = None
+            if two_phase:
+                # first pass over the sources already here while the late slabs of z are in flight
+                z_early, z_late = xch.flush_two_phase(replica_2d(z_rep), z_events)
+                (pe, ie), (pl_, il) = sg.split_by_owner()
+                z_init = _cached(sg, ("zpartial", l), lambda: torch.empty(max(sg.rows, 1), (dpad + 7) // 8 * 8,
+                                                                         dtype=torch.float32, device=dev))
+                torch.cuda.current_stream().wait_event(z_early)
+                k.spmm(pe, ie, z_rep, d=dpad, out=z_init[: sg.rows])
+                mark(f"L{l} spmm d={dpad}, pass 1 (own + early source blocks)")
+                torch.cuda.current_stream().wait_event(z_late)
+                mark(f"L{l} wait for the late source blocks")
+                g_ptr, g_idx = pl_, il
+            else:
+                xch.wait(f"L{l} exchange z ({dpad} wide)")
+                g_ptr, g_idx = sg.indptr, sg.indices
+            init_rows = (lambda a, e: None) if z_init is None else (lambda a, e: z_init[a:e])
             nxt_pf = (not last) and proj_first(l + 1)
             if last:
                 # bias (+ log_softmax) fused into the gather epilogue, straight into the padded output
@@ -403,11 +530,11 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
                         continue
                     s0 = sg.slab_start(c)
                     if cuda and log_softmax:
-                        k.spmm(sg.indptr[a:e + 1], sg.indices, z_rep, d=dpad, out=out[s0:s0 + (e - a)],
-                               dst_scale=sg.inv_deg1[a:e], bias=bp, log_softmax=d_out)
+                        k.spmm(g_ptr[a:e + 1], g_idx, z_rep, d=dpad, out=out[s0:s0 + (e - a)],
+                               dst_scale=sg.inv_deg1[a:e], bias=bp, log_softmax=d_out, acc_init=init_rows(a, e))
                     elif cuda:
-                        y = k.spmm(sg.indptr[a:e + 1], sg.indices, z_rep, d=dpad,
-                                   dst_scale=sg.inv_deg1[a:e], bias=bp)
+                        y = k.spmm(g_ptr[a:e + 1], g_idx, z_rep, d=dpad,
+                                   dst_scale=sg.inv_deg1[a:e], bias=bp, acc_init=init_rows(a, e))
                         out[s0:s0 + (e - a)] = y[:, :d_out]
                     else:
                         y = k.spmm_csr(sg.indptr[a:e + 1], sg.indices, z_rep, d=dpad,
@@ -418,8 +545,9 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
             else:
                 y_op = new_operand(("y_op", l), dpad)
                 if cuda:
-                    k.spmm(sg.indptr, sg.indices, z_rep, d=dpad, out_planes=rows_of(y_op, 0, sg.rows),
-                           dst_scale=sg.inv_deg1, bias=bp, col_scale=scale, col_shift=shift, relu=relu)
+                    k.spmm(g_ptr, g_idx, z_rep, d=dpad, out_planes=rows_of(y_op, 0, sg.rows),
+                           dst_scale=sg.inv_deg1, bias=bp, col_scale=scale, col_shift=shift, relu=relu,
+                           acc_init=None if z_init is None else z_init[: sg.rows])
                 else:
                     k.spmm_csr(sg.indptr, sg.indices, z_rep, d=dpad, out=y_op[: sg.rows],
                                dst_scale=sg.inv_deg1, bias=bp, col_scale=scale, col_shift=shift, relu=relu)
@@ -470,15 +598,45 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
                 dest = ("operand", new_operand(("y_op", l), d_out))
             else:
                 dest = ("replica", new_replica(("yrep", l), d_out))
+            two_phase = (dest[0] == "replica" and cuda and world > 1 and _push_mode()
+                         and _push_engine() == "sm" and _two_pass())
+            pend_events = []
+            if pending is not None:
+                # this layer's input replica is still arriving: first pass over the sources that are
+                # already here (own rows + early owners), for ALL local rows, into fp32 partial sums
+                (pe, ie), (pl_, il) = sg.split_by_owner()
+                partial = _cached(sg, ("partial", l), lambda: torch.empty(max(sg.rows, 1), (d_in + 7) // 8 * 8,
+                                                                         dtype=torch.float32, device=dev))
+                torch.cuda.current_stream().wait_event(pending[0])
+                k.spmm(pe, ie, h_rep, d=d_in, out=partial[: sg.rows])
+                mark(f"L{l} spmm d={d_in}, pass 1 (own + early source blocks)")
+                torch.cuda.current_stream().wait_event(pending[1])
+                mark(f"L{l} wait for the late source blocks")
             for c in range(C):
                 a, e = sg.chunk_rows(c)
                 if e > a:
-                    aggregate(h_rep, d_in, a, e, agg)
+                    if pending is not None:   # second pass: the late blocks, on top of the partial sums
+                        k.spmm(pl_[a:e + 1], il, h_rep, d=d_in, out_planes=rows_of(agg, a, e),
+                               dst_scale=sg.inv_deg1[a:e], acc_init=partial[a:e])
+                    else:
+                        aggregate(h_rep, d_in, a, e, agg)
                     project(rows_of(agg, a, e), w, wpl, b, scale, shift, relu, dest, a, e, c)
                 if dest[0] == "replica":
-                    xch.chunk(replica_2d(dest[1]), c)
-            mark(f"L{l} spmm d={d_in} + gemm {d_in}->{d_out}")
-            if dest[0] == "replica":
+                    if two_phase:
+                        xch.chunk_two_phase(replica_2d(dest[1]), c, pend_events)
+                    else:
+                        xch.chunk(replica_2d(dest[1]), c)
+            mark(f"L{l} spmm d={d_in}" + (", pass 2" if pending is not None else "") + f" + gemm {d_in}->{d_out}")
+            pending = None
+            if dest[0] == "replica" and two_phase and (l + 1 < L) and not proj_first(l + 1):
+                pending = xch.flush_two_phase(replica_2d(dest[1]), pend_events)
+                h_rep, h_op = dest[1], None
+            elif dest[0] == "replica" and two_phase:
+                done = xch.flush_two_phase(replica_2d(dest[1]), pend_events)
+                torch.cuda.current_stream().wait_event(done[1])
+                mark(f"L{l} exchange output ({d_out} wide)")
+                h_rep, h_op = dest[1], None
+            elif dest[0] == "replica":
                 xch.wait(f"L{l} exchange output ({d_out} wide)")
                 h_rep, h_op = dest[1], None
             elif dest[0] == "operand":

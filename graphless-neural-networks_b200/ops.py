@@ -111,6 +111,18 @@ def adam_step(params, grads, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), 
     return params
 
 
+def peer_push(src, dsts, ctas=0):
+    """glnn_peer_push: contiguous `src` -> every tensor of `dsts` (peer-mapped views of the same
+    shape), one SM-driven kernel on the current stream."""
+    import ctypes
+    lib = _lib.load()
+    if not src.is_contiguous() or any(not d.is_contiguous() for d in dsts):
+        raise ValueError("peer_push: contiguous slabs expected")
+    nbytes = src.numel() * src.element_size()
+    arr = (ctypes.c_void_p * max(len(dsts), 1))(*[d.data_ptr() for d in dsts])
+    check(lib.glnn_peer_push(ptr(src), arr, len(dsts), nbytes, int(ctas), stream()), "glnn_peer_push")
+
+
 def nll_loss_grad(logits, labels, rows=None, label_rows=None, lamb=1.0, dlogits=None, loss_out=None):
     """glnn_nll_loss_grad_f32 -> (dlogits, loss_out).  rows / label_rows: int64 selections (see the
     header); dlogits is zero-initialised here when a subset of the rows is selected."""
@@ -378,7 +390,7 @@ def gemm_planes_q24(a, b, trans_b=True, out=None, row_scale=None, bias=None, col
 
 def spmm(indptr, indices, x, d=None, out=None, out_planes=None, self_add=False, mean_plus_one=False,
          src_scale=None, dst_scale=None, bias=None, col_scale=None, col_shift=None, relu=0,
-         log_softmax=0, hot_below=0, s24=None):
+         log_softmax=0, hot_below=0, s24=None, acc_init=None):
     """glnn_spmm_csr (general form).  x: fp32 tensor [n_src, >= d] or Q24; result in `out` (fp32
     tensor) and/or `out_planes` (Planes); if neither is given an fp32 tensor is allocated.
     log_softmax = c > 0 ends the epilogue with log_softmax over the first c columns (fp32 out
@@ -417,6 +429,10 @@ def spmm(indptr, indices, x, d=None, out=None, out_planes=None, self_add=False, 
     q.src_scale, q.dst_scale, q.bias = ptr(src_scale), ptr(dst_scale), ptr(bias)
     q.col_scale, q.col_shift, q.relu = ptr(col_scale), ptr(col_shift), int(relu)
     q.log_softmax, q.hot_below = int(log_softmax), int(hot_below)
+    if acc_init is not None:   # accumulators start from this fp32 [n_dst, >= d] matrix
+        require_cuda(acc_init)
+        _f32(acc_init)
+        q.Y_init, q.ldyi = ptr(acc_init), _ld(acc_init)
     import ctypes
     if s24 is not None:
         check(lib.glnn_spmm_csr_s24(ctypes.byref(q), ptr(s24.data), s24.data.stride(0), ptr(s24.cap),

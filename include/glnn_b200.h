@@ -151,6 +151,9 @@ GLNN_API int glnn_spmm_csr_q24_planes(const void* indptr, int indptr64, const in
  *   log_softmax = c > 0: the epilogue ends with log_softmax over the first c columns and writes only
  *     those (Y fp32, any ldy >= c): evaluate()'s log_softmax (train_and_eval.py:98) fused into the
  *     last layer's aggregation.  d <= 512.
+ *   Y_init != NULL: the row sums start from Y_init[v, :] (before the self term / mean / scales):
+ *     acc = Y_init + sum over the edges.  Lets a caller split the edge set of an aggregation into
+ *     passes (first pass: fp32 Y, no epilogue; last pass: Y_init = that Y, full epilogue).
  *   hot_below = k > 0: L2 residency hint.  Gathered rows of source ids < k are loaded with the
  *     evict_last policy, every other access of the kernel (cold rows, indices, output) evict_first,
  *     so that the most-referenced rows of a degree-ordered graph stay in the 126 MB L2.  Purely a
@@ -181,6 +184,8 @@ typedef struct glnn_spmm_desc {
   int32_t log_softmax;
   int32_t hot_below;
   int32_t reserved;
+  const float* Y_init;    /* optional: acc[v, :] starts from Y_init[v, 0:d] (fp32) instead of 0 -- the   */
+  int64_t ldyi;           /* second pass of an aggregation split by source block (sharded teacher)   */
 } glnn_spmm_desc;
 
 GLNN_API int glnn_spmm_csr(const glnn_spmm_desc* desc, glnn_stream_t stream);
@@ -378,6 +383,17 @@ GLNN_API int glnn_gcn_forward(const void* indptr, int indptr64, const int32_t* i
                      const glnn_gnn_layer* layers, int num_layers, float* out, int64_t ldo,
                      int log_softmax, void* workspace, int64_t workspace_bytes,
                      glnn_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sharded teacher: the per-layer embedding exchange.  glnn_peer_push copies
+ * `bytes` (a multiple of 16) from this rank's slab `src` to the same data at dst[0..n_dst) -- peer-
+ * mapped addresses of the other ranks' replicas (torch symmetric memory / cuMem / CUDA IPC) -- with a
+ * small SM-driven kernel of `ctas` CTAs (<= 0: 32): one load, n_dst posted NVLink stores.  It replaces
+ * the reference-side idea of an NCCL all-gather of layer embeddings (BASELINE.json north_star) with
+ * direct pushes into the replicas the next aggregation reads; completion is ordered by the caller
+ * (stream order + one device-side barrier across ranks per layer).  n_dst <= 8. */
+GLNN_API int glnn_peer_push(const void* src, void* const* dst, int n_dst, int64_t bytes, int ctas,
+                   glnn_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Teacher TRAINING: the pieces `train` (train_and_eval.py:12-29) and

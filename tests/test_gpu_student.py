@@ -405,7 +405,8 @@ def test_adam_kernel_from_injected_gradients(dev, step, wd):
     assert relerr(v.cpu(), v_want) < 1e-6
     assert relerr(p.cpu(), p_want) < 1e-6
     upd_want = p_want - pd
-    assert float(((p.cpu().double() - pd) - upd_want).abs().max() / upd_want.abs().max()) < 2e-5
+    # the applied update, recovered from fp32 parameters: |p| eps / |update| = 3 * 6e-8 / 0.01 ~ 2e-5
+    assert float(((p.cpu().double() - pd) - upd_want).abs().max() / upd_want.abs().max()) < 5e-5
     # torch.optim.Adam from the same state on the same device
     q = torch.nn.Parameter(p0.to(dev).clone())
     opt = torch.optim.Adam([q], lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd)
@@ -413,5 +414,6 @@ def test_adam_kernel_from_injected_gradients(dev, step, wd):
     opt.state[q] = {"step": torch.tensor(float(step - 1)), "exp_avg": m0.to(dev).clone(),
                     "exp_avg_sq": v0.to(dev).clone()}
     opt.step()
-    assert relerr(p.cpu(), q.detach().cpu()) < 1e-6
+    # torch's own fp32 kernel sits up to ~3e-6 from the fp64 formula where |g| ~ eps (step 1)
+    assert relerr(p.cpu(), q.detach().cpu()) < 1e-5
     assert relerr(m.cpu(), opt.state[q]["exp_avg"].cpu()) < 1e-6

@@ -61,7 +61,9 @@ def test_act_block_forward_backward_vs_torch_autograd(dev, n, d, bn, relu_post, 
     assert relerr(y.cpu(), t.detach()) < 2e-6
     dx, dg, db, dbias = blk.backward(dy.to(dev))
     assert relerr(dx.cpu(), want_dx) < 1e-5
-    assert relerr(dbias.cpu(), want_dx.sum(0)) < 1e-5
+    # column sums of dX (the bias gradient): behind BatchNorm they are mathematically zero, so the
+    # bound is relative to the column's absolute mass, not to the (vanishing) exact value
+    assert float((dbias.cpu().double() - want_dx.sum(0)).abs().max()) < 1e-5 * float(want_dx.abs().sum(0).max())
     if bn:
         assert relerr(norm_d.running_mean.cpu(), ref.running_mean) < 1e-6
         assert relerr(norm_d.running_var.cpu(), ref.running_var) < 1e-5
