@@ -179,9 +179,10 @@ def bench_config(workload, n, e, dims, world):
     return {"workload": f"{workload} SAGE teacher full-graph forward + log_softmax",
             "nodes": n, "edges": e, "dims": dims, "norm": "batch(eval)",
             "parallelism": "single GPU" if world == 1 else
-            f"dst-row sharded x{world}: per-layer exchange of the q24 layer output by peer pushes "
-            "into symmetric-memory replicas over NVLink (no NCCL on the forward), output left "
-            "sharded by rows",
+            f"dst-row sharded x{world}: per-layer exchange of the q24 layer output by SM-driven peer "
+            "pushes (glnn_peer_push) into symmetric-memory replicas over NVLink, consumed in two "
+            "passes (own + early source blocks while the late ones are in flight); no NCCL on the "
+            "forward, output left sharded by rows",
             "l2": "inputs (features 0.98 GB, CSR 0.5 GB, activations 2.5 GB) far exceed the "
                   "126 MB L2; no flush needed"}
 
@@ -764,9 +765,11 @@ def run_b200(args):
         def step():
             with torch.no_grad():
                 return DT.sage_forward_sharded(sg, feats_pad, layers, norms, gather_output=False)
-        # per chunk: 3 layers x (aggregation main + hub drain + hub finish) + 3 projections;
-        # + quantise + 3 weight splits
-        launches_per_step = sg.chunks * (9 + 3) + 1 + 3
+        # quantise + 3 weight splits; per chunk: 3 layers x (aggregation main + hub drain + hub finish) +
+        # 3 projections + the peer-push kernels of the two exchanged matrices (early / late receiver
+        # groups); + the first passes (3 kernels each) of the two aggregations that are split by
+        # source block while their input is still arriving
+        launches_per_step = sg.chunks * (9 + 3 + 2 * (2 if world > 2 else 1)) + 1 + 3 + 2 * 3
 
     def barrier():
         if world > 1:

@@ -196,14 +196,19 @@ def _push_ctas():
     return int(os.environ.get("GLNN_PUSH_CTAS", "32"))
 
 
-def _two_pass():
-    """Two-pass consumption of an exchanged replica (GLNN_DIST_TWO_PASS, default on): the producing
+def _two_pass(world=8, which="TWO_PASS"):
+    """Two-pass consumption of an exchanged replica (GLNN_DIST_TWO_PASS = 0 / 1; default: on from 4
+    ranks up -- measured on ogbn-products: 8 ranks 8.24 -> 7.68 ms, 2 ranks 17.25 -> 18.15 ms, where
+    the two half-passes cost more than the exchange they hide): the producing
     layer pushes every chunk to the peers that need it first, then to the others; the consuming
     aggregation runs a first pass over the edges whose sources are already here (own rows + early
     owners: half of the edges) while the late slabs are still in flight, and a second pass over the
     rest on top of the fp32 partial sums (glnn_spmm_csr Y_init)."""
     import os
-    return os.environ.get("GLNN_DIST_TWO_PASS", "1") not in ("", "0")
+    v = os.environ.get("GLNN_DIST_" + which, os.environ.get("GLNN_DIST_TWO_PASS", ""))
+    if v == "":
+        return world >= 4
+    return v != "0"
 
 
 def _replicate_projection():
@@ -493,7 +498,8 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
                     h_op = k.split_planes(mine)
                 else:
                     h_op[: sg.rows] = mine
-            two_phase = cuda and world > 1 and _push_mode() and _push_engine() == "sm" and _two_pass()
+            two_phase = (cuda and world > 1 and _push_mode() and _push_engine() == "sm"
+                         and _two_pass(world, "TWO_PASS_Z"))
             z_events = []
             for c in range(C):
                 a, e = sg.chunk_rows(c)
@@ -599,7 +605,7 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
             else:
                 dest = ("replica", new_replica(("yrep", l), d_out))
             two_phase = (dest[0] == "replica" and cuda and world > 1 and _push_mode()
-                         and _push_engine() == "sm" and _two_pass())
+                         and _push_engine() == "sm" and _two_pass(world))
             pend_events = []
             if pending is not None:
                 # this layer's input replica is still arriving: first pass over the sources that are
