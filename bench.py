@@ -948,9 +948,10 @@ def run_b200(args):
         line["roofline"] = {
             "bound": "hbm", "kernel": "spmm_csr_kernel / " + dom[0], "achieved": achieved,
             "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-            "traffic": _ncu_traffic("r1h_spmm_q24_d256.raw.csv"),
-            "traffic_source": "profiles/r1h_spmm_q24_d256.raw.csv (ncu --set full, same kernel and "
-                              "operand format: q24 768 B rows, d=256, same graph generator)",
+            "traffic": _ncu_traffic("r2_spmm_q24_d256.raw.csv"),
+            "traffic_source": "profiles/r2_spmm_q24_d256.raw.csv (ncu --set full --clock-control none of "
+                              "the shipped kernel: spmm_csr_kernel<32,1,8,0>, 80 registers, 3 CTAs/SM, "
+                              "q24 768 B rows, d=256, same graph generator; profiles/prof_spmm.py)",
             "peak_source": peak_src, "algorithmic_bytes_per_launch": dom[2],
             "gather_bytes_per_launch": gather_bytes, "gather_GBps": gather_gbps,
             "gather_frac_of_peak": gather_gbps / hbm_peak,

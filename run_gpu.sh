@@ -9,5 +9,8 @@ timeout 1200 python -m pytest tests -m gpu -q -rA -p no:cacheprovider > gpurun_o
 tail -5 gpurun_out/t_all.log
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
 timeout 700 python bench.py > gpurun_out/bench_n1.json 2> gpurun_out/bench_n1.err
-timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err
+# launch list of the teacher forward (cold cache, serialised: compare SHARES with the bench breakdown)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
+    --log-file gpurun_out/launches_teacher_products.csv python bench.py --steps 2 --warmup 3 --light > /dev/null 2>&1
 tail -c 600 gpurun_out/bench_n1.json

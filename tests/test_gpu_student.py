@@ -403,7 +403,10 @@ def test_adam_kernel_from_injected_gradients(dev, step, wd):
     ops.adam_step(p, g.to(dev), m, v, step, lr, (b1, b2), eps, wd)
     assert relerr(m.cpu(), m_want) < 1e-6
     assert relerr(v.cpu(), v_want) < 1e-6
-    assert relerr(p.cpu(), p_want) < 1e-6
+    # with weight decay, elements whose g + wd * p cancels down to ~eps (1e-8) turn the fp32 rounding of
+    # that sum (3e-11) into a 1e-3 relative change of their update: inherent to ANY fp32 Adam (torch's
+    # own kernel shows the same against the fp64 formula), hence the wider bound there
+    assert relerr(p.cpu(), p_want) < (1e-6 if wd == 0 else 1e-5)
     upd_want = p_want - pd
     # the applied update, recovered from fp32 parameters: |p| eps / |update| = 3 * 6e-8 / 0.01 ~ 2e-5
     assert float(((p.cpu().double() - pd) - upd_want).abs().max() / upd_want.abs().max()) < 5e-5
