@@ -15,8 +15,9 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, q, chunks):
+def _worker(rank, world, port, q, chunks, two_pass):
     sys.path.insert(0, ROOT)
+    os.environ["GLNN_DIST_TWO_PASS"] = "1" if two_pass else "0"   # default: on from 4 ranks up
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank,
@@ -62,14 +63,16 @@ def _worker(rank, world, port, q, chunks):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,chunks", [(2, 1), (2, 3)])
-def test_sharded_forward_matches_single_gpu(world, chunks):
+@pytest.mark.parametrize("world,chunks,two_pass", [(2, 1, False), (2, 3, True), (2, 1, True)])
+def test_sharded_forward_matches_single_gpu(world, chunks, two_pass):
+    """Sharded forward (SM-driven peer pushes; with and without the two-pass consumption of the
+    exchanged replicas) == the single-GPU forward on the same inputs."""
     if not torch.cuda.is_available() or torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + 3 * chunks + (os.getpid() % 150)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, chunks)) for r in range(world)]
+    port = 29700 + 3 * chunks + int(two_pass) + (os.getpid() % 150)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, chunks, two_pass)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
