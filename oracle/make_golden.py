@@ -308,7 +308,41 @@ def run_teacher_train_bn_drop_cases():
                     lamb=0.8, steps=3, seed=34, norm="batch", dropout=0.3)
 
 
+def teacher_runner_case(name, n, e, f, hidden, c, layers, lr, wd, patience, max_epoch, seed):
+    """The reference's own run_transductive (train_and_eval.py:144-287) for a GCN teacher: full-batch
+    `train` every epoch, `evaluate` + early stopping on `score_val >= best`, restore, final evaluate.
+    dropout 0, no norm: nothing random after the seeded init."""
+    rng = np.random.default_rng(seed)
+    src, dst = rand_graph(rng, n, e, self_loops=True, dup=10)
+    g = dgl_shim.graph((src, dst), num_nodes=n)
+    gen = torch.Generator().manual_seed(seed + 1)
+    feats = torch.randn(n, f, generator=gen)
+    # labels a GCN can learn: argmax of the neighbourhood-averaged leading features
+    labels = (g.spmm_sum(feats)[:, :c] / g.in_degrees().clamp(min=1).unsqueeze(1).float()).argmax(1)
+    perm = torch.randperm(n, generator=gen)
+    indices = (perm[: n // 4], perm[n // 4: n // 2], perm[n // 2:])
+    conf = dict(seed=seed, device="cpu", batch_size=64, patience=patience, max_epoch=max_epoch,
+                eval_interval=1, model_name="GCN", num_layers=layers, feat_dim=f, hidden_dim=hidden,
+                label_dim=c, dropout_ratio=0.0, norm_type="none", fan_out="5,5", num_workers=0)
+    ref_utils.set_seed(seed)
+    model = ref_models.Model(conf)
+    init = sd_np(model, "init.")
+    opt = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
+    hist = []
+    out, s_val, s_test = ref_te.run_transductive(conf, model, g, feats, labels, indices, torch.nn.NLLLoss(),
+                                                 ref_utils.get_evaluator("cora"), opt, _NullLogger(), hist)
+    np.savez_compressed(
+        os.path.join(OUT, f"runner_{name}.npz"), src=src, dst=dst, n=n, feats=feats.numpy(),
+        labels=labels.numpy(), num_layers=layers, hidden=hidden, lr=lr, wd=wd, patience=patience,
+        max_epoch=max_epoch, seed=seed, hist=np.array(hist, dtype=np.float64),
+        scores=np.array([float(s_val), float(s_test)]), out=out.detach().numpy(),
+        **{f"index.{i}": ix.numpy() for i, ix in enumerate(indices)}, **init, **sd_np(model, "final."))
+    print(name, "epochs run", len(hist), "scores", float(s_val), float(s_test))
+
+
 def run_runner_cases():
+    teacher_runner_case("teacher_gcn_tran", n=400, e=2400, f=24, hidden=16, c=4, layers=2, lr=0.05, wd=5e-4,
+                        patience=3, max_epoch=12, seed=41)
     runner_case("tran_none2", False, n=600, f=16, hidden=32, c=5, layers=2, norm="none", bs=64, lr=0.01,
                 wd=5e-4, lamb=0.3, patience=3, max_epoch=6, seed=21)
     runner_case("tran_bn3", False, n=700, f=12, hidden=24, c=4, layers=3, norm="batch", bs=64, lr=0.01,

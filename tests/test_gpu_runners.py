@@ -107,3 +107,39 @@ def test_distill_runner_matches_reference_history(dev, case):
     for k, v in d.items():
         if k.startswith("final.") and k.endswith("weight") and ".layers." in k:
             assert relerr_q(sd[k[len("final."):]].cpu(), v, 0.99) < 2e-2, k
+
+
+def test_gcn_teacher_run_transductive_matches_reference_history(dev):
+    """run_transductive (train_and_eval.py:144-287) for a GCN teacher on the kernels -- `train` is the
+    hand-written kernel sequence (no autograd), `evaluate` the fused forward + reduction -- against the
+    reference's own run (fixture runner_teacher_gcn_tran): same number of epochs, per-epoch evaluation
+    losses / scores, final scores and log-probabilities."""
+    from glnn_b200 import graph as G, train_and_eval as TE
+    from glnn_b200.models import Model
+    from glnn_b200.utils import get_evaluator
+    d = load("runner_teacher_gcn_tran")
+    feats, labels = torch.from_numpy(d["feats"]), torch.from_numpy(d["labels"])
+    indices = tuple(torch.from_numpy(d[f"index.{i}"]) for i in range(3))
+    conf = dict(seed=int(d["seed"]), device=dev, batch_size=64, patience=int(d["patience"]),
+                max_epoch=int(d["max_epoch"]), eval_interval=1, model_name="GCN",
+                num_layers=int(d["num_layers"]), feat_dim=feats.shape[1], hidden_dim=int(d["hidden"]),
+                label_dim=d["out"].shape[1], dropout_ratio=0.0, norm_type="none", fan_out="5,5",
+                num_workers=0)
+    model = Model(conf)
+    model.load_state_dict({k[len("init."):]: torch.from_numpy(np.array(v)) for k, v in d.items()
+                           if k.startswith("init.")})
+    g = G.graph((d["src"], d["dst"]), num_nodes=int(d["n"]))
+    opt = torch.optim.Adam(model.parameters(), lr=float(d["lr"]), weight_decay=float(d["wd"]))
+    hist = []
+    out, s_val, s_test = TE.run_transductive(conf, model, g, feats, labels, indices, torch.nn.NLLLoss(),
+                                             get_evaluator("cora"), opt, _Quiet(), hist)
+    want, got = d["hist"], np.array(hist, dtype=np.float64)
+    assert got.shape == want.shape and want.shape[0] >= 3
+    assert np.allclose(got[:, 1:4], want[:, 1:4], rtol=1e-3, atol=1e-6)
+    sizes = [ix.numel() for ix in indices]
+    for j, m in enumerate(sizes):
+        assert np.all(np.abs(got[:, 4 + j] - want[:, 4 + j]) <= 1.0 / m + 1e-6), j
+    assert abs(s_val - float(d["scores"][0])) <= 1.0 / sizes[1] + 1e-6
+    assert abs(s_test - float(d["scores"][1])) <= 1.0 / sizes[2] + 1e-6
+    err = np.abs(out.cpu().numpy() - d["out"]).max() / np.abs(d["out"]).max()
+    assert err < 2e-3, err

@@ -403,13 +403,16 @@ def test_adam_kernel_from_injected_gradients(dev, step, wd):
     ops.adam_step(p, g.to(dev), m, v, step, lr, (b1, b2), eps, wd)
     assert relerr(m.cpu(), m_want) < 1e-6
     assert relerr(v.cpu(), v_want) < 1e-6
-    # with weight decay, elements whose g + wd * p cancels down to ~eps (1e-8) turn the fp32 rounding of
-    # that sum (3e-11) into a 1e-3 relative change of their update: inherent to ANY fp32 Adam (torch's
-    # own kernel shows the same against the fp64 formula), hence the wider bound there
-    assert relerr(p.cpu(), p_want) < (1e-6 if wd == 0 else 1e-5)
+    # With weight decay, the few elements whose g + wd * p cancels down to ~eps (1e-8) turn the fp32
+    # rounding of that sum (3e-11) into a 1e-3 relative change of THEIR update: inherent to any fp32
+    # Adam (torch's own kernel shows the same against the fp64 formula).  They are held to the size of
+    # one update (lr); everything else to 1e-6 of max|p| and 5e-5 of the update.
+    stable = ge.abs() > 1e-5
+    assert relerr(p.cpu()[stable], p_want[stable]) < 1e-6
+    assert float((p.cpu().double() - p_want).abs().max()) < lr * 5e-3
     upd_want = p_want - pd
     # the applied update, recovered from fp32 parameters: |p| eps / |update| = 3 * 6e-8 / 0.01 ~ 2e-5
-    assert float(((p.cpu().double() - pd) - upd_want).abs().max() / upd_want.abs().max()) < 5e-5
+    assert float((((p.cpu().double() - pd) - upd_want).abs()[stable]).max() / upd_want.abs().max()) < 5e-5
     # torch.optim.Adam from the same state on the same device
     q = torch.nn.Parameter(p0.to(dev).clone())
     opt = torch.optim.Adam([q], lr=lr, betas=(b1, b2), eps=eps, weight_decay=wd)
@@ -418,5 +421,6 @@ def test_adam_kernel_from_injected_gradients(dev, step, wd):
                     "exp_avg_sq": v0.to(dev).clone()}
     opt.step()
     # torch's own fp32 kernel sits up to ~3e-6 from the fp64 formula where |g| ~ eps (step 1)
-    assert relerr(p.cpu(), q.detach().cpu()) < 1e-5
+    assert relerr(p.cpu()[stable], q.detach().cpu()[stable]) < 1e-5
+    assert float((p.cpu() - q.detach().cpu()).abs().max()) < lr * 5e-3
     assert relerr(m.cpu(), opt.state[q]["exp_avg"].cpu()) < 1e-6
