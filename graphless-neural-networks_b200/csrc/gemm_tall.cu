@@ -37,19 +37,24 @@ constexpr int BM = 128;
 // measured both on the products forward (GLNN_TALL_BK): 1.17 / 1.27 / 0.60 ms (64) against 1.23 /
 // 1.31 / 0.71 ms (32) for the three projections -- the deeper ring does not help, so the ring depth
 // is not what holds the kernel at 41 % tensor-pipe activity; 64 stays the default.
-constexpr int EPI_WARPS = 8;
-constexpr int NTHREADS = 64 + EPI_WARPS * 32;
 constexpr int SLAB = 32;  // columns per epilogue slab
-
-template <int BN, int BK>
+// Epilogue warps per CTA: a template parameter, 8 (default) or 16 (GLNN_TALL_EW=16: 4 warps per TMEM
+// lane quarter, 64 columns each, single-buffered TMEM reads to stay within 113 registers).  Round 2
+// measured both on the products forward after ncu's source page had spread the stall samples evenly
+// over the ~5000 epilogue instructions: 1.18 / 1.26 ms (8 warps) against 1.30 / 1.29 ms (16 warps) for
+// the two 256-wide projections -- like the ring depth, the epilogue's issue rate is not what holds the
+// kernel at 4 TB/s of algorithmic traffic.
+template <int BN, int BK, int EW>
 struct Cfg {
+  static constexpr int NTHREADS = 64 + EW * 32;
+  static constexpr int STAGE_ROWS = EW == 8 ? 16 : 8;   // rows of a warp's staging buffer
   static constexpr int A_BYTES = BM * BK * 2;  // one bf16 plane of one stage
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int STAGES = (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) * (64 / BK);
   static constexpr uint32_t SBO = 8 * BK * 2;            // bytes between 8-row groups of a plane
   static constexpr uint32_t LAYOUT = BK == 64 ? 2 : 4;   // SWIZZLE_128B / SWIZZLE_64B
-  static constexpr int STAGING = EPI_WARPS * 16 * SLAB * 4;  // 16 rows x 32 fp32 columns per epilogue warp
+  static constexpr int STAGING = EW * STAGE_ROWS * SLAB * 4;  // STAGE_ROWS x 32 fp32 columns per epilogue warp
   static constexpr int EPI_VEC = 3 * BN * 4;                 // bias, BN scale, BN shift (padded to BN)
   static constexpr int TOTAL = STAGES * STAGE + STAGING + EPI_VEC + 1024 /*alignment slack*/ +
                                256 /*barriers*/;
@@ -93,12 +98,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr));
 }
 
-template <int BN, int BK>
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <int BN, int BK, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 gemm_tall_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap map_ah,
                  const __grid_constant__ CUtensorMap map_al, const __grid_constant__ CUtensorMap map_bh,
                  const __grid_constant__ CUtensorMap map_bl) {
-  using S = Cfg<BN, BK>;
+  using S = Cfg<BN, BK, EW>;
+  constexpr int NTHREADS = S::NTHREADS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* tiles = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // SWIZZLE_128B atoms
   float* epi_vec = reinterpret_cast<float*>(tiles + S::STAGES * S::STAGE + S::STAGING);
@@ -120,7 +126,7 @@ gemm_tall_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap map_ah,
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], EPI_WARPS);
+      mbar_init(&acc_empty[a], EW);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -202,17 +208,22 @@ gemm_tall_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap map_ah,
     }
   } else {
     // ------------------------------- epilogue -------------------------------
-    // Each warp owns 32 rows (its TMEM lane quarter) x BN/2 columns of the tile and works through
-    // them in 32-column chunks on its own: TMEM -> registers -> epilogue math (bias / BN vectors are
-    // broadcast reads from shared memory) -> private swizzled staging (16 rows x 32 columns, two
-    // passes) -> coalesced 128-byte row segments.  No CTA-wide barrier: the eight warps drift apart
-    // and hide each other's latencies; the next chunk's tcgen05.ld is in flight while the current
-    // chunk is stored.
-    const int ew = warp - 2;          // 0..7
+    // Each warp owns 32 rows (its TMEM lane quarter) x BN / (EW/4) columns of the tile and works
+    // through them in 32-column chunks on its own: TMEM -> registers -> epilogue math (bias / BN
+    // vectors are broadcast reads from shared memory) -> private swizzled staging (STAGE_ROWS rows x 32
+    // columns per pass) -> coalesced 128-byte row segments.  No CTA-wide barrier: the warps drift apart
+    // and hide each other's latencies.  EW = 8: the next chunk's tcgen05.ld is in flight while the
+    // current chunk is stored (two register buffers); EW = 16: one buffer, twice the warps.
+    const int ew = warp - 2;          // 0..EW-1
     const int q = warp & 3;           // TMEM lane quarter this warp may access
-    const int half = ew >> 2;         // which half of the tile's columns
-    constexpr int CHUNKS = BN / 64;   // 32-column chunks per warp and tile
-    const uint32_t sb = smem_u32(tiles) + S::STAGES * S::STAGE + ew * (16 * SLAB * 4);
+    const int part = ew >> 2;         // which slice of the tile's columns
+    constexpr int PARTS = EW / 4;
+    constexpr int WCOLS = BN / PARTS;           // columns per warp
+    constexpr int CHUNKS = WCOLS / SLAB;        // 32-column chunks per warp and tile
+    static_assert(CHUNKS >= 1, "tile too narrow for this many epilogue warps");
+    constexpr int SR = S::STAGE_ROWS;           // 16 (two passes) or 8 (four passes)
+    constexpr int NBUF = EW == 8 ? 2 : 1;
+    const uint32_t sb = smem_u32(tiles) + S::STAGES * S::STAGE + ew * (SR * SLAB * 4);
     const uint32_t ev = smem_u32(tiles) + S::STAGES * S::STAGE + S::STAGING;
     uint32_t tcount = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++tcount) {
@@ -221,44 +232,48 @@ gemm_tall_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap map_ah,
       mbar_wait(&acc_full[a], (tcount >> 1) & 1);
       tc_fence_after();
       const float rs = (g.row_scale && m0 + lane < g.M) ? __ldg(g.row_scale + m0 + lane) : 1.f;
-      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + half * (BN / 2);
-      uint32_t r[2][32];
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * BN + part * WCOLS;
+      uint32_t r[NBUF][32];
       tmem_ld32(tbase, r[0]);
 #pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
-        const int col0 = half * (BN / 2) + c * SLAB;
+        const int col0 = part * WCOLS + c * SLAB;
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (NBUF == 2 && c + 1 < CHUNKS) tmem_ld32(tbase + (c + 1) * SLAB, r[(c + 1) & 1]);
+        float o[32];
+        if (col0 < g.N) {
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 vb = lds128(ev + (col0 + j4 * 4) * 4);
+            const float4 vs = lds128(ev + (BN + col0 + j4 * 4) * 4);
+            const float4 vt = lds128(ev + (2 * BN + col0 + j4 * 4) * 4);
+            const float bb[4] = {vb.x, vb.y, vb.z, vb.w}, ss[4] = {vs.x, vs.y, vs.z, vs.w},
+                        tt[4] = {vt.x, vt.y, vt.z, vt.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float x = __uint_as_float(r[c % NBUF][j4 * 4 + j]) * rs + bb[j];
+              if (g.relu == 2) x = fmaxf(x, 0.f);
+              if (has_affine) x = fmaf(x, ss[j], tt[j]);
+              if (g.relu == 1) x = fmaxf(x, 0.f);
+              o[j4 * 4 + j] = x;
+            }
+          }
+        }
+        // the accumulator values of this chunk are consumed: fetch the next chunk (single buffer) or,
+        // after the last one, hand the accumulator back to the MMA warp
         if (c + 1 < CHUNKS) {
-          tmem_ld32(tbase + (c + 1) * SLAB, r[(c + 1) & 1]);
+          if (NBUF == 1) tmem_ld32(tbase + (c + 1) * SLAB, r[0]);
         } else {
-          // last chunk of this accumulator is in registers: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[a]);
         }
         if (col0 >= g.N) continue;
-        float o[32];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 vb = lds128(ev + (col0 + j4 * 4) * 4);
-          const float4 vs = lds128(ev + (BN + col0 + j4 * 4) * 4);
-          const float4 vt = lds128(ev + (2 * BN + col0 + j4 * 4) * 4);
-          const float bb[4] = {vb.x, vb.y, vb.z, vb.w}, ss[4] = {vs.x, vs.y, vs.z, vs.w},
-                      tt[4] = {vt.x, vt.y, vt.z, vt.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float x = __uint_as_float(r[c & 1][j4 * 4 + j]) * rs + bb[j];
-            if (g.relu == 2) x = fmaxf(x, 0.f);
-            if (has_affine) x = fmaf(x, ss[j], tt[j]);
-            if (g.relu == 1) x = fmaxf(x, 0.f);
-            o[j4 * 4 + j] = x;
-          }
-        }
-#pragma unroll
-        for (int pass = 0; pass < 2; ++pass) {
+        for (int pass = 0; pass < 32 / SR; ++pass) {
           __syncwarp();  // the previous pass's staging reads are done
-          if ((lane >> 4) == pass) {
-            const int rl = lane & 15;
+          if (lane / SR == pass) {
+            const int rl = lane % SR;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4)  // 16-byte piece p of row r lives at piece p ^ (r & 7)
               sts128(sb + (rl * SLAB + ((j4 ^ (rl & 7)) * 4)) * 4,
@@ -267,9 +282,9 @@ gemm_tall_kernel(const GemmArgs g, const __grid_constant__ CUtensorMap map_ah,
           __syncwarp();
           // coalesced stores: 8 lanes cover one 128-byte row segment, 4 rows per instruction
 #pragma unroll
-          for (int rr = 0; rr < 16; rr += 4) {
+          for (int rr = 0; rr < SR; rr += 4) {
             const int r_out = rr + (lane >> 3), p = lane & 7;
-            const int64_t mr = m0 + pass * 16 + r_out;
+            const int64_t mr = m0 + pass * SR + r_out;
             const int64_t n = col0 + p * 4;
             if (mr < g.M && n < g.N) {
               const float4 v = lds128(sb + (r_out * SLAB + ((p ^ (r_out & 7)) * 4)) * 4);
@@ -330,11 +345,11 @@ static int make_map(CUtensorMap* map, const uint16_t* base, int64_t rows, int64_
   return 0;
 }
 
-template <int BN, int BK>
+template <int BN, int BK, int EW>
 static int launch(const GemmArgs& g, cudaStream_t st) {
-  using S = Cfg<BN, BK>;
+  using S = Cfg<BN, BK, EW>;
   static bool configured = false;
-  auto kern = gemm_tall_kernel<BN, BK>;
+  auto kern = gemm_tall_kernel<BN, BK, EW>;
   if (!configured) {
     GLNN_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     configured = true;
@@ -347,7 +362,7 @@ static int launch(const GemmArgs& g, cudaStream_t st) {
   if ((rc = make_map(&mbl, g.Bl, g.N, g.K, g.ldb, BN, BK))) return rc;
   const int ntiles = static_cast<int>((g.M + BM - 1) / BM);
   const int grid = std::min(ntiles, sm_count());
-  kern<<<grid, NTHREADS, S::TOTAL, st>>>(g, mah, mal, mbh, mbl);
+  kern<<<grid, S::NTHREADS, S::TOTAL, st>>>(g, mah, mal, mbh, mbl);
   GLNN_LAUNCH_OK("gemm_tall_kernel");
   return 0;
 }
@@ -365,14 +380,15 @@ int gemm_tall_planes(const GemmArgs& g, cudaStream_t st, bool* taken) {
   if (g.M >= (1LL << 31) - tall::BM) return 0;  // TMA coordinates are int32
   int rc;
   static const bool bk64 = !(getenv("GLNN_TALL_BK") != nullptr && atoi(getenv("GLNN_TALL_BK")) == 32);
+  static const bool ew8 = !(getenv("GLNN_TALL_EW") != nullptr && atoi(getenv("GLNN_TALL_EW")) == 16);
   if (bk64) {  // default
-    if (g.N > 128) rc = tall::launch<256, 64>(g, st);
-    else if (g.N > 64) rc = tall::launch<128, 64>(g, st);
-    else rc = tall::launch<64, 64>(g, st);
+    if (g.N > 128) rc = ew8 ? tall::launch<256, 64, 8>(g, st) : tall::launch<256, 64, 16>(g, st);
+    else if (g.N > 64) rc = ew8 ? tall::launch<128, 64, 8>(g, st) : tall::launch<128, 64, 16>(g, st);
+    else rc = tall::launch<64, 64, 8>(g, st);
   } else {
-    if (g.N > 128) rc = tall::launch<256, 32>(g, st);
-    else if (g.N > 64) rc = tall::launch<128, 32>(g, st);
-    else rc = tall::launch<64, 32>(g, st);
+    if (g.N > 128) rc = tall::launch<256, 32, 8>(g, st);
+    else if (g.N > 64) rc = tall::launch<128, 32, 8>(g, st);
+    else rc = tall::launch<64, 32, 8>(g, st);
   }
   if (rc != 0) return rc;
   *taken = true;
