@@ -874,13 +874,16 @@ def run_b200(args):
         h_outs = [torch.empty(sg.rows, dims[3]).pin_memory() for _ in range(2)]
         h_out = h_outs[0]
         pipe = HostShardedTeacherPipeline(sg, layers, norms, dims[0], dims[3], dev)
+        h_split = pipe.host_split()   # two-pass exchange: the CSR split by source owner travels too
 
         def e2e_step():
-            pipe.submit(h_ptr, h_idx, h_feats, h_outs[pipe.step % 2])
+            pipe.submit(h_ptr, h_idx, h_feats, h_outs[pipe.step % 2], h_split)
 
         def e2e_drain():
             pipe.drain()
         h2d = h_ptr.numel() * h_ptr.element_size() + h_idx.numel() * 4 + h_feats.numel() * 4
+        if h_split is not None:
+            h2d += sum(t.numel() * t.element_size() for t in h_split)
     e2e_step()
     e2e_drain()
     barrier()

@@ -64,20 +64,38 @@ class HostShardedTeacherPipeline:
     neighbouring steps overlap with compute exactly as in HostTeacherPipeline."""
 
     def __init__(self, sg, layers, norms, feat_dim, label_dim, device, group=None, depth=2):
+        from . import dist_teacher as DT
         self.sg, self.layers, self.norms, self.group = sg, layers, norms, group
         self.dev, self.depth, self.step = device, depth, 0
         self.h2d, self.d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        # with the two-pass exchange the later aggregations read the CSR split by source owner: the
+        # host ships that form too (same edges, two index arrays), so every gather of a step runs on
+        # data uploaded in that step
+        self.two_pass = bool(device.type == "cuda" and sg.world > 1 and DT._two_pass(sg.world))
         self.slots = []
         for _ in range(depth):
-            self.slots.append(dict(
+            slot = dict(
                 indptr=torch.empty_like(sg.indptr), indices=torch.empty_like(sg.indices),
                 feats=torch.empty(sg.rows, feat_dim, dtype=torch.float32, device=device),
                 out=torch.empty(sg.rows, label_dim, dtype=torch.float32, device=device),
-                uploaded=torch.cuda.Event(), computed=torch.cuda.Event(), downloaded=torch.cuda.Event()))
+                uploaded=torch.cuda.Event(), computed=torch.cuda.Event(), downloaded=torch.cuda.Event())
+            if self.two_pass:
+                slot["split"] = tuple(torch.empty_like(t) for pair in sg.split_by_owner() for t in pair)
+            self.slots.append(slot)
 
-    def submit(self, h_indptr, h_indices, h_feats, h_out):
+    def host_split(self):
+        """Pinned host copies of the CSR split by source owner, (early indptr, early indices, late indptr,
+        late indices), or None when the exchange is consumed in one pass."""
+        if not self.two_pass:
+            return None
+        return tuple(t.cpu().pin_memory() for pair in self.sg.split_by_owner() for t in pair)
+
+    def submit(self, h_indptr, h_indices, h_feats, h_out, h_split=None):
         """h_*: pinned host tensors (this rank's relabelled CSR slice, its feature rows [rows, F]);
-        h_out: pinned [rows, C].  Returns immediately; drain() before reading h_out."""
+        h_out: pinned [rows, C]; h_split: host_split() when the two-pass exchange is active.  Returns
+        immediately; drain() before reading h_out."""
+        if self.two_pass and h_split is None:
+            raise ValueError("two-pass exchange: pass h_split=pipe.host_split()")
         from . import dist_teacher as DT
         sg, s = self.sg, self.slots[self.step % self.depth]
         cur = torch.cuda.current_stream(self.dev)
@@ -88,16 +106,24 @@ class HostShardedTeacherPipeline:
             s["indptr"].copy_(h_indptr, non_blocking=True)
             s["indices"].copy_(h_indices, non_blocking=True)
             s["feats"].copy_(h_feats, non_blocking=True)
+            if self.two_pass:
+                for dst, src in zip(s["split"], h_split):
+                    dst.copy_(src, non_blocking=True)
             s["uploaded"].record(self.h2d)
         cur.wait_event(s["uploaded"])
-        keep = (sg.indptr, sg.indices)
+        keep = (sg.indptr, sg.indices, sg.__dict__.get("_split"))
         sg.indptr, sg.indices = s["indptr"], s["indices"]
+        if self.two_pass:
+            sp = s["split"]
+            sg._split = ((sp[0], sp[1]), (sp[2], sp[3]))
         try:
             with torch.no_grad():
                 out = DT.sage_forward_sharded(sg, None, self.layers, self.norms, group=self.group,
                                               gather_output=False, feats_local=s["feats"])
         finally:
-            sg.indptr, sg.indices = keep
+            sg.indptr, sg.indices = keep[0], keep[1]
+            if self.two_pass:
+                sg._split = keep[2]
         for c in range(sg.chunks):   # this rank's rows of the padded output, back in local order
             a, e = sg.chunk_rows(c)
             if e > a:

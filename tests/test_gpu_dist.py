@@ -52,8 +52,9 @@ def _worker(rank, world, port, q, chunks, two_pass):
     h_ptr, h_idx = sg.indptr.cpu().pin_memory(), sg.indices.cpu().pin_memory()
     h_feats = feats[sg.r0:sg.r0 + sg.rows].cpu().pin_memory()
     h_outs = [torch.empty(sg.rows, 47).pin_memory() for _ in range(3)]
+    h_split = pipe.host_split()        # None unless the two-pass exchange is active
     for h in h_outs:
-        pipe.submit(h_ptr, h_idx, h_feats, h)
+        pipe.submit(h_ptr, h_idx, h_feats, h, h_split)
     pipe.drain()
     torch.cuda.synchronize()
     want = ref[sg.r0:sg.r0 + sg.rows].cpu()
