@@ -881,9 +881,10 @@ def run_b200(args):
 
         def e2e_drain():
             pipe.drain()
-        h2d = h_ptr.numel() * h_ptr.element_size() + h_idx.numel() * 4 + h_feats.numel() * 4
-        if h_split is not None:
-            h2d += sum(t.numel() * t.element_size() for t in h_split)
+        if h_split is not None:   # the split form replaces the merged CSR slice
+            h2d = sum(t.numel() * t.element_size() for t in h_split) + h_feats.numel() * 4
+        else:
+            h2d = h_ptr.numel() * h_ptr.element_size() + h_idx.numel() * 4 + h_feats.numel() * 4
     e2e_step()
     e2e_drain()
     barrier()

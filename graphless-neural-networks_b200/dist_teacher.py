@@ -349,7 +349,7 @@ class _Exchange:
 
 
 def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None, log_softmax=True,
-                         timings=None, gather_output=True, feats_local=None):
+                         timings=None, gather_output=True, feats_local=None, split_only=False):
     """layers: [(W [out,in], b)], norms: [(scale, shift)] folded eval-BN per hidden layer (or []).
     feats_pad: padded replica (sg.to_padded) of the input features, valid on every rank -- OR None
     with feats_local = this rank's OWN feature rows [sg.rows, d_in] (local order): the replica of the
@@ -359,6 +359,10 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
     the returned tensor is a cached buffer that the next call overwrites.  With gather_output=False
     the result stays sharded: only this rank's rows of it are valid (sg.local_rows_of) -- what a
     sharded consumer (loss / accuracy reduction, a sharded student) needs.
+
+    split_only=True: only the owner-split CSR (sg.split_by_owner()) is trusted -- sg.indptr / sg.indices
+    are not read.  The host pipeline uses it with the two-pass exchange so that it uploads each edge
+    once: aggregations whose input is complete run as two launches over the two halves.
 
     Exchange plan: an aggregate-first layer needs the full replica of its input (all-gather of the
     previous output, d_in wide); a project-first layer (4-padded d_out < d_in) projects only the
@@ -423,7 +427,14 @@ def sage_forward_sharded(sg, feats_pad, layers, norms, group=None, kernels=None,
 
     def aggregate(rep, d, a, b, out_op):
         """mean over (neighbours + self) of replica rows for local rows [a, b) -> operand rows."""
-        if cuda:
+        if cuda and split_only:
+            (pe, ie), (pl_, il) = sg.split_by_owner()
+            part = _cached(sg, ("partial_so", d), lambda: torch.empty(max(sg.rows, 1), (d + 7) // 8 * 8,
+                                                                       dtype=torch.float32, device=dev))
+            k.spmm(pe[a:b + 1], ie, rep, d=d, out=part[a:b])
+            k.spmm(pl_[a:b + 1], il, rep, d=d, out_planes=rows_of(out_op, a, b),
+                   dst_scale=sg.inv_deg1[a:b], acc_init=part[a:b])
+        elif cuda:
             k.spmm(sg.indptr[a:b + 1], sg.indices, rep, d=d, out_planes=rows_of(out_op, a, b),
                    dst_scale=sg.inv_deg1[a:b])
         else:

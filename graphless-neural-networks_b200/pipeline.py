@@ -68,9 +68,9 @@ class HostShardedTeacherPipeline:
         self.sg, self.layers, self.norms, self.group = sg, layers, norms, group
         self.dev, self.depth, self.step = device, depth, 0
         self.h2d, self.d2h = torch.cuda.Stream(device), torch.cuda.Stream(device)
-        # with the two-pass exchange the later aggregations read the CSR split by source owner: the
-        # host ships that form too (same edges, two index arrays), so every gather of a step runs on
-        # data uploaded in that step
+        # with the two-pass exchange the aggregations read the CSR split by source owner: the host ships
+        # THAT form instead of the merged CSR (same edges, two index arrays, each edge once), so every
+        # gather of a step runs on data uploaded in that step
         self.two_pass = bool(device.type == "cuda" and sg.world > 1 and DT._two_pass(sg.world))
         self.slots = []
         for _ in range(depth):
@@ -92,8 +92,8 @@ class HostShardedTeacherPipeline:
 
     def submit(self, h_indptr, h_indices, h_feats, h_out, h_split=None):
         """h_*: pinned host tensors (this rank's relabelled CSR slice, its feature rows [rows, F]);
-        h_out: pinned [rows, C]; h_split: host_split() when the two-pass exchange is active.  Returns
-        immediately; drain() before reading h_out."""
+        h_out: pinned [rows, C]; h_split: host_split() when the two-pass exchange is active (then
+        h_indptr / h_indices are not read).  Returns immediately; drain() before reading h_out."""
         if self.two_pass and h_split is None:
             raise ValueError("two-pass exchange: pass h_split=pipe.host_split()")
         from . import dist_teacher as DT
@@ -103,12 +103,13 @@ class HostShardedTeacherPipeline:
             self.h2d.wait_event(s["computed"])   # the slot's previous forward has consumed its inputs
             cur.wait_event(s["downloaded"])      # ... and its output rows have left the device
         with torch.cuda.stream(self.h2d):
-            s["indptr"].copy_(h_indptr, non_blocking=True)
-            s["indices"].copy_(h_indices, non_blocking=True)
-            s["feats"].copy_(h_feats, non_blocking=True)
-            if self.two_pass:
+            if self.two_pass:   # every edge travels once: the owner-split form replaces the merged CSR
                 for dst, src in zip(s["split"], h_split):
                     dst.copy_(src, non_blocking=True)
+            else:
+                s["indptr"].copy_(h_indptr, non_blocking=True)
+                s["indices"].copy_(h_indices, non_blocking=True)
+            s["feats"].copy_(h_feats, non_blocking=True)
             s["uploaded"].record(self.h2d)
         cur.wait_event(s["uploaded"])
         keep = (sg.indptr, sg.indices, sg.__dict__.get("_split"))
@@ -119,7 +120,8 @@ class HostShardedTeacherPipeline:
         try:
             with torch.no_grad():
                 out = DT.sage_forward_sharded(sg, None, self.layers, self.norms, group=self.group,
-                                              gather_output=False, feats_local=s["feats"])
+                                              gather_output=False, feats_local=s["feats"],
+                                              split_only=self.two_pass)
         finally:
             sg.indptr, sg.indices = keep[0], keep[1]
             if self.two_pass:
