@@ -152,3 +152,40 @@ def test_student_data_parallel_protocol_equals_single_process(world, norm):
             assert np.allclose(got[k].astype(np.float64), v.double().numpy(), rtol=1e-9, atol=1e-12), (rank, k)
         for k, v in st.items():
             assert np.allclose(got_v[k], v["exp_avg_sq"].numpy(), rtol=1e-9, atol=1e-30), (rank, k)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_two_pass_split_partitions_the_edges_and_the_push_plan_is_consistent(world):
+    """Host logic of the two-pass exchange (dist_teacher.py): for every rank the owner-split CSRs hold
+    every edge of the rank's slice exactly once, in CSR order, early edges = sources owned by the early
+    owners (the explicit self edge included); rank r is an early receiver of s exactly when s is an
+    early owner of r; every ordered pair of distinct ranks is served exactly once (early or late)."""
+    import torch
+    from glnn_b200 import dist_teacher as DT
+    from glnn_b200.workloads import synthetic_graph
+    g = synthetic_graph(3000, 20000, mirror=True, self_loops=False, device="cpu", seed=2)
+    shards = [DT.ShardedGraph(g, r, world, chunks=2) for r in range(world)]
+    for r, sg in enumerate(shards):
+        early = sg.early_owners()
+        assert early[0] == r and len(early) == max(1, world // 2) and len(set(early)) == len(early)
+        for s in range(world):
+            assert (r in shards[s].early_receivers()) == (s in early and s != r)
+        (pe, ie), (pl, il) = sg.split_by_owner()
+        assert int(pe[-1]) + int(pl[-1]) == sg.indices.numel()
+        owner = lambda idx: (idx.long() // sg.rc) % world
+        assert set(owner(ie).tolist()) <= set(early)
+        assert not (set(owner(il).tolist()) & set(early))
+        p = sg.indptr.long()
+        for v in (0, 1, sg.rows // 2, sg.rows - 1):
+            row = sg.indices[p[v]:p[v + 1]]
+            e_part, l_part = ie[pe[v]:pe[v + 1]], il[pl[v]:pl[v + 1]]
+            m = torch.tensor([int(o) in early for o in owner(row)])
+            assert torch.equal(row[m], e_part) and torch.equal(row[~m], l_part)   # order kept
+            # the self edge (own slot in the replica) is always in the early half
+            self_pid = sg.pad_ids[sg.r0 + v]
+            assert int((e_part.long() == self_pid).sum()) >= 1
+    # every ordered pair (sender, receiver) appears exactly once in the sender's push plan
+    for s, sg in enumerate(shards):
+        early_r = sg.early_receivers()
+        late_r = [(s + i) % world for i in range(1, world) if (s + i) % world not in early_r]
+        assert sorted(early_r + late_r) == [x for x in range(world) if x != s]
