@@ -643,8 +643,8 @@ def other_configs(dev, torch, hbm_peak):
                          "reference's per-step host sync",
              "train_step_ms": round(t_train * 1e3, 4), "evaluate_ms": round(t_eval * 1e3, 4),
              "train_nodes_per_s": n / t_train, "eval_nodes_per_s": n / t_eval,
-             "note": "launch-latency-bound at this size (SURVEY 8a3); training runs autograd over the "
-                     "aggregation / projection kernels"}
+             "note": "launch-latency-bound at this size (SURVEY 8a3); the train step is the kernel "
+                     "sequence of teacher_train.gcn_train_step (hand-written backward, no autograd)"}
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import glnn_oracle as O
