@@ -426,8 +426,16 @@ int gemm_tc_planes(GemmArgs g, cudaStream_t st) {
     const int rc = gemm_tall_planes(g, st, &taken);
     if (rc != 0 || taken) return rc;
   }
-  const int bn = g.N > 128 ? 256 : 128;
-  const int64_t tiles = ((g.M + tc::BM - 1) / tc::BM) * ((g.N + bn - 1) / bn);
+  // 128 x 256 tiles (two-stage ring) when there are enough of them to fill the machine; otherwise
+  // 128 x 128 tiles: twice the CTAs and a three-stage ring (two loads in flight) -- the small students
+  // (bs 512, H 256 / 1024) run 4-32 CTAs per projection and are bound by the per-CTA timeline
+  // (GLNN_TC_SMALL_TILES: 0 = round-1 rule, 1 = down to 128 columns, 2 = down to 64 columns)
+  static const int small_tiles = getenv("GLNN_TC_SMALL_TILES") ? atoi(getenv("GLNN_TC_SMALL_TILES")) : 2;
+  const int64_t mt = (g.M + tc::BM - 1) / tc::BM;
+  int bn = g.N > 128 ? 256 : (g.N > 64 || small_tiles < 2 ? 128 : 64);
+  if (small_tiles >= 1 && bn == 256 && mt * ((g.N + 255) / 256) * 2 <= sm_count()) bn = 128;
+  if (small_tiles >= 2 && bn == 128 && g.N > 64 && mt * ((g.N + 127) / 128) * 2 <= sm_count()) bn = 64;
+  const int64_t tiles = mt * ((g.N + bn - 1) / bn);
   const int nkb = static_cast<int>((g.K + tc::BK - 1) / tc::BK);
   int splits = 1;
   const bool linear = !g.relu && !g.col_scale && !g.Ch && !g.Cq && g.C;
@@ -444,11 +452,13 @@ int gemm_tc_planes(GemmArgs g, cudaStream_t st) {
       GLNN_CUDA_OK(cudaMemset2DAsync(g.C, sizeof(float) * g.ldc, 0, sizeof(float) * g.N, g.M, st));
     }
     return bn == 256 ? tc::launch_major<256, true, true>(g, splits, st)
-                     : tc::launch_major<128, true, true>(g, splits, st);
+                     : (bn == 128 ? tc::launch_major<128, true, true>(g, splits, st)
+                                  : tc::launch_major<64, true, true>(g, splits, st));
   }
   g.kb_per_split = 0;
   return bn == 256 ? tc::launch_major<256, true, false>(g, 1, st)
-                   : tc::launch_major<128, true, false>(g, 1, st);
+                   : (bn == 128 ? tc::launch_major<128, true, false>(g, 1, st)
+                                : tc::launch_major<64, true, false>(g, 1, st));
 }
 
 }  // namespace glnn
