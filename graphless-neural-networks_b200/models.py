@@ -106,6 +106,14 @@ class MLP(_Encoder):
         if feats.is_cuda and not self.training and self.fused_supported() \
                 and not torch.is_grad_enabled():
             return [], mlp_engine.eval_logits(self, feats)
+        # train-mode / autograd / CPU forward: not a kernel path.  Training goes through
+        # train_and_eval.train_mini_batch (fused step); this torch-module forward only runs when the
+        # caller opts in (GLNN_ALLOW_TORCH_FALLBACK=1) or asks for forward_fitnet's hidden states.
+        from .train_and_eval import torch_fallback_allowed
+        if not torch_fallback_allowed():
+            raise _lib.GlnnError("MLP.forward outside the fused eval path (train mode, autograd enabled or "
+                                 "CPU tensors): use train_mini_batch / evaluate_mini_batch, or set "
+                                 "GLNN_ALLOW_TORCH_FALLBACK=1 for the plain torch-module forward")
         return self._forward_autograd(feats)
 
     def _forward_autograd(self, feats):

@@ -32,6 +32,26 @@ def _warn_once(key, msg):
         warnings.warn(msg, stacklevel=3)
 
 
+def torch_fallback_allowed():
+    """The step functions have NO silent fallback: a model / criterion / optimizer / device the B200
+    kernels do not implement raises.  GLNN_ALLOW_TORCH_FALLBACK=1 is the explicit escape hatch that
+    lets the generic torch loop run instead (used by the CPU tests that compare the runners' host
+    bookkeeping with the reference's own functions); it is never a measured path."""
+    import os
+    return os.environ.get("GLNN_ALLOW_TORCH_FALLBACK", "0") not in ("", "0")
+
+
+def _outside_fused_path(key, what):
+    from ._lib import GlnnError
+    if not torch_fallback_allowed():
+        raise GlnnError(f"{what}: outside the fused B200 path (it needs CUDA tensors, a glnn_b200 MLP / "
+                        "SAGE / GCN with norm_type 'none' or 'batch', NLLLoss / KLDivLoss(batchmean, "
+                        "log_target) and torch.optim.Adam).  There is no silent fallback; set "
+                        "GLNN_ALLOW_TORCH_FALLBACK=1 to run the generic torch loop explicitly.")
+    _warn_once(key, f"{what}: model/criterion/optimizer outside the fused B200 path; "
+                    "running the generic autograd loop")
+
+
 # ------------------------------------------------------------------------------------------------
 # criterion / evaluator recognition
 # ------------------------------------------------------------------------------------------------
@@ -105,8 +125,7 @@ def train_mini_batch(model, feats, labels, batch_size, criterion, optimizer, lam
             and not (enc.norm_type == "batch" and idx_batch.shape[1] < 2):
         loss_sum = mlp_engine.train_pass(enc, optimizer, feats, labels, idx_batch, lamb)
         return loss_sum.item() / num_batches
-    _warn_once("tmb", "train_mini_batch: model/criterion/optimizer outside the fused B200 path; "
-                      "running the generic autograd loop")
+    _outside_fused_path("tmb", "train_mini_batch")
     total_loss = 0.0
     for i in range(num_batches):
         rows = idx_batch[i]
@@ -128,7 +147,10 @@ def evaluate(model, data, feats, labels, criterion, evaluator, idx_eval=None):
             out = enc.inference(data, feats, log_softmax=True)
         elif isinstance(enc, GCN) and feats.is_cuda:
             out = enc(data, feats, log_softmax=True)[1]
+        elif isinstance(enc, MLP) and feats.is_cuda and enc.fused_supported():
+            out = mlp_engine.eval_forward(enc, feats, log_softmax=True)
         else:
+            _outside_fused_path("ev", "evaluate")
             out = model.inference(data, feats).log_softmax(dim=1)
         loss, score = _loss_and_score(out, labels, criterion, evaluator, idx_eval)
     return out, loss, score
@@ -142,6 +164,7 @@ def evaluate_mini_batch(model, feats, labels, criterion, batch_size, evaluator, 
             # eval-mode rows are independent of the batching, so the chunk size only bounds scratch
             out_all = mlp_engine.eval_forward(enc, feats, log_softmax=True)
         else:
+            _outside_fused_path("emb", "evaluate_mini_batch")
             chunks = [model.inference(None, feats[s:s + batch_size]).log_softmax(dim=1)
                       for s in range(0, len(feats), batch_size)]
             out_all = torch.cat(chunks)

@@ -76,6 +76,27 @@ def test_product_path_has_no_cpu_fallback():
         m.inference(g, torch.zeros(2, 4))
 
 
+def test_step_functions_raise_instead_of_falling_back(monkeypatch):
+    """No silent eager-torch path: CPU tensors (or anything else outside the fused kernels) raise
+    unless the caller sets GLNN_ALLOW_TORCH_FALLBACK=1."""
+    from glnn_b200 import _lib, train_and_eval as TE
+    from glnn_b200.models import Model
+    monkeypatch.delenv("GLNN_ALLOW_TORCH_FALLBACK", raising=False)
+    m = Model(dict(model_name="MLP", num_layers=2, feat_dim=6, hidden_dim=8, label_dim=3,
+                   dropout_ratio=0.0, norm_type="none", device="cpu"))
+    opt = torch.optim.Adam(m.parameters(), lr=0.01)
+    x, y = torch.randn(20, 6), torch.randint(0, 3, (20,))
+    with pytest.raises(_lib.GlnnError):
+        TE.train_mini_batch(m, x, y, 10, torch.nn.NLLLoss(), opt)
+    with pytest.raises(_lib.GlnnError):
+        TE.evaluate_mini_batch(m, x, y, torch.nn.NLLLoss(), 10, lambda o, l: 0.0)
+    with pytest.raises(_lib.GlnnError):
+        m(None, x)
+    m.eval()
+    with torch.no_grad(), pytest.raises(_lib.GlnnError):
+        m(None, x)
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "graphless-neural-networks_b200")
     for fn in os.listdir(pkg):
@@ -143,9 +164,10 @@ def test_batch_index_rule():
     assert torch.equal(a.view(-1), torch.randperm(100))      # same CPU randperm call as the reference
 
 
-def test_cpu_generic_loop_matches_oracle_without_gpu():
-    """Out-of-scope configurations fall back to a generic autograd loop; check it against the
-    oracle so the drop-in stays correct there too (CPU tensors, tiny)."""
+def test_cpu_generic_loop_matches_oracle_without_gpu(monkeypatch):
+    """With GLNN_ALLOW_TORCH_FALLBACK=1 out-of-scope configurations run a generic autograd loop;
+    check it against the oracle so the opt-in stays correct too (CPU tensors, tiny)."""
+    monkeypatch.setenv("GLNN_ALLOW_TORCH_FALLBACK", "1")
     import glnn_oracle as O
     import warnings
     from glnn_b200 import train_and_eval as TE

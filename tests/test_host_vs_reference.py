@@ -98,6 +98,14 @@ def test_min_cut_loss_equals_the_dense_formula():
     assert abs((S.t() @ A.t() @ S).trace().item() - (S.t() @ A @ S).trace().item()) < 1e-9
 
 
+@pytest.fixture(autouse=True)
+def _explicit_torch_loop(monkeypatch):
+    """These tests compare the runners' HOST bookkeeping (epoch loop, early stopping, index
+    handling) with the reference on CPU tensors, so they opt in to the generic torch loop; the
+    product default is to raise (tests/test_abi_and_host.py)."""
+    monkeypatch.setenv("GLNN_ALLOW_TORCH_FALLBACK", "1")
+
+
 @pytest.fixture(scope="module")
 def ref_modules(ref_utils):
     """The reference's models.py / train_and_eval.py, imported unmodified over the DGL shim."""
