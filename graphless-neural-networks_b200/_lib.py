@@ -123,6 +123,11 @@ SIGNATURES = {
                                         c_vp]),
     "glnn_block_mark": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
     "glnn_block_relabel": (C.c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "glnn_csr_build_workspace_bytes": (C.c_size_t, [c_i64, c_i64]),
+    "glnn_csr_from_coo": (C.c_int, [c_vp, c_vp, C.c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                    C.c_size_t, c_vp]),
+    "glnn_csr_subgraph": (C.c_int, [c_vp, C.c_int, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                    C.c_size_t, c_vp]),
     "glnn_sage_inference_host": (C.c_int, [c_vp, c_vp, c_i64, c_vp, C.POINTER(SageLayerHost),
                                            C.c_int, c_f32, c_vp]),
 }

@@ -18,12 +18,20 @@ class CSRGraph:
     # -- construction -----------------------------------------------------------------------
     @staticmethod
     def from_edges(src, dst, num_nodes=None, device=None):
-        """Builds the CSR with a stable sort by destination (on `device` if given: a 124M-edge
-        graph sorts in well under a second on the GPU)."""
-        src = torch.as_tensor(src, dtype=torch.int64, device=device)
-        dst = torch.as_tensor(dst, dtype=torch.int64, device=device)
+        """CSR with the edges of every row in their input order (stable by destination).  On a CUDA
+        device this is glnn_csr_from_coo (csrc/csr_build.cu: degree counts, scan, 8-bit LSD radix
+        passes); edge lists that live on the host are sorted there, as DGL does for the reference."""
+        src = torch.as_tensor(src, device=device)
+        dst = torch.as_tensor(dst, device=device)
+        if src.dtype != torch.int32 or dst.dtype != torch.int32:
+            src, dst = src.to(torch.int64), dst.to(torch.int64)
         if num_nodes is None:
             num_nodes = int(max(src.max(), dst.max())) + 1 if src.numel() else 0
+        if src.is_cuda:
+            from . import ops
+            indptr, indices, out_deg = ops.csr_from_coo(src, dst, num_nodes)
+            return CSRGraph(indptr, indices, num_nodes, out_deg)
+        src, dst = src.to(torch.int64), dst.to(torch.int64)
         order = torch.sort(dst, stable=True).indices
         indices = src[order].to(torch.int32)
         counts = torch.bincount(dst, minlength=num_nodes)
@@ -80,14 +88,23 @@ class CSRGraph:
 
     def subgraph(self, nodes):
         """Node-induced subgraph with nodes relabelled in the given order (dgl.DGLGraph.subgraph;
-        used by the inductive split, train_and_eval.py:324)."""
+        used by the inductive split, train_and_eval.py:324).  The new destination is a function of
+        the old one, so on the device no sort is needed: glnn_csr_subgraph compacts every kept row
+        in place order."""
         nodes = torch.as_tensor(nodes, dtype=torch.int64, device=self.device)
-        relabel = torch.full((self._n,), -1, dtype=torch.int64, device=self.device)
-        relabel[nodes] = torch.arange(nodes.numel(), device=self.device)
-        src, dst = self.edges()
-        s, d = relabel[src], relabel[dst]
-        keep = (s >= 0) & (d >= 0)
-        g = CSRGraph.from_edges(s[keep], d[keep], nodes.numel())
+        if self.indices.is_cuda:
+            from . import ops
+            relabel = torch.full((self._n,), -1, dtype=torch.int32, device=self.device)
+            relabel[nodes] = torch.arange(nodes.numel(), dtype=torch.int32, device=self.device)
+            indptr, indices, out_deg = ops.csr_subgraph(self.indptr, self.indices, relabel, nodes.numel())
+            g = CSRGraph(indptr, indices, nodes.numel(), out_deg)
+        else:
+            relabel = torch.full((self._n,), -1, dtype=torch.int64, device=self.device)
+            relabel[nodes] = torch.arange(nodes.numel(), device=self.device)
+            src, dst = self.edges()
+            s, d = relabel[src], relabel[dst]
+            keep = (s >= 0) & (d >= 0)
+            g = CSRGraph.from_edges(s[keep], d[keep], nodes.numel())
         g.ndata = {k: v[nodes] for k, v in self.ndata.items()}
         return g
 

@@ -247,6 +247,56 @@ def block_relabel(src, node_map):
     return src
 
 
+def csr_from_coo(src, dst, num_nodes, want_out_deg=True):
+    """glnn_csr_from_coo: CUDA edge list (int64 or int32) -> (indptr int32 [n+1], indices int32 [E],
+    out_deg int64 [n] | None), stable by destination.  Raises ValueError for ids outside [0, n)."""
+    lib = _lib.load()
+    require_cuda(src, dst)
+    if src.dtype != dst.dtype or src.dtype not in (torch.int64, torch.int32):
+        raise ValueError("src / dst must both be int64 or both int32")
+    if src.dim() != 1 or src.shape != dst.shape:
+        raise ValueError("src / dst must be 1-d arrays of the same length")
+    src, dst = src.contiguous(), dst.contiguous()
+    n, e, dev = int(num_nodes), src.numel(), src.device
+    indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+    indices = torch.empty(e, dtype=torch.int32, device=dev)
+    out_deg = torch.empty(n, dtype=torch.int64, device=dev) if want_out_deg else None
+    status = torch.empty(1, dtype=torch.int32, device=dev)
+    ws_bytes = int(lib.glnn_csr_build_workspace_bytes(n, e))
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 256
+    check(lib.glnn_csr_from_coo(ptr(src), ptr(dst), int(src.dtype == torch.int64), e, n, ptr(indptr),
+                                ptr(indices), ptr(out_deg) if want_out_deg else None, ptr(status),
+                                ws.data_ptr() + off, ws_bytes, stream()), "glnn_csr_from_coo")
+    bad = int(status.item())
+    if bad:
+        raise ValueError(f"csr_from_coo: {bad} edges have a node id outside [0, {n})")
+    return indptr, indices, out_deg
+
+
+def csr_subgraph(indptr, indices, relabel, n_new):
+    """glnn_csr_subgraph: (new_indptr int32 [n_new+1], new_indices int32, new_out_deg int64 [n_new]) of
+    the node-induced subgraph; relabel int32 [n] holds the new id of every kept node, -1 elsewhere."""
+    lib = _lib.load()
+    require_cuda(indptr, indices, relabel)
+    if relabel.dtype != torch.int32 or indices.dtype != torch.int32:
+        raise ValueError("relabel / indices must be int32")
+    n, n_new, dev = relabel.numel(), int(n_new), relabel.device
+    i64 = int(indptr.dtype == torch.int64)
+    new_ptr = torch.empty(n_new + 1, dtype=torch.int32, device=dev)
+    ws_bytes = 12 * (n_new + 1) + 1024
+    ws = torch.empty(ws_bytes + 256, dtype=torch.uint8, device=dev)
+    wp = ws.data_ptr() + (-ws.data_ptr()) % 256
+    check(lib.glnn_csr_subgraph(ptr(indptr), i64, ptr(indices), n, ptr(relabel), n_new, ptr(new_ptr), None,
+                                None, wp, ws_bytes, stream()), "glnn_csr_subgraph")
+    total = int(new_ptr[-1].item()) if n_new else 0
+    new_idx = torch.empty(total, dtype=torch.int32, device=dev)
+    out_deg = torch.empty(n_new, dtype=torch.int64, device=dev)
+    check(lib.glnn_csr_subgraph(ptr(indptr), i64, ptr(indices), n, ptr(relabel), n_new, ptr(new_ptr),
+                                ptr(new_idx), ptr(out_deg), wp, ws_bytes, stream()), "glnn_csr_subgraph")
+    return new_ptr, new_idx, out_deg
+
+
 class Planes:
     """fp32 matrix kept as bf16 hi / lo planes (see include/glnn_b200.h): .hi/.lo int16 tensors
     [rows, ldp], logical width .cols."""

@@ -23,15 +23,12 @@ from .graph import CSRGraph
 
 
 def _transpose_csr(indptr, indices, n_src):
-    """CSR over sources of the same edge set (drives the backward aggregation of a fixed graph)."""
+    """CSR over sources of the same edge set (drives the backward aggregation of a fixed graph):
+    the edge list in CSR order, re-sorted by source on the device (glnn_csr_from_coo, stable)."""
     n_dst = indptr.numel() - 1
     deg = (indptr[1:] - indptr[:-1]).to(torch.int64)
-    dst = torch.repeat_interleave(torch.arange(n_dst, device=indices.device), deg)
-    src = indices.to(torch.int64)
-    order = torch.sort(src, stable=True).indices
-    t_indices = dst[order].to(torch.int32)
-    t_indptr = torch.zeros(n_src + 1, dtype=torch.int64, device=indices.device)
-    torch.cumsum(torch.bincount(src, minlength=n_src), 0, out=t_indptr[1:])
+    dst = torch.repeat_interleave(torch.arange(n_dst, device=indices.device, dtype=torch.int32), deg)
+    t_indptr, t_indices, _ = ops.csr_from_coo(dst, indices, n_src, want_out_deg=False)
     return t_indptr.to(indptr.dtype), t_indices
 
 

@@ -473,6 +473,30 @@ GLNN_API int glnn_sample_neighbors(const void* indptr, int indptr64, const int32
 GLNN_API int glnn_block_mark(const int32_t* src, int64_t total, uint8_t* flag, glnn_stream_t stream);
 GLNN_API int glnn_block_relabel(int32_t* src, int64_t total, const int32_t* map, glnn_stream_t stream);
 
+/* Graph construction on the device (what DGL does on the host for dgl.graph((src, dst)) /
+ * g.create_formats_(), dataloader.py:78,105 and train_and_eval.py:178, and for g.subgraph(idx_obs),
+ * train_and_eval.py:324).
+ * glnn_csr_from_coo: edge list -> CSR over destinations, int32, STABLE (the edges of a row keep their
+ * input order; multi-edges kept): degree counts + exclusive scan + a least-significant-digit radix
+ * sort of (dst, src) pairs, 8 bits per pass.  src / dst are int64 (idx64 = 1) or int32 device arrays;
+ * indptr [n_nodes + 1]; indices [n_edges]; out_deg [n_nodes] int64 or NULL.  *status (device int32)
+ * receives the number of edges with an id outside [0, n_nodes) -- the caller must treat non-zero as an
+ * error (such edges are stored as 0 -> 0 to keep the kernels in bounds).  Fewer than 2^31 edges.
+ * glnn_csr_subgraph: node-induced subgraph; relabel[v] = new id of old node v or -1.  Row
+ * relabel[v] of the result holds the relabelled kept sources of old row v in their old order.
+ * new_indptr [n_new + 1]; with new_indices == NULL and new_out_deg == NULL only new_indptr is computed
+ * (read new_indptr[n_new], allocate, call again); new_out_deg [n_new] int64 or NULL.
+ * Workspaces: 256-byte aligned device memory; glnn_csr_build_workspace_bytes(n_nodes, n_edges) for
+ * from_coo, 12 * (n_new + 1) + 1024 bytes suffice for subgraph. */
+GLNN_API size_t glnn_csr_build_workspace_bytes(int64_t n_nodes, int64_t n_edges);
+GLNN_API int glnn_csr_from_coo(const void* src, const void* dst, int idx64, int64_t n_edges,
+                               int64_t n_nodes, int32_t* indptr, int32_t* indices, int64_t* out_deg,
+                               int32_t* status, void* workspace, size_t ws_bytes, glnn_stream_t stream);
+GLNN_API int glnn_csr_subgraph(const void* indptr, int indptr64, const int32_t* indices, int64_t n_nodes,
+                               const int32_t* relabel, int64_t n_new, int32_t* new_indptr,
+                               int32_t* new_indices, int64_t* new_out_deg, void* workspace,
+                               size_t ws_bytes, glnn_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Host-buffer entry point (what an out-of-process / non-torch caller binds; used for the e2e
  * benchmark leg).  SAGE("gcn") eval forward = SAGE.inference + log_softmax: copies the CSR graph,
