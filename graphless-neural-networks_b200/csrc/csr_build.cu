@@ -15,6 +15,7 @@
 //                       function of the old one, so no sort is needed: a warp per old row counts,
 //                       then compacts, its kept sources in order (ballot ranks).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -22,8 +23,9 @@ namespace glnn {
 namespace csrb {
 
 constexpr int kThreads = 256;
-constexpr int kItems = 8;
-constexpr int kTile = kThreads * kItems;  // 2048 items per radix tile
+// items per thread of a radix tile (tile = 256 threads x items): a template parameter, chosen per call
+// (GLNN_CSR_ITEMS = 4 | 8 | 16, default 8 -> 2048-item tiles)
+constexpr int kMinItems = 4;
 constexpr int kScanItems = 16;
 constexpr int kScanTile = kThreads * kScanItems;  // 4096 elements per scan block
 constexpr unsigned kFull = 0xffffffffu;
@@ -162,14 +164,15 @@ __global__ void widen_kernel(const int32_t* __restrict__ in, int64_t n, int64_t*
   if (i < n) out[i] = in[i];
 }
 
-// digit histogram of one 2048-item tile, stored digit-major: hist[digit * nb + tile]
+// digit histogram of one tile, stored digit-major: hist[digit * nb + tile]
+template <int kItems>
 __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const int32_t* __restrict__ key, int64_t E,
                                                               int shift, int32_t* __restrict__ hist,
                                                               int64_t nb) {
   __shared__ int h[256];
   h[threadIdx.x] = 0;
   __syncthreads();
-  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile;
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * (kThreads * kItems);
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
     const int64_t j = base + i * kThreads + threadIdx.x;
@@ -179,11 +182,12 @@ __global__ void __launch_bounds__(kThreads) radix_hist_kernel(const int32_t* __r
   hist[static_cast<int64_t>(threadIdx.x) * nb + blockIdx.x] = h[threadIdx.x];
 }
 
-// Stable scatter of one tile.  Item order inside the tile: warp w owns the 256 consecutive items
-// [w * 256, (w + 1) * 256), iteration i covers 32 consecutive ones, lane = position.  Rank of an item
+// Stable scatter of one tile.  Item order inside the tile: warp w owns 32 * kItems consecutive items,
+// iteration i covers 32 consecutive ones, lane = position.  Rank of an item
 // among the tile's items with the same digit = (count in earlier warps) + (count in this warp's earlier
 // iterations) + (lower lanes of its match group).  goff = exclusive scan of hist (digit-major), i.e.
 // the first output slot of (digit, tile).  out_key == nullptr on the last pass.
+template <int kItems, bool HW_MATCH>
 __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(
     const int32_t* __restrict__ key, const int32_t* __restrict__ val, int64_t E, int shift,
     const int32_t* __restrict__ goff, int64_t nb, int32_t* __restrict__ out_key,
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(
 #pragma unroll
   for (int w = 0; w < kThreads / 32; ++w) cnt[w][threadIdx.x] = 0;
   __syncthreads();
-  const int64_t base = static_cast<int64_t>(blockIdx.x) * kTile + warp * (32 * kItems);
+  const int64_t base = static_cast<int64_t>(blockIdx.x) * (kThreads * kItems) + warp * (32 * kItems);
   int k[kItems], v[kItems], rank[kItems];
 #pragma unroll
   for (int i = 0; i < kItems; ++i) {
@@ -202,7 +206,22 @@ __global__ void __launch_bounds__(kThreads) radix_scatter_kernel(
     k[i] = valid ? key[j] : 0;
     v[i] = valid ? val[j] : 0;
     const unsigned d = valid ? static_cast<unsigned>((k[i] >> shift) & 255) : 0xffffffffu;
-    const unsigned grp = __match_any_sync(kFull, d);
+    unsigned grp;  // lanes holding the same digit (invalid lanes form their own group)
+    if constexpr (HW_MATCH) {
+      grp = __match_any_sync(kFull, d);
+    } else {
+      // eight ballots, one per digit bit, refine the peer mask; the MATCH instruction serialises over
+      // the ~28 distinct digits of a warp in the MIO pipe (ncu: mio_throttle + short_scoreboard were
+      // the top stalls of this kernel), votes do not
+      grp = __ballot_sync(kFull, valid);
+      if (!valid) grp = ~grp;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned m = __ballot_sync(kFull, bit);
+        grp &= bit ? m : ~m;
+      }
+    }
     const unsigned lower = grp & ((1u << lane) - 1u);
     int old = 0;
     if (valid && lower == 0) {  // lowest lane of the group advances the warp's counter
@@ -248,9 +267,20 @@ struct Workspace {
 
 static size_t up256(size_t b) { return (b + 255) & ~static_cast<size_t>(255); }
 
+static int items_per_thread() {
+  static const int items = []() {
+    const char* e = getenv("GLNN_CSR_ITEMS");
+    const int v = e ? atoi(e) : 8;
+    return (v == 4 || v == 16) ? v : 8;
+  }();
+  return items;
+}
+
+// sized for the smallest tile, so that every tile choice fits
 static Workspace carve(void* base, int64_t N, int64_t E) {
   Workspace w;
-  const int64_t nb = (E + kTile - 1) / kTile;
+  const int64_t min_tile = kThreads * kMinItems;
+  const int64_t nb = (E + min_tile - 1) / min_tile;
   const int64_t scan_n = std::max<int64_t>(256 * nb, N + 1);
   uint8_t* p = static_cast<uint8_t*>(base);
   size_t off = 0;
@@ -337,7 +367,7 @@ extern "C" int glnn_csr_from_coo(const void* src, const void* dst, int idx64, in
   using namespace glnn::csrb;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GLNN_REQUIRE(n_nodes >= 0 && n_edges >= 0, GLNN_ERR_ARG, "csr_from_coo: negative size");
-  GLNN_REQUIRE(n_edges < (1LL << 31) - kTile && n_nodes < (1LL << 31) - 1, GLNN_ERR_SHAPE,
+  GLNN_REQUIRE(n_edges < (1LL << 31) - 4096 && n_nodes < (1LL << 31) - 1, GLNN_ERR_SHAPE,
                "csr_from_coo: int32 CSR needs fewer than 2^31 edges and nodes");
   GLNN_REQUIRE(indptr && status, GLNN_ERR_ARG, "csr_from_coo: null output");
   GLNN_REQUIRE(n_edges == 0 || n_nodes > 0, GLNN_ERR_SHAPE, "csr_from_coo: edges without nodes");
@@ -354,7 +384,10 @@ extern "C" int glnn_csr_from_coo(const void* src, const void* dst, int idx64, in
   GLNN_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, GLNN_ERR_ALIGN,
                "csr_from_coo: workspace must be 256-byte aligned");
   const int passes = radix_passes(n_nodes);
-  const int64_t nb = (n_edges + kTile - 1) / kTile;
+  const int items = items_per_thread();
+  static const bool hw_match = getenv("GLNN_CSR_MATCH") != nullptr && atoi(getenv("GLNN_CSR_MATCH")) == 1;
+  const int64_t tile = static_cast<int64_t>(kThreads) * items;
+  const int64_t nb = (n_edges + tile - 1) / tile;
   // payload ping-pong between the workspace buffer X and the output `indices` (Y), arranged so that
   // the last pass writes Y: an odd number of passes starts in X, an even number in Y
   int32_t* val_cur = (passes & 1) ? w.val_x : indices;
@@ -384,12 +417,26 @@ extern "C" int glnn_csr_from_coo(const void* src, const void* dst, int idx64, in
   for (int p = 0; p < passes; ++p) {
     const int shift = 8 * p;
     const bool last = p == passes - 1;
-    radix_hist_kernel<<<static_cast<unsigned>(nb), kThreads, 0, st>>>(key_cur, n_edges, shift, w.hist, nb);
+    const unsigned grid = static_cast<unsigned>(nb);
+    if (items == 4) radix_hist_kernel<4><<<grid, kThreads, 0, st>>>(key_cur, n_edges, shift, w.hist, nb);
+    else if (items == 16) radix_hist_kernel<16><<<grid, kThreads, 0, st>>>(key_cur, n_edges, shift, w.hist, nb);
+    else radix_hist_kernel<8><<<grid, kThreads, 0, st>>>(key_cur, n_edges, shift, w.hist, nb);
     GLNN_LAUNCH_OK("radix_hist_kernel");
     rc = exclusive_scan(w.hist, w.hist, 256 * nb, w.bsum, st);
     if (rc != 0) return rc;
-    radix_scatter_kernel<<<static_cast<unsigned>(nb), kThreads, 0, st>>>(
-        key_cur, val_cur, n_edges, shift, w.hist, nb, last ? nullptr : key_nxt, val_nxt);
+    int32_t* ok = last ? nullptr : key_nxt;
+#define GLNN_SCATTER(IT, HW) \
+  radix_scatter_kernel<IT, HW><<<grid, kThreads, 0, st>>>(key_cur, val_cur, n_edges, shift, w.hist, nb, ok, val_nxt)
+    if (hw_match) {
+      if (items == 4) GLNN_SCATTER(4, true);
+      else if (items == 16) GLNN_SCATTER(16, true);
+      else GLNN_SCATTER(8, true);
+    } else {
+      if (items == 4) GLNN_SCATTER(4, false);
+      else if (items == 16) GLNN_SCATTER(16, false);
+      else GLNN_SCATTER(8, false);
+    }
+#undef GLNN_SCATTER
     GLNN_LAUNCH_OK("radix_scatter_kernel");
     std::swap(key_cur, key_nxt);
     std::swap(val_cur, val_nxt);

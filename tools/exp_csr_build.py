@@ -15,6 +15,10 @@ from glnn_b200.graph import CSRGraph
 from glnn_b200.workloads import SHAPES, synthetic_edges
 
 dev = torch.device("cuda:0")
+# --tile-sweep: only the products-sized glnn_csr_from_coo, for the radix tile chosen by GLNN_CSR_ITEMS
+#               (one process per value: the library reads it once), with and without out-degrees
+# --once:       one products-sized call and nothing else (for an ncu launch list / --set full capture)
+MODE = sys.argv[1] if len(sys.argv) > 1 else ""
 
 
 def ms(fn, iters=5):
@@ -37,6 +41,23 @@ def library_route(src, dst, n):
     torch.cumsum(torch.bincount(dst, minlength=n), 0, out=indptr[1:])
     return indptr.to(torch.int32), indices, torch.bincount(src, minlength=n)
 
+
+if MODE in ("--tile-sweep", "--once"):
+    s = SHAPES["ogbn-products"]
+    n = s["n"]
+    src, dst = synthetic_edges(n, s["e_raw"], True, s["self_loops"], dev, 0)
+    if MODE == "--once":
+        ops.csr_from_coo(src, dst, n)
+        torch.cuda.synchronize()
+        sys.exit(0)
+    ref = library_route(src, dst, n)
+    for want in (True, False):
+        got = ops.csr_from_coo(src, dst, n, want_out_deg=want)
+        same = torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]) and (not want or torch.equal(got[2], ref[2]))
+        t = ms(lambda: ops.csr_from_coo(src, dst, n, want_out_deg=want))
+        print(json.dumps({"exp": "csr_from_coo tile sweep", "items_per_thread": os.environ.get("GLNN_CSR_ITEMS", "8"),
+                          "out_degrees": want, "identical": same, "ms": round(t, 3)}), flush=True)
+    sys.exit(0)
 
 for name in ("ogbn-arxiv", "ogbn-products"):
     s = SHAPES[name]
